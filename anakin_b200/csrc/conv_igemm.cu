@@ -1,0 +1,749 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the reference's NV conv family: SaberConv2D / SaberConvEltwise /
+// SaberGemmLikeConv / SaberDirectConv / SaberWinogradConv dispatchers
+// (reference saber/funcs/impl/cuda/saber_conv.cpp:17-585,
+//  saber_conv_eltwise.cpp:32-318, saber_conv_gemmlike.cpp:38-168,
+//  saber_conv_direct.cpp:40-220) and the closed SASS kernels behind them
+// (third-party/sass/include/sass_funcs.h:54-935).
+//
+// GEMM view:  D[M x N] = A[M x Kg] * B[N x Kg]^T
+//   M  = n*ho*wo output pixels (NHWC rows), N = output channels,
+//   Kg = r*s*c, ordered (r, s, c) with c innermost.
+// A is never materialised: one TMA *im2col* load fetches, for a filter tap
+// (r,s) and a channel chunk, the [128 pixels x chunk bytes] operand tile straight
+// from the NHWC activation tensor into swizzled shared memory (zero-filling the
+// padding halo).  B (packed weights) arrives through a tiled TMA load.  A single
+// elected thread issues tcgen05.mma with the accumulator in TMEM; four epilogue
+// warps read it back with tcgen05.ld and apply bias / per-channel scale /
+// residual / relu / requantise in registers before the vectorised store.
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM owner + MMA
+// issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/b200_saber.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int BLOCK_M = 128;
+constexpr int STAGE_K_BYTES = 128;  // K bytes per pipeline stage (4 MMAs of 32 B)
+constexpr int A_STAGE_BYTES = BLOCK_M * STAGE_K_BYTES;
+
+struct ConvKParams {
+    int32_t M_total, HoWo, Wo;
+    int32_t pad_h, pad_w, stride_h, stride_w, dil_h, dil_w;
+    int32_t R, S;
+    int32_t CC;        // channel chunks per filter tap
+    int32_t chunk;     // bytes per chunk (16|32|64|128)
+    int32_t chunk_el;  // elements per chunk
+    int32_t KS;        // k-steps issued (KS_real rounded up to even when chunk==16)
+    int32_t KS_real;   // R*S*CC
+    int32_t K;         // output channels
+    int32_t ldc;       // output / residual row pitch (elements)
+    int32_t relu;
+    float neg_slope;
+    float sum_scale;
+    int32_t out_dtype, res_dtype;
+    const float* bias;
+    const float* scale;
+    const void* res;
+    void* out;
+};
+
+template <int BN>
+struct SmemPlan {
+    static constexpr int B_STAGE_BYTES = BN * STAGE_K_BYTES;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BN >= 256) ? 4 : (BN == 128 ? 3 : 4);
+    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    // + barriers (full[STAGES], empty[STAGES], tmem_full) + tmem ptr, + 1024 alignment slack
+    static constexpr int TOTAL = TILE_BYTES + 256 + 1024;
+    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+__device__ __forceinline__ uint32_t layout_type_for_chunk(int chunk) {
+    return chunk == 128 ? 2u : (chunk == 64 ? 4u : (chunk == 32 ? 6u : 0u));
+}
+
+// ----------------------------------------------------------------- epilogue helpers
+__device__ __forceinline__ int32_t sat_s8(float f) {
+    // cvt.rni.sat.s8.f32 == round-to-nearest-even + saturate (vcvtps2dq RN + vpmovsdb)
+    int32_t r;
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return r;
+}
+__device__ __forceinline__ int32_t sat_u8(float f) {
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return static_cast<int32_t>(r);
+}
+
+template <int KIND>
+__device__ __forceinline__ void epilogue_chunk16(const ConvKParams& p, const uint32_t (&v)[16],
+                                                 int64_t row, int ch0, int nvalid) {
+    float f[16];
+    const int64_t off = row * static_cast<int64_t>(p.ldc) + ch0;
+    if constexpr (KIND == KIND_I8) {
+        // x86 Saber int8 epilogue: (acc + bias) * scale, [relu], [+ res*sum_scale], [relu], rne+sat
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int ch = ch0 + i;
+            const bool ok = i < nvalid;
+            const float b = (p.bias != nullptr && ok) ? __ldg(p.bias + ch) : 0.f;
+            const float s = (p.scale != nullptr && ok) ? __ldg(p.scale + ch) : 1.f;
+            float x = __fadd_rn(__int2float_rn(static_cast<int32_t>(v[i])), b);
+            f[i] = __fmul_rn(x, s);
+        }
+        const bool has_res = (p.res_dtype >= 0) && (p.res != nullptr);
+        if (p.relu && !has_res) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (has_res) {
+            float r[16];
+            if (p.res_dtype == B200_FLOAT) {
+                const float* rp = reinterpret_cast<const float*>(p.res) + off;
+                if (nvalid == 16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 t = __ldg(reinterpret_cast<const float4*>(rp) + q);
+                        r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = i < nvalid ? __ldg(rp + i) : 0.f;
+                }
+            } else {
+                const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + off;
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (nvalid == 16) {
+                    uint4 t = __ldg(reinterpret_cast<const uint4*>(rp));
+                    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+                } else {
+                    for (int i = 0; i < nvalid; ++i)
+                        w[i >> 2] |= static_cast<uint32_t>(__ldg(rp + i)) << (8 * (i & 3));
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                    r[i] = (p.res_dtype == B200_INT8)
+                               ? static_cast<float>(static_cast<int8_t>(byte))
+                               : static_cast<float>(byte);
+                }
+            }
+            if (p.sum_scale == 1.f) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = __fadd_rn(f[i], r[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = __fmaf_rn(r[i], p.sum_scale, f[i]);
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+        }
+    } else {
+        // float epilogue: acc (+ beta*res) + bias, relu(neg_slope)
+        const bool has_res = (p.res_dtype >= 0) && (p.res != nullptr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (has_res) {
+            if (p.res_dtype == B200_FLOAT) {
+                const float* rp = reinterpret_cast<const float*>(p.res) + off;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (i < nvalid) f[i] = __fmaf_rn(p.sum_scale, __ldg(rp + i), f[i]);
+            } else {
+                const __half* rp = reinterpret_cast<const __half*>(p.res) + off;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (i < nvalid) f[i] = __fmaf_rn(p.sum_scale, __half2float(rp[i]), f[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float b = (p.bias != nullptr && i < nvalid) ? __ldg(p.bias + ch0 + i) : 0.f;
+            float x = __fadd_rn(f[i], b);
+            if (p.relu) x = x > 0.f ? x : __fmul_rn(x, p.neg_slope);
+            f[i] = x;
+        }
+    }
+
+    // ---- store
+    if (p.out_dtype == B200_FLOAT) {
+        float* op = reinterpret_cast<float*>(p.out) + off;
+        if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                reinterpret_cast<float4*>(op)[q] =
+                    make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else {
+            for (int i = 0; i < nvalid; ++i) op[i] = f[i];
+        }
+    } else if (p.out_dtype == B200_HALF) {
+        __half* op = reinterpret_cast<__half*>(p.out) + off;
+        if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+                w[q] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+            for (int i = 0; i < nvalid; ++i) op[i] = __float2half_rn(f[i]);
+        }
+    } else {
+        uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off;
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int32_t q = (p.out_dtype == B200_INT8) ? sat_s8(f[i]) : sat_u8(f[i]);
+            w[i >> 2] |= (static_cast<uint32_t>(q) & 0xffu) << (8 * (i & 3));
+        }
+        if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int i = 0; i < nvalid; ++i)
+                op[i] = static_cast<uint8_t>((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+        }
+    }
+}
+
+// ----------------------------------------------------------------- the kernel
+template <int KIND, int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                  const __grid_constant__ CUtensorMap map_b, const ConvKParams p,
+                  const uint32_t idesc) {
+    using SP = SmemPlan<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SP::TILE_BYTES);
+    uint64_t* empty_bar = full_bar + SP::STAGES;
+    uint64_t* tmem_full_bar = empty_bar + SP::STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int subs_per_stage = STAGE_K_BYTES / p.chunk;
+    const int num_stage_iters = (p.KS + subs_per_stage - 1) / subs_per_stage;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int i = 0; i < SP::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp_idx == 1) {
+        tmem_alloc<SP::TMEM_COLS>(tmem_ptr_smem);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // PDL: everything above overlapped the previous kernel's tail; its outputs
+    // (our activations / residual) are only touched below this point.
+    pdl_wait_prior_grid();
+
+    const int m0 = blockIdx.x * BLOCK_M;
+    const int n0 = blockIdx.y * BN;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            const int n_img = m0 / p.HoWo;
+            const int rem = m0 - n_img * p.HoWo;
+            const int p0 = rem / p.Wo;
+            const int q0 = rem - p0 * p.Wo;
+            const int base_w = q0 * p.stride_w - p.pad_w;
+            const int base_h = p0 * p.stride_h - p.pad_h;
+            const uint32_t a_sub_bytes = BLOCK_M * p.chunk;
+            const uint32_t b_sub_bytes = BN * p.chunk;
+            int ks = 0, r = 0, s = 0, cc = 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < num_stage_iters; ++it) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int nsub = min(subs_per_stage, p.KS - ks);
+                mbar_arrive_expect_tx(&full_bar[stage], nsub * (a_sub_bytes + b_sub_bytes));
+                uint8_t* a_dst = smem + stage * SP::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + A_STAGE_BYTES;
+                for (int j = 0; j < nsub; ++j) {
+                    // the padding k-step (ks == KS_real) re-reads tap (0,0); its weights are zero
+                    const bool pad_step = ks >= p.KS_real;
+                    const int rr = pad_step ? 0 : r, ss = pad_step ? 0 : s, c_ = pad_step ? 0 : cc;
+                    tma_load_im2col_4d(&map_a, &full_bar[stage], a_dst + j * a_sub_bytes,
+                                       c_ * p.chunk_el, base_w, base_h, n_img,
+                                       static_cast<uint16_t>(ss * p.dil_w),
+                                       static_cast<uint16_t>(rr * p.dil_h));
+                    tma_load_2d(&map_b, &full_bar[stage], b_dst + j * b_sub_bytes,
+                                ks * p.chunk_el, n0);
+                    ++ks;
+                    if (++cc == p.CC) {
+                        cc = 0;
+                        if (++s == p.S) { s = 0; ++r; }
+                    }
+                }
+                if (++stage == SP::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t lt = layout_type_for_chunk(p.chunk);
+            const uint32_t a_sub_bytes = BLOCK_M * p.chunk;
+            const uint32_t b_sub_bytes = BN * p.chunk;
+            int ks = 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t accum = 0;
+            for (int it = 0; it < num_stage_iters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const int nsub = min(subs_per_stage, p.KS - ks);
+                const uint32_t a_base = smem_u32(smem + stage * SP::STAGE_BYTES);
+                const uint32_t b_base = a_base + A_STAGE_BYTES;
+                if (p.chunk >= 32) {
+                    const uint32_t sbo = 8u * p.chunk;
+                    const int mma_per_sub = p.chunk >> 5;
+                    for (int j = 0; j < nsub; ++j) {
+                        for (int q = 0; q < mma_per_sub; ++q) {
+                            const uint64_t ad =
+                                make_smem_desc(a_base + j * a_sub_bytes + q * 32, 16, sbo, lt);
+                            const uint64_t bd =
+                                make_smem_desc(b_base + j * b_sub_bytes + q * 32, 16, sbo, lt);
+                            tc_mma<KIND>(tmem_base, ad, bd, idesc, accum);
+                            accum = 1;
+                        }
+                    }
+                } else {
+                    // 16-byte chunks: one K=32B MMA spans two sub-tiles (no-swizzle, LBO = sub-tile)
+                    for (int j = 0; j < nsub; j += 2) {
+                        const uint64_t ad =
+                            make_smem_desc(a_base + j * a_sub_bytes, a_sub_bytes, 128, 0);
+                        const uint64_t bd =
+                            make_smem_desc(b_base + j * b_sub_bytes, b_sub_bytes, 128, 0);
+                        tc_mma<KIND>(tmem_base, ad, bd, idesc, accum);
+                        accum = 1;
+                    }
+                }
+                ks += nsub;
+                tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+                if (++stage == SP::STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp_idx & 3;
+        const int64_t row = static_cast<int64_t>(m0) + quarter * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const bool row_ok = row < p.M_total;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            if (n0 + c0 >= p.K) break;  // warp-uniform
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            if (row_ok) {
+                const int nvalid = min(16, p.K - (n0 + c0));
+                epilogue_chunk16<KIND>(p, v, row, n0 + c0, nvalid);
+            }
+        }
+        tc_fence_before();
+    }
+
+    pdl_launch_dependents();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<SP::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                     cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled g_encode_tiled = nullptr;
+static PFN_encodeIm2col g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+static std::once_flag g_driver_once;
+
+static void load_driver_entry_points() {
+    std::call_once(g_driver_once, [] {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_encode_im2col = reinterpret_cast<PFN_encodeIm2col>(fn);
+        cudaDriverGetVersion(&g_driver_version);
+        (void)cudaGetLastError();
+    });
+}
+
+static int elem_size(int math) { return math == B200_MATH_I8 ? 1 : (math == B200_MATH_F16 ? 2 : 4); }
+
+static int dtype_size(int dt) {
+    switch (dt) {
+        case B200_HALF: return 2;
+        case B200_FLOAT: return 4;
+        case B200_INT32: return 4;
+        default: return 1;
+    }
+}
+
+// Largest chunk (bytes) in {128,64,32,16} that divides the per-pixel channel bytes.
+static int pick_chunk(int c_bytes) {
+    if (c_bytes % 128 == 0) return 128;
+    if (c_bytes % 64 == 0) return 64;
+    if (c_bytes % 32 == 0) return 32;
+    if (c_bytes % 16 == 0) return 16;
+    return 0;
+}
+
+struct Geometry {
+    int es, chunk, chunk_el, CC, KS_real, KS, ho, wo;
+    int64_t M_total;
+    bool ok;
+};
+
+static Geometry make_geometry(const b200_conv_desc_t* d) {
+    Geometry g{};
+    g.es = elem_size(d->math);
+    g.chunk = pick_chunk(d->c * g.es);
+    g.ok = g.chunk != 0 && d->n > 0 && d->h > 0 && d->w > 0 && d->k > 0 && d->r > 0 && d->s > 0 &&
+           d->stride_h > 0 && d->stride_w > 0 && d->dil_h > 0 && d->dil_w > 0;
+    if (!g.ok) return g;
+    g.chunk_el = g.chunk / g.es;
+    g.CC = d->c * g.es / g.chunk;
+    g.KS_real = d->r * d->s * g.CC;
+    g.KS = (g.chunk == 16) ? ((g.KS_real + 1) & ~1) : g.KS_real;
+    g.ho = (d->h + 2 * d->pad_h - (d->dil_h * (d->r - 1) + 1)) / d->stride_h + 1;
+    g.wo = (d->w + 2 * d->pad_w - (d->dil_w * (d->s - 1) + 1)) / d->stride_w + 1;
+    g.M_total = static_cast<int64_t>(d->n) * g.ho * g.wo;
+    g.ok = g.ho > 0 && g.wo > 0 && g.M_total < (1ll << 31);
+    return g;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_conv_plan {
+    b200_conv_desc_t desc;
+    Geometry g;
+    int bn;
+    dim3 grid;
+    int smem_bytes;
+    uint32_t idesc;
+    ConvKParams kp;
+    const void* weights;
+    CUtensorMap map_b;
+    CUtensorMap map_a;
+    const void* map_a_ptr;  // activation pointer map_a was encoded for
+    void (*launch)(b200_conv_plan*, void* stream);
+};
+
+template <int KIND, int BN>
+static void launch_conv(b200_conv_plan* pl, void* stream) {
+    auto kern = conv_igemm_kernel<KIND, BN>;
+    static std::once_flag once;
+    std::call_once(once, [&] {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SmemPlan<BN>::TOTAL);
+    });
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = pl->grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = SmemPlan<BN>::TOTAL;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, pl->map_a, pl->map_b, pl->kp, pl->idesc);
+    count_launch();
+}
+
+template <int KIND>
+static bool select_launch(b200_conv_plan* pl) {
+    switch (pl->bn) {
+        case 32: pl->launch = launch_conv<KIND, 32>; pl->smem_bytes = SmemPlan<32>::TOTAL; return true;
+        case 64: pl->launch = launch_conv<KIND, 64>; pl->smem_bytes = SmemPlan<64>::TOTAL; return true;
+        case 128: pl->launch = launch_conv<KIND, 128>; pl->smem_bytes = SmemPlan<128>::TOTAL; return true;
+        case 256: pl->launch = launch_conv<KIND, 256>; pl->smem_bytes = SmemPlan<256>::TOTAL; return true;
+    }
+    return false;
+}
+
+static CUtensorMapSwizzle swizzle_for_chunk(int chunk) {
+    return chunk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : (chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                       : (chunk == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE));
+}
+static CUtensorMapDataType tma_dtype(int math) {
+    return math == B200_MATH_I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                : (math == B200_MATH_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                         : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
+
+static int encode_map_a(b200_conv_plan* pl, const void* in) {
+    const b200_conv_desc_t& d = pl->desc;
+    const Geometry& g = pl->g;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.c), static_cast<cuuint64_t>(d.w),
+                          static_cast<cuuint64_t>(d.h), static_cast<cuuint64_t>(d.n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.c) * g.es,
+                             static_cast<cuuint64_t>(d.w) * d.c * g.es,
+                             static_cast<cuuint64_t>(d.h) * d.w * d.c * g.es};
+    int lower[2] = {-d.pad_w, -d.pad_h};
+    int upper[2] = {d.pad_w - (d.s - 1) * d.dil_w, d.pad_h - (d.r - 1) * d.dil_h};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride_w),
+                          static_cast<cuuint32_t>(d.stride_h), 1};
+    CUresult r = g_encode_im2col(&pl->map_a, tma_dtype(d.math), 4, const_cast<void*>(in), dims,
+                                 strides, lower, upper, static_cast<cuuint32_t>(g.chunk_el),
+                                 BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle_for_chunk(g.chunk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[b200_saber] cuTensorMapEncodeIm2col failed: %d\n", static_cast<int>(r));
+        return B200_INVALID_VALUE;
+    }
+    // Drivers up to 13.1 mis-encode im2col maps of tensors smaller than 128 KiB; the
+    // documented workaround is to clear bit 21 of the second descriptor qword.
+    const size_t bytes = static_cast<size_t>(d.n) * d.h * d.w * d.c * g.es;
+    if (g_driver_version <= 13010 && bytes < 131072)
+        reinterpret_cast<uint64_t*>(&pl->map_a)[1] &= ~(1ull << 21);
+    pl->map_a_ptr = in;
+    return B200_SUCCESS;
+}
+
+extern "C" {
+
+int b200_conv_out_hw(const b200_conv_desc_t* d, int32_t* ho, int32_t* wo) {
+    if (!d) return B200_INVALID_VALUE;
+    Geometry g = make_geometry(d);
+    if (!g.ok) return B200_INVALID_VALUE;
+    if (ho) *ho = g.ho;
+    if (wo) *wo = g.wo;
+    return B200_SUCCESS;
+}
+
+size_t b200_conv_packed_weight_bytes(const b200_conv_desc_t* d) {
+    if (!d) return 0;
+    Geometry g = make_geometry(d);
+    if (!g.ok) return 0;
+    return static_cast<size_t>(d->k) * g.KS * g.chunk;
+}
+
+int b200_conv_pack_weights(const b200_conv_desc_t* d, const void* src_kcrs, int32_t c_real,
+                           void* dst_packed) {
+    if (!d || !src_kcrs || !dst_packed) return B200_INVALID_VALUE;
+    Geometry g = make_geometry(d);
+    if (!g.ok || c_real > d->c || c_real <= 0) return B200_INVALID_VALUE;
+    const size_t row_bytes = static_cast<size_t>(g.KS) * g.chunk;
+    memset(dst_packed, 0, row_bytes * d->k);
+    const int es = g.es;
+    const uint8_t* src = static_cast<const uint8_t*>(src_kcrs);
+    uint8_t* dst = static_cast<uint8_t*>(dst_packed);
+    const int RS = d->r * d->s;
+    for (int ko = 0; ko < d->k; ++ko) {
+        for (int rs = 0; rs < RS; ++rs) {
+            for (int c = 0; c < c_real; ++c) {
+                const size_t s_off = ((static_cast<size_t>(ko) * c_real + c) * RS + rs) * es;
+                const size_t d_off = ko * row_bytes + (static_cast<size_t>(rs) * d->c + c) * es;
+                memcpy(dst + d_off, src + s_off, es);
+            }
+        }
+    }
+    return B200_SUCCESS;
+}
+
+int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_dev,
+                          const float* bias_dev, const float* scale_dev,
+                          b200_conv_plan_t** plan_out) {
+    if (!d || !packed_weights_dev || !plan_out) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    if (d->math != B200_MATH_I8 && d->math != B200_MATH_F16 && d->math != B200_MATH_TF32)
+        return B200_UNIMPL_ERROR;
+    if (d->fuse_pool != 0) return B200_UNIMPL_ERROR;
+    load_driver_entry_points();
+    if (!g_encode_tiled || !g_encode_im2col) return B200_NOT_INITIALIZED;
+    Geometry g = make_geometry(d);
+    if (!g.ok) return B200_INVALID_VALUE;
+    // operand / epilogue dtype consistency
+    if (d->math == B200_MATH_I8 && !(d->in_dtype == B200_INT8 || d->in_dtype == B200_UINT8))
+        return B200_INVALID_VALUE;
+    if (d->math == B200_MATH_F16 && d->in_dtype != B200_HALF) return B200_INVALID_VALUE;
+    if (d->math == B200_MATH_TF32 && d->in_dtype != B200_FLOAT) return B200_INVALID_VALUE;
+    if (d->ldc < d->k) return B200_INVALID_VALUE;
+    // TMA im2col hardware limits (corner and offset field widths for 2 spatial dims)
+    const int up_w = d->pad_w - (d->s - 1) * d->dil_w, up_h = d->pad_h - (d->r - 1) * d->dil_h;
+    if (d->pad_w > 127 || d->pad_h > 127 || up_w < -128 || up_h < -128 || up_w > 127 || up_h > 127 ||
+        (d->s - 1) * d->dil_w > 254 || (d->r - 1) * d->dil_h > 254 || d->stride_w > 8 || d->stride_h > 8)
+        return B200_UNIMPL_ERROR;
+
+    b200_conv_plan* pl = new (std::nothrow) b200_conv_plan();
+    if (!pl) return B200_MEM_ALLOC_FAILED;
+    pl->desc = *d;
+    pl->g = g;
+    pl->weights = packed_weights_dev;
+    pl->map_a_ptr = nullptr;
+
+    // ---- tile-N heuristic: widest tile that still yields >= ~1 wave of CTAs
+    const int tiles_m = static_cast<int>((g.M_total + BLOCK_M - 1) / BLOCK_M);
+    const int kr32 = (d->k + 31) / 32 * 32;
+    int bn = 32;
+    const int cands[4] = {256, 128, 64, 32};
+    const int sms = sm_count();
+    bool found = false;
+    for (int i = 0; i < 4 && !found; ++i) {
+        if (cands[i] > kr32 && cands[i] != 32) continue;
+        const int ctas = tiles_m * ((d->k + cands[i] - 1) / cands[i]);
+        if (ctas >= sms) { bn = cands[i]; found = true; }
+    }
+    if (!found) {
+        // not enough work for a full wave: take the tile that maximises CTA count but keep
+        // N >= 64 when that costs no parallelism
+        bn = 32;
+        if (kr32 >= 64 && tiles_m * ((d->k + 63) / 64) == tiles_m * ((d->k + 31) / 32)) bn = 64;
+    }
+    pl->bn = bn;
+    pl->grid = dim3(tiles_m, (d->k + bn - 1) / bn, 1);
+
+    bool ok = false;
+    uint32_t a_fmt = 0, b_fmt = 0, c_fmt = 1;
+    if (d->math == B200_MATH_I8) {
+        ok = select_launch<KIND_I8>(pl);
+        a_fmt = (d->in_dtype == B200_INT8) ? 1u : 0u;
+        b_fmt = 1u;
+        c_fmt = 2u;
+    } else if (d->math == B200_MATH_F16) {
+        ok = select_launch<KIND_F16>(pl);
+        a_fmt = b_fmt = 0u;
+    } else {
+        ok = select_launch<KIND_TF32>(pl);
+        a_fmt = b_fmt = 2u;
+    }
+    if (!ok) { delete pl; return B200_UNIMPL_ERROR; }
+    pl->idesc = make_idesc(c_fmt, a_fmt, b_fmt, BLOCK_M, bn);
+
+    // ---- weights tensor map: [k rows][KS*chunk_el] K-major, box {chunk_el, bn}
+    {
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.KS) * g.chunk_el,
+                              static_cast<cuuint64_t>(d->k)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(g.KS) * g.chunk};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(g.chunk_el), static_cast<cuuint32_t>(bn)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode_tiled(&pl->map_b, tma_dtype(d->math), 2,
+                                    const_cast<void*>(packed_weights_dev), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_chunk(g.chunk),
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "[b200_saber] cuTensorMapEncodeTiled(weights) failed: %d\n",
+                    static_cast<int>(r));
+            delete pl;
+            return B200_INVALID_VALUE;
+        }
+    }
+
+    ConvKParams& kp = pl->kp;
+    kp.M_total = static_cast<int32_t>(g.M_total);
+    kp.HoWo = g.ho * g.wo;
+    kp.Wo = g.wo;
+    kp.pad_h = d->pad_h; kp.pad_w = d->pad_w;
+    kp.stride_h = d->stride_h; kp.stride_w = d->stride_w;
+    kp.dil_h = d->dil_h; kp.dil_w = d->dil_w;
+    kp.R = d->r; kp.S = d->s;
+    kp.CC = g.CC; kp.chunk = g.chunk; kp.chunk_el = g.chunk_el;
+    kp.KS = g.KS; kp.KS_real = g.KS_real;
+    kp.K = d->k; kp.ldc = d->ldc;
+    kp.relu = d->relu; kp.neg_slope = d->neg_slope; kp.sum_scale = d->sum_scale;
+    kp.out_dtype = d->out_dtype; kp.res_dtype = d->res_dtype;
+    kp.bias = bias_dev; kp.scale = scale_dev;
+    kp.res = nullptr; kp.out = nullptr;
+    *plan_out = pl;
+    return B200_SUCCESS;
+}
+
+int b200_conv_plan_run(b200_conv_plan_t* pl, const void* in, const void* res, void* out,
+                       void* stream) {
+    if (!pl || !in || !out) return B200_INVALID_VALUE;
+    if (pl->desc.res_dtype >= 0 && !res) return B200_INVALID_VALUE;
+    if (in != pl->map_a_ptr) {
+        int st = encode_map_a(pl, in);
+        if (st != B200_SUCCESS) return st;
+    }
+    pl->kp.res = res;
+    pl->kp.out = out;
+    pl->launch(pl, stream);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[b200_saber] conv launch failed: %s\n", cudaGetErrorString(e));
+        return B200_UNKNOWN_ERROR;
+    }
+    return B200_SUCCESS;
+}
+
+void b200_conv_plan_destroy(b200_conv_plan_t* pl) { delete pl; }
+
+int b200_conv_plan_info(const b200_conv_plan_t* pl, int32_t* block_n, int32_t* grid_x,
+                        int32_t* grid_y, int32_t* k_steps, int32_t* smem_bytes) {
+    if (!pl) return B200_INVALID_VALUE;
+    if (block_n) *block_n = pl->bn;
+    if (grid_x) *grid_x = pl->grid.x;
+    if (grid_y) *grid_y = pl->grid.y;
+    if (k_steps) *k_steps = pl->g.KS;
+    if (smem_bytes) *smem_bytes = pl->smem_bytes;
+    return B200_SUCCESS;
+}
+
+int b200_fc_desc(b200_conv_desc_t* d, int32_t math, int32_t in_dtype, int32_t out_dtype, int32_t m,
+                 int32_t k_in, int32_t n_out) {
+    if (!d) return B200_INVALID_VALUE;
+    memset(d, 0, sizeof(*d));
+    d->math = math; d->in_dtype = in_dtype; d->out_dtype = out_dtype; d->res_dtype = -1;
+    d->n = m; d->h = 1; d->w = 1; d->c = k_in; d->k = n_out; d->ldc = n_out;
+    d->r = d->s = 1; d->stride_h = d->stride_w = 1; d->dil_h = d->dil_w = 1;
+    d->sum_scale = 1.f;
+    return B200_SUCCESS;
+}
+
+}  // extern "C"

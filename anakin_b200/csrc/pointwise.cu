@@ -1,0 +1,696 @@
+// Bandwidth-bound Saber ops on NHWC tensors: pooling, softmax, eltwise, activation,
+// scale and the layout / precision transforms at graph boundaries.  All are 128-bit
+// vectorised, grid sized to the data, judged against the HBM roofline only.
+//
+// Replaces (reference, all under saber/funcs/impl/cuda/base/cuda_c/):
+//   saber_pooling.cu:20-229 + vender_pooling.cpp (cuDNN) -> pool_kernel
+//   saber_softmax.cu:10-430  (one *thread* per row)      -> softmax_rows_kernel (one warp per row)
+//   saber_eltwise.cu:6-360                                -> eltwise_*_kernel
+//   saber_activation.cu:11-420                            -> activation_kernel
+//   saber_scale.cu:8-70                                   -> scale_kernel
+//   calibrate.cu:10-700, reorder.cu                       -> nchw_to_nhwc_kernel / nhwc_to_nchw_kernel
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200_saber.h"
+#include "common.cuh"
+
+namespace b200 {
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+static int check_launch(const char* what) {
+    count_launch();
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[b200_saber] %s launch failed: %s\n", what, cudaGetErrorString(e));
+        return B200_UNKNOWN_ERROR;
+    }
+    return B200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ pooling
+struct PoolP {
+    int n, h, w, c, oh, ow;
+    int wh, ww, ph, pw, sh, sw;
+    int type;
+};
+
+// One thread = one output pixel x 4 fp32 channels.
+// Window logic = reference test/saber/test_saber_pooling.cpp:14-104 (incl. the
+// include-padding divisor rule).
+__global__ void pool_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, PoolP p) {
+    const int cv = p.c >> 2;
+    const long long total = 1ll * p.n * p.oh * p.ow * cv;
+    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
+         idx += 1ll * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int ow = static_cast<int>(t % p.ow); t /= p.ow;
+        const int oh = static_cast<int>(t % p.oh);
+        const int n = static_cast<int>(t / p.oh);
+        int sh = oh * p.sh, eh = sh + p.wh;
+        sh = (sh - p.ph) < 0 ? 0 : sh - p.ph;
+        eh = (eh - p.ph) > p.h ? p.h : eh - p.ph;
+        int sw = ow * p.sw, ew = sw + p.ww;
+        sw = (sw - p.pw) < 0 ? 0 : sw - p.pw;
+        ew = (ew - p.pw) > p.w ? p.w : ew - p.pw;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kh = sh; kh < eh; ++kh) {
+            for (int kw = sw; kw < ew; ++kw) {
+                const float4 x = __ldg(in + ((1ll * n * p.h + kh) * p.w + kw) * cv + v);
+                if (kh == sh && kw == sw) {
+                    r = x;
+                } else if (p.type == B200_POOL_MAX) {
+                    r.x = r.x >= x.x ? r.x : x.x; r.y = r.y >= x.y ? r.y : x.y;
+                    r.z = r.z >= x.z ? r.z : x.z; r.w = r.w >= x.w ? r.w : x.w;
+                } else {
+                    r.x = __fadd_rn(r.x, x.x); r.y = __fadd_rn(r.y, x.y);
+                    r.z = __fadd_rn(r.z, x.z); r.w = __fadd_rn(r.w, x.w);
+                }
+            }
+        }
+        if (p.type == B200_POOL_AVG_INCLUDE_PAD) {
+            int bh = p.wh, bw = p.ww;
+            if (ew == p.w) { bw = (sw + p.ww >= p.w + p.pw) ? p.w + p.pw : sw + p.ww; bw -= sw; }
+            if (eh == p.h) { bh = (sh + p.wh >= p.h + p.ph) ? p.h + p.ph : sh + p.wh; bh -= sh; }
+            const float d = static_cast<float>(bh * bw);
+            r.x = __fdiv_rn(r.x, d); r.y = __fdiv_rn(r.y, d); r.z = __fdiv_rn(r.z, d); r.w = __fdiv_rn(r.w, d);
+        } else if (p.type == B200_POOL_AVG_EXCLUDE_PAD) {
+            const float d = static_cast<float>((ew - sw) * (eh - sh));
+            r.x = __fdiv_rn(r.x, d); r.y = __fdiv_rn(r.y, d); r.z = __fdiv_rn(r.z, d); r.w = __fdiv_rn(r.w, d);
+        }
+        out[((1ll * n * p.oh + oh) * p.ow + ow) * cv + v] = r;
+    }
+}
+
+// fp16: 8 channels per thread, accumulate in fp32.
+__global__ void pool_f16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolP p) {
+    const int cv = p.c >> 3;
+    const long long total = 1ll * p.n * p.oh * p.ow * cv;
+    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
+         idx += 1ll * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int ow = static_cast<int>(t % p.ow); t /= p.ow;
+        const int oh = static_cast<int>(t % p.oh);
+        const int n = static_cast<int>(t / p.oh);
+        int sh = oh * p.sh, eh = sh + p.wh;
+        sh = (sh - p.ph) < 0 ? 0 : sh - p.ph;
+        eh = (eh - p.ph) > p.h ? p.h : eh - p.ph;
+        int sw = ow * p.sw, ew = sw + p.ww;
+        sw = (sw - p.pw) < 0 ? 0 : sw - p.pw;
+        ew = (ew - p.pw) > p.w ? p.w : ew - p.pw;
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = 0.f;
+        for (int kh = sh; kh < eh; ++kh) {
+            for (int kw = sw; kw < ew; ++kw) {
+                const uint4 x = __ldg(in + ((1ll * n * p.h + kh) * p.w + kw) * cv + v);
+                const __half2* hx = reinterpret_cast<const __half2*>(&x);
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { float2 q = __half22float2(hx[i]); f[2 * i] = q.x; f[2 * i + 1] = q.y; }
+                const bool first = (kh == sh && kw == sw);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (first) r[i] = f[i];
+                    else if (p.type == B200_POOL_MAX) r[i] = r[i] >= f[i] ? r[i] : f[i];
+                    else r[i] = __fadd_rn(r[i], f[i]);
+                }
+            }
+        }
+        float d = 1.f;
+        if (p.type == B200_POOL_AVG_INCLUDE_PAD) {
+            int bh = p.wh, bw = p.ww;
+            if (ew == p.w) { bw = (sw + p.ww >= p.w + p.pw) ? p.w + p.pw : sw + p.ww; bw -= sw; }
+            if (eh == p.h) { bh = (sh + p.wh >= p.h + p.ph) ? p.h + p.ph : sh + p.wh; bh -= sh; }
+            d = static_cast<float>(bh * bw);
+        } else if (p.type == B200_POOL_AVG_EXCLUDE_PAD) {
+            d = static_cast<float>((ew - sw) * (eh - sh));
+        }
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            ho[i] = __floats2half2_rn(__fdiv_rn(r[2 * i], d), __fdiv_rn(r[2 * i + 1], d));
+        out[((1ll * n * p.oh + oh) * p.ow + ow) * cv + v] = o;
+    }
+}
+
+// int8 / uint8 NHWC: 16 channels per thread. Semantics = reference
+// test/saber/conv_func_helper.h:29-100 (pool_basic_check_int8): float sum of the raw
+// codes, avg-incl divides by window_h*window_w, nearbyintf (RNE), saturate.
+template <bool kUnsigned>
+__global__ void pool_q8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolP p) {
+    const int cv = p.c >> 4;
+    const long long total = 1ll * p.n * p.oh * p.ow * cv;
+    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
+         idx += 1ll * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int ow = static_cast<int>(t % p.ow); t /= p.ow;
+        const int oh = static_cast<int>(t % p.oh);
+        const int n = static_cast<int>(t / p.oh);
+        int sh = oh * p.sh, eh = sh + p.wh;
+        if (p.ph > 0) {
+            sh = (sh - p.ph) < 0 ? 0 : sh - p.ph;
+            eh = (eh - p.ph) > p.h ? p.h : eh - p.ph;
+        }
+        if (eh > p.h) eh = p.h;
+        int sw = ow * p.sw, ew = sw + p.ww;
+        if (p.pw > 0) {
+            sw = (sw - p.pw) < 0 ? 0 : sw - p.pw;
+            ew = (ew - p.pw) > p.w ? p.w : ew - p.pw;
+        }
+        if (ew > p.w) ew = p.w;
+        float r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0.f;
+        for (int kh = sh; kh < eh; ++kh) {
+            for (int kw = sw; kw < ew; ++kw) {
+                const uint4 x = __ldg(in + ((1ll * n * p.h + kh) * p.w + kw) * cv + v);
+                const uint32_t wds[4] = {x.x, x.y, x.z, x.w};
+                const bool first = (kh == sh && kw == sw);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t b = (wds[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                    const float f = kUnsigned ? static_cast<float>(b)
+                                              : static_cast<float>(static_cast<int8_t>(b));
+                    if (first) r[i] = f;
+                    else if (p.type == B200_POOL_MAX) r[i] = r[i] >= f ? r[i] : f;
+                    else r[i] = __fadd_rn(r[i], f);
+                }
+            }
+        }
+        float d = 1.f;
+        if (p.type == B200_POOL_AVG_INCLUDE_PAD) d = static_cast<float>(p.wh * p.ww);
+        else if (p.type == B200_POOL_AVG_EXCLUDE_PAD) d = static_cast<float>((ew - sw) * (eh - sh));
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float q = (p.type == B200_POOL_MAX) ? r[i] : __fdiv_rn(r[i], d);
+            uint32_t code;
+            if (kUnsigned) asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(code) : "f"(q));
+            else { int32_t sc; asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(sc) : "f"(q)); code = static_cast<uint32_t>(sc) & 0xffu; }
+            o[i >> 2] |= (code & 0xffu) << (8 * (i & 3));
+        }
+        out[((1ll * n * p.oh + oh) * p.ow + ow) * cv + v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------ softmax
+// inner == 1: one warp per row, shuffle reductions (reference uses one thread per row).
+__global__ void softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
+                                    int len) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* x = in + 1ll * warp * len;
+    float* y = out + 1ll * warp * len;
+    float mx = -3.402823466e+38f;
+    for (int i = lane; i < len; i += 32) mx = fmaxf(mx, __ldg(x + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int i = lane; i < len; i += 32) {
+        const float e = expf(__ldg(x + i) - mx);
+        y[i] = e;
+        sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int i = lane; i < len; i += 32) y[i] = __fdiv_rn(y[i], sum);
+}
+// inner > 1 (softmax over a non-innermost axis): one thread per (outer, inner) column.
+__global__ void softmax_strided_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                       int outer, int len, int inner) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= outer * inner) return;
+    const int o = idx / inner, i = idx % inner;
+    const float* x = in + (1ll * o * len) * inner + i;
+    float* y = out + (1ll * o * len) * inner + i;
+    float mx = -3.402823466e+38f;
+    for (int a = 0; a < len; ++a) mx = fmaxf(mx, x[1ll * a * inner]);
+    float sum = 0.f;
+    for (int a = 0; a < len; ++a) { const float e = expf(x[1ll * a * inner] - mx); y[1ll * a * inner] = e; sum += e; }
+    for (int a = 0; a < len; ++a) y[1ll * a * inner] = __fdiv_rn(y[1ll * a * inner], sum);
+}
+
+// ------------------------------------------------------------------ eltwise
+__device__ __forceinline__ float elt_op(int op, float a, float b, float c0, float c1) {
+    if (op == B200_ELT_SUM) return __fadd_rn(__fmul_rn(c0, a), __fmul_rn(c1, b));
+    if (op == B200_ELT_PROD) return __fmul_rn(a, b);
+    return a > b ? a : b;
+}
+__global__ void eltwise_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                   float* __restrict__ out, size_t count, int op, float c0, float c1,
+                                   int relu) {
+    const size_t nv = count >> 2;
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = tid; i < nv; i += stride) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i);
+        const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
+        float4 r;
+        r.x = elt_op(op, x.x, y.x, c0, c1); r.y = elt_op(op, x.y, y.y, c0, c1);
+        r.z = elt_op(op, x.z, y.z, c0, c1); r.w = elt_op(op, x.w, y.w, c0, c1);
+        if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+        reinterpret_cast<float4*>(out)[i] = r;
+    }
+    for (size_t i = (nv << 2) + tid; i < count; i += stride) {
+        float r = elt_op(op, a[i], b[i], c0, c1);
+        out[i] = relu ? fmaxf(r, 0.f) : r;
+    }
+}
+__global__ void eltwise_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                   __half* __restrict__ out, size_t count, int op, float c0, float c1,
+                                   int relu) {
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = tid; i < count; i += stride) {
+        float r = elt_op(op, __half2float(a[i]), __half2float(b[i]), c0, c1);
+        out[i] = __float2half_rn(relu ? fmaxf(r, 0.f) : r);
+    }
+}
+// int8 sum (x86 semantics, reference saber/funcs/impl/x86/saber_eltwise.cpp:72-111):
+//   tmp = a*sa + b*sb; relu; saturate(roundf(tmp))   (roundf = half away from zero)
+__global__ void eltwise_q8_kernel(const uint8_t* __restrict__ a, int a_unsigned,
+                                  const uint8_t* __restrict__ b, int b_unsigned,
+                                  uint8_t* __restrict__ out, int out_unsigned, size_t count, float sa,
+                                  float sb, int relu) {
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t nv = count >> 4;
+    for (size_t i = tid; i < nv; i += stride) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(a) + i);
+        const uint4 y = __ldg(reinterpret_cast<const uint4*>(b) + i);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t xb = (xs[j >> 2] >> (8 * (j & 3))) & 0xffu, yb = (ys[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            const float fa = a_unsigned ? static_cast<float>(xb) : static_cast<float>(static_cast<int8_t>(xb));
+            const float fb = b_unsigned ? static_cast<float>(yb) : static_cast<float>(static_cast<int8_t>(yb));
+            float f = __fadd_rn(__fmul_rn(fa, sa), __fmul_rn(fb, sb));
+            if (relu) f = f > 0.f ? f : 0.f;
+            float r = roundf(f);
+            r = out_unsigned ? fminf(fmaxf(r, 0.f), 255.f) : fminf(fmaxf(r, -128.f), 127.f);
+            o[j >> 2] |= (static_cast<uint32_t>(static_cast<int32_t>(r)) & 0xffu) << (8 * (j & 3));
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    for (size_t i = (nv << 4) + tid; i < count; i += stride) {
+        const float fa = a_unsigned ? static_cast<float>(a[i]) : static_cast<float>(static_cast<int8_t>(a[i]));
+        const float fb = b_unsigned ? static_cast<float>(b[i]) : static_cast<float>(static_cast<int8_t>(b[i]));
+        float f = __fadd_rn(__fmul_rn(fa, sa), __fmul_rn(fb, sb));
+        if (relu) f = f > 0.f ? f : 0.f;
+        float r = roundf(f);
+        r = out_unsigned ? fminf(fmaxf(r, 0.f), 255.f) : fminf(fmaxf(r, -128.f), 127.f);
+        out[i] = static_cast<uint8_t>(static_cast<int32_t>(r) & 0xff);
+    }
+}
+
+// ------------------------------------------------------------------ activation / scale
+__device__ __forceinline__ float act_op(int act, float x, float slope, float coef) {
+    switch (act) {
+        case B200_ACT_RELU: return x > 0.f ? x : __fmul_rn(x, slope);
+        case B200_ACT_SIGMOID: return __fdiv_rn(1.0f, expf(-x) + 1.0f);
+        case B200_ACT_TANH: return tanhf(x);
+        case B200_ACT_CLIPPED_RELU: { float y = x > 0.f ? x : 0.f; return y < coef ? y : coef; }
+        case B200_ACT_ELU: return x > 0.f ? x : __fmul_rn(coef, expf(x) - 1.f);
+        default: return x;
+    }
+}
+__global__ void activation_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                      size_t count, int act, float slope, float coef) {
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t nv = count >> 2;
+    for (size_t i = tid; i < nv; i += stride) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(in) + i);
+        reinterpret_cast<float4*>(out)[i] = make_float4(act_op(act, x.x, slope, coef), act_op(act, x.y, slope, coef),
+                                                        act_op(act, x.z, slope, coef), act_op(act, x.w, slope, coef));
+    }
+    for (size_t i = (nv << 2) + tid; i < count; i += stride) out[i] = act_op(act, in[i], slope, coef);
+}
+__global__ void activation_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out,
+                                      size_t count, int act, float slope, float coef) {
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = tid; i < count; i += stride)
+        out[i] = __float2half_rn(act_op(act, __half2float(in[i]), slope, coef));
+}
+__global__ void scale_f32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t pixels,
+                                 int c, const float* __restrict__ w, const float* __restrict__ b) {
+    const size_t total = pixels * c;
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = tid; i < total; i += stride) {
+        const int ch = static_cast<int>(i % c);
+        float y = __fmul_rn(in[i], __ldg(w + ch));
+        if (b) y = __fadd_rn(y, __ldg(b + ch));
+        out[i] = y;
+    }
+}
+__global__ void scale_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, size_t pixels,
+                                 int c, const float* __restrict__ w, const float* __restrict__ b) {
+    const size_t total = pixels * c;
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = tid; i < total; i += stride) {
+        const int ch = static_cast<int>(i % c);
+        float y = __fmul_rn(__half2float(in[i]), __ldg(w + ch));
+        if (b) y = __fadd_rn(y, __ldg(b + ch));
+        out[i] = __float2half_rn(y);
+    }
+}
+
+// ------------------------------------------------------------------ layout / precision transforms
+// NCHW fp32 -> NHWC (c padded to c_pad with zeros) in out_dtype; a 32x32 smem transpose of
+// the (c, hw) plane keeps both the read (along hw) and the write (along c) coalesced.
+template <int OUT>  // 0 f32, 1 f16, 2 s8, 3 u8
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, void* __restrict__ out, int c,
+                                    int hw, int c_pad, float inv_scale) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int ch = c0 + j, px = hw0 + threadIdx.x;
+        tile[j][threadIdx.x] = (ch < c && px < hw) ? __ldg(in + (1ll * n * c + ch) * hw + px) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int px = hw0 + j, ch = c0 + threadIdx.x;
+        if (px >= hw || ch >= c_pad) continue;
+        const float x = tile[threadIdx.x][j];
+        const long long o = (1ll * n * hw + px) * c_pad + ch;
+        if (OUT == 0) {
+            static_cast<float*>(out)[o] = x;
+        } else if (OUT == 1) {
+            static_cast<__half*>(out)[o] = __float2half_rn(x);
+        } else if (OUT == 2) {
+            // secur_cast2char(x * inv): roundf + clamp (reference x86_utils.h:318-347)
+            float t = roundf(__fmul_rn(x, inv_scale));
+            t = fminf(fmaxf(t, -128.f), 127.f);
+            static_cast<int8_t*>(out)[o] = static_cast<int8_t>(static_cast<int>(t));
+        } else {
+            // static_cast<unsigned char>(x * inv): truncation (reference x86_utils.h:360-372)
+            float t = __fmul_rn(x, inv_scale);
+            t = fminf(fmaxf(t, 0.f), 255.f);
+            static_cast<uint8_t*>(out)[o] = static_cast<uint8_t>(static_cast<int>(t));
+        }
+    }
+}
+template <int IN>  // 0 f32, 1 f16, 2 s8, 3 u8
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ in, float* __restrict__ out, int c, int hw,
+                                    int c_pad, float scale) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int px = hw0 + j, ch = c0 + threadIdx.x;
+        float x = 0.f;
+        if (px < hw && ch < c) {
+            const long long i = (1ll * n * hw + px) * c_pad + ch;
+            if (IN == 0) x = static_cast<const float*>(in)[i];
+            else if (IN == 1) x = __half2float(static_cast<const __half*>(in)[i]);
+            else if (IN == 2) x = static_cast<float>(static_cast<const int8_t*>(in)[i]);
+            else x = static_cast<float>(static_cast<const uint8_t*>(in)[i]);
+        }
+        tile[j][threadIdx.x] = x;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int ch = c0 + j, px = hw0 + threadIdx.x;
+        if (ch < c && px < hw) out[(1ll * n * c + ch) * hw + px] = __fmul_rn(tile[threadIdx.x][j], scale);
+    }
+}
+
+// ------------------------------------------------------------------ depthwise conv
+// NHWC, one thread = one output pixel x VEC channels, weights [r][s][c].
+// fp32/fp16 math in fp32: acc = sum x*w (r,s order), + bias, relu(neg_slope).
+template <typename T, int VEC>
+__global__ void dwconv_kernel(const T* __restrict__ in, const T* __restrict__ wgt,
+                              const float* __restrict__ bias, T* __restrict__ out, int n, int h, int w,
+                              int c, int oh, int ow, int r, int s, int ph, int pw, int sh, int sw,
+                              int dh, int dw, int relu, float slope) {
+    const int cv = c / VEC;
+    const long long total = 1ll * n * oh * ow * cv;
+    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
+         idx += 1ll * gridDim.x * blockDim.x) {
+        const int v = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int x0 = static_cast<int>(t % ow); t /= ow;
+        const int y0 = static_cast<int>(t % oh);
+        const int b = static_cast<int>(t / oh);
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int kr = 0; kr < r; ++kr) {
+            const int iy = y0 * sh - ph + kr * dh;
+            if (iy < 0 || iy >= h) continue;
+            for (int ks = 0; ks < s; ++ks) {
+                const int ix = x0 * sw - pw + ks * dw;
+                if (ix < 0 || ix >= w) continue;
+                const T* ip = in + ((1ll * b * h + iy) * w + ix) * c + v * VEC;
+                const T* wp = wgt + (1ll * kr * s + ks) * c + v * VEC;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i)
+                    acc[i] = __fmaf_rn(static_cast<float>(ip[i]), static_cast<float>(wp[i]), acc[i]);
+            }
+        }
+        T* op = out + ((1ll * b * oh + y0) * ow + x0) * c + v * VEC;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float y = acc[i] + (bias ? __ldg(bias + v * VEC + i) : 0.f);
+            if (relu) y = y > 0.f ? y : y * slope;
+            op[i] = static_cast<T>(y);
+        }
+    }
+}
+
+static unsigned grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148ll * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<unsigned>(g);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_pool_out_hw(const b200_pool_desc_t* d, int32_t* ho, int32_t* wo) {
+    if (!d || d->h <= 0 || d->w <= 0) return B200_INVALID_VALUE;
+    int oh, ow;
+    if (d->global_pooling) {
+        oh = ow = 1;
+    } else {
+        if (d->stride_h <= 0 || d->stride_w <= 0 || d->window_h <= 0 || d->window_w <= 0)
+            return B200_INVALID_VALUE;
+        if (d->floor_as_conv) {
+            oh = static_cast<int>(static_cast<float>(d->h + 2 * d->pad_h - d->window_h) / d->stride_h) + 1;
+            ow = static_cast<int>(static_cast<float>(d->w + 2 * d->pad_w - d->window_w) / d->stride_w) + 1;
+            if (oh <= 0) oh = 1;
+            if (ow <= 0) ow = 1;
+        } else {
+            oh = static_cast<int>(ceilf(static_cast<float>(d->h + 2 * d->pad_h - d->window_h) / d->stride_h)) + 1;
+            ow = static_cast<int>(ceilf(static_cast<float>(d->w + 2 * d->pad_w - d->window_w) / d->stride_w)) + 1;
+        }
+        if (d->pad_h > 0 || d->pad_w > 0) {
+            if ((oh - 1) * d->stride_h >= d->h + d->pad_h) --oh;
+            if ((ow - 1) * d->stride_w >= d->w + d->pad_w) --ow;
+        }
+    }
+    if (ho) *ho = oh;
+    if (wo) *wo = ow;
+    return B200_SUCCESS;
+}
+
+int b200_pool_run(const b200_pool_desc_t* d, const void* in, void* out, void* stream) {
+    if (!d || !in || !out) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    PoolP p;
+    int32_t oh, ow;
+    int st = b200_pool_out_hw(d, &oh, &ow);
+    if (st != B200_SUCCESS) return st;
+    p.n = d->n; p.h = d->h; p.w = d->w; p.c = d->c; p.oh = oh; p.ow = ow;
+    if (d->global_pooling) {
+        p.wh = d->h; p.ww = d->w; p.ph = p.pw = 0; p.sh = d->h; p.sw = d->w;
+    } else {
+        p.wh = d->window_h; p.ww = d->window_w; p.ph = d->pad_h; p.pw = d->pad_w;
+        p.sh = d->stride_h; p.sw = d->stride_w;
+    }
+    p.type = d->type;
+    if (p.type < B200_POOL_MAX || p.type > B200_POOL_AVG_EXCLUDE_PAD) return B200_INVALID_VALUE;
+    const int block = 256;
+    if (d->dtype == B200_FLOAT) {
+        if (d->c % 4) return B200_INVALID_VALUE;
+        const long long total = 1ll * p.n * oh * ow * (d->c / 4);
+        pool_f32_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
+            static_cast<const float4*>(in), static_cast<float4*>(out), p);
+    } else if (d->dtype == B200_HALF) {
+        if (d->c % 8) return B200_INVALID_VALUE;
+        const long long total = 1ll * p.n * oh * ow * (d->c / 8);
+        pool_f16_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
+            static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+    } else if (d->dtype == B200_INT8 || d->dtype == B200_UINT8) {
+        if (d->c % 16) return B200_INVALID_VALUE;
+        const long long total = 1ll * p.n * oh * ow * (d->c / 16);
+        if (d->dtype == B200_UINT8)
+            pool_q8_kernel<true><<<grid_for(total, block), block, 0, S(stream)>>>(
+                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+        else
+            pool_q8_kernel<false><<<grid_for(total, block), block, 0, S(stream)>>>(
+                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+    } else {
+        return B200_UNIMPL_ERROR;
+    }
+    return check_launch("pool");
+}
+
+int b200_softmax_run(const float* in, float* out, int32_t outer, int32_t axis_size, int32_t inner,
+                     void* stream) {
+    if (!in || !out || outer <= 0 || axis_size <= 0 || inner <= 0) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    if (inner == 1) {
+        const int block = 128;  // 4 rows per CTA
+        const unsigned grid = (static_cast<unsigned>(outer) * 32 + block - 1) / block;
+        softmax_rows_kernel<<<grid, block, 0, S(stream)>>>(in, out, outer, axis_size);
+    } else {
+        const int block = 128;
+        softmax_strided_kernel<<<(outer * inner + block - 1) / block, block, 0, S(stream)>>>(
+            in, out, outer, axis_size, inner);
+    }
+    return check_launch("softmax");
+}
+
+int b200_eltwise_run(int32_t dtype_a, int32_t dtype_b, int32_t dtype_out, int32_t op, const void* a,
+                     const void* b, void* out, size_t count, float c0, float c1, int32_t relu,
+                     void* stream) {
+    if (!a || !b || !out || count == 0) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    if (op < B200_ELT_PROD || op > B200_ELT_MAX) return B200_UNIMPL_ERROR;
+    const int block = 256;
+    if (dtype_a == B200_FLOAT && dtype_b == B200_FLOAT && dtype_out == B200_FLOAT) {
+        eltwise_f32_kernel<<<grid_for((count + 3) / 4, block), block, 0, S(stream)>>>(
+            static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(out), count,
+            op, c0, c1, relu);
+    } else if (dtype_a == B200_HALF && dtype_b == B200_HALF && dtype_out == B200_HALF) {
+        eltwise_f16_kernel<<<grid_for(count, block), block, 0, S(stream)>>>(
+            static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(out),
+            count, op, c0, c1, relu);
+    } else {
+        auto q8 = [](int dt) { return dt == B200_INT8 || dt == B200_UINT8; };
+        if (!q8(dtype_a) || !q8(dtype_b) || !q8(dtype_out) || op != B200_ELT_SUM) return B200_UNIMPL_ERROR;
+        eltwise_q8_kernel<<<grid_for((count + 15) / 16, block), block, 0, S(stream)>>>(
+            static_cast<const uint8_t*>(a), dtype_a == B200_UINT8, static_cast<const uint8_t*>(b),
+            dtype_b == B200_UINT8, static_cast<uint8_t*>(out), dtype_out == B200_UINT8, count, c0, c1,
+            relu);
+    }
+    return check_launch("eltwise");
+}
+
+int b200_activation_run(int32_t dtype, int32_t act, const void* in, void* out, size_t count,
+                        float neg_slope, float coef, void* stream) {
+    if (!in || !out || count == 0) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    const int block = 256;
+    if (dtype == B200_FLOAT)
+        activation_f32_kernel<<<grid_for((count + 3) / 4, block), block, 0, S(stream)>>>(
+            static_cast<const float*>(in), static_cast<float*>(out), count, act, neg_slope, coef);
+    else if (dtype == B200_HALF)
+        activation_f16_kernel<<<grid_for(count, block), block, 0, S(stream)>>>(
+            static_cast<const __half*>(in), static_cast<__half*>(out), count, act, neg_slope, coef);
+    else
+        return B200_UNIMPL_ERROR;
+    return check_launch("activation");
+}
+
+int b200_scale_run(int32_t dtype, const void* in, void* out, size_t pixels, int32_t c, const float* w,
+                   const float* b, void* stream) {
+    if (!in || !out || !w || pixels == 0 || c <= 0) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    const int block = 256;
+    if (dtype == B200_FLOAT)
+        scale_f32_kernel<<<grid_for(pixels * c, block), block, 0, S(stream)>>>(
+            static_cast<const float*>(in), static_cast<float*>(out), pixels, c, w, b);
+    else if (dtype == B200_HALF)
+        scale_f16_kernel<<<grid_for(pixels * c, block), block, 0, S(stream)>>>(
+            static_cast<const __half*>(in), static_cast<__half*>(out), pixels, c, w, b);
+    else
+        return B200_UNIMPL_ERROR;
+    return check_launch("scale");
+}
+
+int b200_nchw_to_nhwc(const float* in, void* out, int32_t out_dtype, int32_t n, int32_t c, int32_t h,
+                      int32_t w, int32_t c_pad, float inv_scale, int32_t split_hi_lo, void* stream) {
+    if (!in || !out || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_pad < c) return B200_INVALID_VALUE;
+    if (split_hi_lo) return B200_UNIMPL_ERROR;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    const int hw = h * w;
+    dim3 grid((hw + 31) / 32, (c_pad + 31) / 32, n), block(32, 8);
+    switch (out_dtype) {
+        case B200_FLOAT: nchw_to_nhwc_kernel<0><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, inv_scale); break;
+        case B200_HALF: nchw_to_nhwc_kernel<1><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, inv_scale); break;
+        case B200_INT8: nchw_to_nhwc_kernel<2><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, inv_scale); break;
+        case B200_UINT8: nchw_to_nhwc_kernel<3><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, inv_scale); break;
+        default: return B200_UNIMPL_ERROR;
+    }
+    return check_launch("nchw_to_nhwc");
+}
+
+int b200_nhwc_to_nchw(const void* in, int32_t in_dtype, float* out, int32_t n, int32_t c, int32_t h,
+                      int32_t w, int32_t c_pad, float scale, void* stream) {
+    if (!in || !out || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_pad < c) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    const int hw = h * w;
+    dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+    switch (in_dtype) {
+        case B200_FLOAT: nhwc_to_nchw_kernel<0><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, scale); break;
+        case B200_HALF: nhwc_to_nchw_kernel<1><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, scale); break;
+        case B200_INT8: nhwc_to_nchw_kernel<2><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, scale); break;
+        case B200_UINT8: nhwc_to_nchw_kernel<3><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, scale); break;
+        default: return B200_UNIMPL_ERROR;
+    }
+    return check_launch("nhwc_to_nchw");
+}
+
+int b200_dwconv_run(const b200_conv_desc_t* d, const void* in, const void* weights_rsc,
+                    const float* bias, const float* scale, void* out, void* stream) {
+    if (!d || !in || !weights_rsc || !out) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    (void)scale;
+    if (d->k != d->c) return B200_INVALID_VALUE;
+    const int oh = (d->h + 2 * d->pad_h - (d->dil_h * (d->r - 1) + 1)) / d->stride_h + 1;
+    const int ow = (d->w + 2 * d->pad_w - (d->dil_w * (d->s - 1) + 1)) / d->stride_w + 1;
+    if (oh <= 0 || ow <= 0) return B200_INVALID_VALUE;
+    const int block = 256;
+    if (d->in_dtype == B200_FLOAT && d->out_dtype == B200_FLOAT) {
+        if (d->c % 4) return B200_INVALID_VALUE;
+        const long long total = 1ll * d->n * oh * ow * (d->c / 4);
+        dwconv_kernel<float, 4><<<grid_for(total, block), block, 0, S(stream)>>>(
+            static_cast<const float*>(in), static_cast<const float*>(weights_rsc), bias,
+            static_cast<float*>(out), d->n, d->h, d->w, d->c, oh, ow, d->r, d->s, d->pad_h, d->pad_w,
+            d->stride_h, d->stride_w, d->dil_h, d->dil_w, d->relu, d->neg_slope);
+    } else if (d->in_dtype == B200_HALF && d->out_dtype == B200_HALF) {
+        if (d->c % 8) return B200_INVALID_VALUE;
+        const long long total = 1ll * d->n * oh * ow * (d->c / 8);
+        dwconv_kernel<__half, 8><<<grid_for(total, block), block, 0, S(stream)>>>(
+            static_cast<const __half*>(in), static_cast<const __half*>(weights_rsc), bias,
+            static_cast<__half*>(out), d->n, d->h, d->w, d->c, oh, ow, d->r, d->s, d->pad_h, d->pad_w,
+            d->stride_h, d->stride_w, d->dil_h, d->dil_w, d->relu, d->neg_slope);
+    } else {
+        return B200_UNIMPL_ERROR;
+    }
+    return check_launch("dwconv");
+}
+
+}  // extern "C"

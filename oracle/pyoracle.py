@@ -1,0 +1,339 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c) and, when built, of the
+reference's own naive test oracle compiled from /root/reference (oracle/_ref/).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py -- never by anakin_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libanakin_ref_oracle.so")
+
+DT_FLOAT, DT_INT8, DT_UINT8 = 1, 3, 7
+
+
+def build(ref=True):
+    """Compile liboracle.so (always) and oracle/_ref (only where /root/reference exists)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
+    if ref and os.path.isdir("/root/reference/test/saber") and not os.path.exists(_REF):
+        subprocess.check_call(["make", "-C", _HERE, "ref"])
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build(ref=False)
+        _lib = C.CDLL(_LIB)
+        _lib.oracle_conv_out_size.restype = C.c_int
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def ref_lib():
+    """The reference's own oracle (None when it has not been / cannot be built here)."""
+    global _ref
+    if _ref is None and os.path.exists(_REF):
+        _ref = C.CDLL(_REF)
+    return _ref
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(x):
+    return C.c_float(float(x))
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def set_threads(n):
+    lib().oracle_set_threads(int(n))
+
+
+def conv_out_size(i, pad, dil, k, stride):
+    return (i + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+
+def pool_out_size(h, w, wh, ww, ph, pw, sh, sw, global_pooling=False, floor_as_conv=False):
+    oh, ow = C.c_int(), C.c_int()
+    lib().oracle_pool_out_size(h, w, wh, ww, ph, pw, sh, sw, int(global_pooling), int(floor_as_conv),
+                               C.byref(oh), C.byref(ow))
+    return oh.value, ow.value
+
+
+def conv_f32_nchw(x, w, bias, group=1, stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False,
+                  neg_slope=0.0, beta=0.0, alpha=1.0, dst=None):
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    n, c, h, wd = x.shape
+    k, _, r, s = w.shape
+    oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
+    ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
+    out = np.zeros((n, k, oh, ow), np.float32) if dst is None else np.ascontiguousarray(dst, np.float32).copy()
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    lib().oracle_conv_f32_nchw(_p(x), _p(w), _p(b), _p(out), n, c, h, wd, k, group, r, s, stride[0],
+                               stride[1], dil[0], dil[1], pad[0], pad[1], int(b is not None),
+                               int(relu), _f(neg_slope), _f(beta), _f(alpha))
+    return out
+
+
+def conv_f32_nhwc(x, w, bias, residual=None, group=1, stride=(1, 1), dil=(1, 1), pad=(0, 0),
+                  relu=False, neg_slope=0.0, beta=1.0):
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    n, h, wd, c = x.shape
+    k, _, r, s = w.shape
+    oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
+    ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
+    out = np.zeros((n, oh, ow, k), np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    res = None if residual is None else np.ascontiguousarray(residual, np.float32)
+    lib().oracle_conv_f32_nhwc(_p(x), _p(w), _p(b), _p(res), _p(out), n, c, h, wd, k, group, r, s,
+                               stride[0], stride[1], dil[0], dil[1], pad[0], pad[1],
+                               int(b is not None), int(relu), _f(neg_slope), _f(beta))
+    return out
+
+
+_NP = {DT_FLOAT: np.float32, DT_INT8: np.int8, DT_UINT8: np.uint8}
+
+
+def _dt(a):
+    return {np.dtype(np.float32): DT_FLOAT, np.dtype(np.int8): DT_INT8, np.dtype(np.uint8): DT_UINT8}[a.dtype]
+
+
+def conv_s8_nhwc_x86(x, w_s8, bias_f, scale, residual=None, sum_scale=1.0, out_dtype=DT_INT8,
+                     stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False):
+    """x: NHWC s8/u8, w_s8: KCRS int8; returns NHWC out_dtype."""
+    x = np.ascontiguousarray(x)
+    w_s8 = np.ascontiguousarray(w_s8, np.int8)
+    n, h, wd, c = x.shape
+    k, cw, r, s = w_s8.shape
+    assert cw == c
+    oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
+    ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
+    out = np.zeros((n, oh, ow, k), _NP[out_dtype])
+    b = None if bias_f is None else np.ascontiguousarray(bias_f, np.float32)
+    sc = None if scale is None else np.ascontiguousarray(scale, np.float32)
+    res = None if residual is None else np.ascontiguousarray(residual)
+    lib().oracle_conv_s8_nhwc_x86(_p(x), _dt(x), _p(w_s8), _p(b), _p(sc), _p(res),
+                                  _dt(res) if res is not None else -1, _f(sum_scale), _p(out),
+                                  out_dtype, n, c, h, wd, k, r, s, stride[0], stride[1], dil[0],
+                                  dil[1], pad[0], pad[1], int(relu))
+    return out
+
+
+def conv_s8_nhwc_basic(x, w_s8, bias_i32, scale, dst=None, has_elt_sum=False, sum_scale=1.0,
+                       beta=0.0, group=1, stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False,
+                       round_down=False, use_ref=False):
+    """Restatement (or, use_ref=True, the reference itself) of conv_basic_check_int8."""
+    x = np.ascontiguousarray(x)
+    w_s8 = np.ascontiguousarray(w_s8, np.int8)
+    n, h, wd, c = x.shape
+    k, _, r, s = w_s8.shape
+    oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
+    ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
+    out = np.zeros((n, oh, ow, k), np.int8) if dst is None else np.ascontiguousarray(dst, np.int8).copy()
+    b = None if bias_i32 is None else np.ascontiguousarray(bias_i32, np.int32)
+    sc = np.ascontiguousarray(scale, np.float32)
+    uns = int(x.dtype == np.uint8)
+    if use_ref:
+        ref_lib().ref_conv_basic_check_int8(_p(x), uns, _p(w_s8), _p(b), _p(out), n, c, h, wd, k, oh,
+                                            ow, group, s, r, stride[1], stride[0], dil[1], dil[0],
+                                            pad[1], pad[0], int(b is not None), int(relu), _p(sc),
+                                            int(has_elt_sum), _f(sum_scale), _f(beta), int(round_down))
+    else:
+        lib().oracle_conv_s8_nhwc_basic(_p(x), uns, _p(w_s8), _p(b), _p(out), n, c, h, wd, k, group,
+                                        r, s, stride[0], stride[1], dil[0], dil[1], pad[0], pad[1],
+                                        int(b is not None), int(relu), _p(sc), int(has_elt_sum),
+                                        _f(sum_scale), _f(beta), int(round_down))
+    return out
+
+
+def ref_conv_f32_nchw(x, w, bias, group=1, stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False,
+                      beta=0.0, alpha=1.0, dst=None):
+    """The reference's conv_basic_check itself (oracle/_ref)."""
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    n, c, h, wd = x.shape
+    k, _, r, s = w.shape
+    oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
+    ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
+    out = np.zeros((n, k, oh, ow), np.float32) if dst is None else np.ascontiguousarray(dst, np.float32).copy()
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    ref_lib().ref_conv_basic_check_f32(_p(x), _p(w), _p(b), _p(out), n, c, h, wd, k, oh, ow, group, s,
+                                       r, stride[1], stride[0], dil[1], dil[0], pad[1], pad[0],
+                                       int(b is not None), int(relu), _f(beta), _f(alpha))
+    return out
+
+
+def int8_conv_scales(w_scale, bias, in_scale, in_dtype, out_scale, out_dtype, res_scale=1.0,
+                     res_dtype=DT_INT8):
+    w_scale = np.ascontiguousarray(w_scale, np.float32)
+    k = w_scale.shape[0]
+    sc = np.zeros(k, np.float32)
+    bf = np.zeros(k, np.float32)
+    ss = C.c_float()
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    lib().oracle_int8_conv_scales(_p(w_scale), _p(b), k, _f(in_scale), in_dtype, _f(out_scale),
+                                  out_dtype, _f(res_scale), res_dtype, _p(sc), _p(bf), C.byref(ss))
+    return sc, bf, ss.value
+
+
+def quant_weights_per_oc(w):
+    w = np.ascontiguousarray(w, np.float32)
+    k = w.shape[0]
+    per = w.size // k
+    out = np.zeros(w.shape, np.int8)
+    sc = np.zeros(k, np.float32)
+    lib().oracle_quant_weights_per_oc(_p(w), k, per, _p(out), _p(sc))
+    return out, sc
+
+
+def quant_fp32_s8(x, scale):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.shape, np.int8)
+    lib().oracle_quant_fp32_s8(_p(x), _p(out), C.c_size_t(x.size), _f(scale))
+    return out
+
+
+def quant_fp32_u8(x, scale):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.shape, np.uint8)
+    lib().oracle_quant_fp32_u8(_p(x), _p(out), C.c_size_t(x.size), _f(scale))
+    return out
+
+
+def fold_bn_scale(w, bias, bn_scale_factor, eps, mean, var, gamma, beta_s):
+    w = np.ascontiguousarray(w, np.float32).copy()
+    k = w.shape[0]
+    b = np.zeros(k, np.float32) if bias is None else np.ascontiguousarray(bias, np.float32).copy()
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    mean, var, gamma, beta_s = f32(mean), f32(var), f32(gamma), f32(beta_s)
+    lib().oracle_fold_bn_scale(_p(w), _p(b), k, w.size // k, _f(bn_scale_factor), _f(eps), _p(mean),
+                               _p(var), _p(gamma), _p(beta_s))
+    return w, b
+
+
+def pool_f32(x, window, pad, stride, ptype, nhwc=False, global_pooling=False, floor_as_conv=False):
+    x = np.ascontiguousarray(x, np.float32)
+    if nhwc:
+        n, h, w, c = x.shape
+    else:
+        n, c, h, w = x.shape
+    if global_pooling:
+        window, stride, pad = (h, w), (h, w), (0, 0)
+    oh, ow = pool_out_size(h, w, window[0], window[1], pad[0], pad[1], stride[0], stride[1],
+                           global_pooling, floor_as_conv)
+    out = np.zeros((n, oh, ow, c) if nhwc else (n, c, oh, ow), np.float32)
+    lib().oracle_pool_f32(_p(x), _p(out), n, c, h, w, oh, ow, window[0], window[1], pad[0], pad[1],
+                          stride[0], stride[1], int(ptype), int(nhwc))
+    return out
+
+
+def pool_s8_nhwc(x, window, pad, stride, ptype, global_pooling=False, floor_as_conv=False,
+                 use_ref=False):
+    x = np.ascontiguousarray(x)
+    n, h, w, c = x.shape
+    if global_pooling:
+        window, stride, pad = (h, w), (h, w), (0, 0)
+    oh, ow = pool_out_size(h, w, window[0], window[1], pad[0], pad[1], stride[0], stride[1],
+                           global_pooling, floor_as_conv)
+    out = np.zeros((n, oh, ow, c), x.dtype)
+    uns = int(x.dtype == np.uint8)
+    if use_ref:
+        ref_lib().ref_pool_basic_check_int8(_p(x), _p(out), uns, n, c, h, w, oh, ow, window[1],
+                                            window[0], stride[1], stride[0], pad[1], pad[0], int(ptype))
+    else:
+        lib().oracle_pool_s8_nhwc(_p(x), _p(out), uns, n, c, h, w, oh, ow, window[0], window[1],
+                                  pad[0], pad[1], stride[0], stride[1], int(ptype))
+    return out
+
+
+def fc_f32(x, w, bias):
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    m = x.shape[0]
+    k = x.size // m
+    n_out = w.size // k
+    out = np.zeros((m, n_out), np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    lib().oracle_fc_f32(_p(x), _p(w), _p(b), _p(out), m, k, n_out)
+    return out
+
+
+def fc_s8(x, w_s8, bias, scale):
+    x = np.ascontiguousarray(x)
+    w_s8 = np.ascontiguousarray(w_s8, np.int8)
+    m = x.shape[0]
+    k = x.size // m
+    n_out = w_s8.size // k
+    out = np.zeros((m, n_out), np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    sc = np.ascontiguousarray(scale, np.float32)
+    lib().oracle_fc_s8(_p(x), _dt(x), _p(w_s8), _p(b), _p(sc), _p(out), m, k, n_out)
+    return out
+
+
+def softmax_f32(x, outer, axis_size, inner=1):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.shape, np.float32)
+    lib().oracle_softmax_f32(_p(x), _p(out), outer, axis_size, inner)
+    return out
+
+
+def eltwise_f32(a, b, op=2, c0=1.0, c1=1.0, relu=False):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    out = np.zeros(a.shape, np.float32)
+    lib().oracle_eltwise_f32(_p(a), _p(b), _p(out), C.c_size_t(a.size), op, _f(c0), _f(c1), int(relu))
+    return out
+
+
+def eltwise_sum_q8(a, b, sa, sb, out_dtype, relu=False):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    out = np.zeros(a.shape, _NP[out_dtype])
+    lib().oracle_eltwise_sum_q8(_p(a), _dt(a), _p(b), _dt(b), _p(out), out_dtype, C.c_size_t(a.size),
+                                _f(sa), _f(sb), int(relu))
+    return out
+
+
+def activation_f32(x, act, neg_slope=0.0, coef=1.0):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.shape, np.float32)
+    lib().oracle_activation_f32(_p(x), _p(out), C.c_size_t(x.size), act, _f(neg_slope), _f(coef))
+    return out
+
+
+def scale_f32(x, outer, c, inner, w, b):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.shape, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    b = None if b is None else np.ascontiguousarray(b, np.float32)
+    lib().oracle_scale_f32(_p(x), _p(out), outer, c, inner, _p(w), _p(b))
+    return out
+
+
+def tensor_cmp(a, b, use_ref=False):
+    a = np.ascontiguousarray(a, np.float32).ravel()
+    b = np.ascontiguousarray(b, np.float32).ravel()
+    mr, md = C.c_double(), C.c_double()
+    if use_ref:
+        ref_lib().ref_tensor_cmp_host(_p(a), _p(b), a.size, C.byref(mr), C.byref(md))
+    else:
+        lib().oracle_tensor_cmp(_p(a), _p(b), C.c_size_t(a.size), C.byref(mr), C.byref(md))
+    return mr.value, md.value

@@ -1,0 +1,134 @@
+"""GPU parity: tcgen05 implicit-GEMM conv (C ABI) vs the CPU oracle.
+
+INT8 must be bit-exact against oracle_conv_s8_nhwc_x86 (x86 Saber semantics). Float
+kinds are checked with the reference's own criterion (test_saber_base.h:470 with
+tensor_cmp_host: max_diff < 1e-3 or max_ratio <= 1e-3) against conv_basic_check semantics
+evaluated on the operand values the tensor core sees (f16 / tf32-truncated inputs).
+Shape sweep follows test/saber/test_saber_conv.cpp:868-901,1000-1015 plus the ResNet-50
+layer shapes of SURVEY.md section 8d.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# (n, h, w, c, k, r, stride, pad, dil)
+I8_CASES = [
+    (2, 12, 12, 64, 64, 1, 1, 0, 1),
+    (1, 21, 21, 128, 32, 1, 1, 0, 1),
+    (3, 12, 12, 64, 64, 3, 1, 1, 1),
+    (1, 24, 24, 32, 40, 3, 2, 1, 1),
+    (2, 14, 14, 256, 256, 3, 1, 1, 1),
+    (1, 36, 36, 16, 64, 3, 1, 1, 2),
+    (2, 56, 56, 64, 256, 1, 1, 0, 1),
+    (2, 56, 56, 256, 128, 1, 2, 0, 1),
+    (1, 7, 7, 512, 2048, 1, 1, 0, 1),
+    (8, 7, 7, 512, 512, 3, 1, 1, 1),
+    (1, 64, 64, 16, 64, 7, 2, 3, 1),   # stem-like, 3 real channels padded to 16
+    (8, 1, 1, 2048, 1000, 1, 1, 0, 1),  # fc as 1x1 conv, ragged N
+]
+
+
+def _mk_i8(rng, case, in_unsigned):
+    n, h, w, c, k, r, stride, pad, dil = case
+    c_real = 3 if (r == 7) else c
+    if in_unsigned:
+        x = rng.integers(0, 256, (n, h, w, c_real)).astype(np.uint8)
+    else:
+        x = rng.integers(-128, 128, (n, h, w, c_real)).astype(np.int8)
+    wq = rng.integers(-127, 128, (k, c_real, r, r)).astype(np.int8)
+    bias = rng.uniform(-2000, 2000, k).astype(np.float32)
+    kk = c_real * r * r
+    scale = rng.uniform(0.5, 1.5, k).astype(np.float32) * np.float32(1.0 / (40.0 * np.sqrt(kk) * 8))
+    return x, wq, bias, scale
+
+
+@pytest.mark.parametrize("case", I8_CASES)
+@pytest.mark.parametrize("variant", ["s8_relu_u8", "u8_res_s8", "s8_f32"])
+def test_conv_int8_bit_exact(case, variant, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev, pad_channels
+    rng = np.random.default_rng(hash((case, variant)) % (2 ** 31))
+    n, h, w, c, k, r, stride, pad, dil = case
+    in_unsigned = variant == "u8_res_s8"
+    x, wq, bias, scale = _mk_i8(rng, case, in_unsigned)
+    out_dtype = {"s8_relu_u8": A.UINT8, "u8_res_s8": A.INT8, "s8_f32": A.FLOAT}[variant]
+    relu = variant != "s8_f32"
+    kw = dict(stride=(stride, stride), pad=(pad, pad), dil=(dil, dil), relu=relu)
+    res = None
+    sum_scale = 1.0
+    oh = oracle.conv_out_size(h, pad, dil, r, stride)
+    if variant == "u8_res_s8":
+        res = rng.integers(0, 256, (n, oh, oh, k)).astype(np.uint8)
+        sum_scale = 0.37
+    want = oracle.conv_s8_nhwc_x86(x, wq, bias, scale, residual=res, sum_scale=sum_scale,
+                                   out_dtype=out_dtype, **kw)
+    xin = pad_channels(x, c)
+    run = ConvRunner(A.MATH_I8, xin.shape, A.UINT8 if in_unsigned else A.INT8, wq, bias, scale,
+                     out_dtype, res_dtype=(A.UINT8 if res is not None else -1), sum_scale=sum_scale, **kw)
+    got = run.run(dev(xin), dev(res) if res is not None else None)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert got.shape == want.shape
+    if out_dtype == A.FLOAT:
+        np.testing.assert_array_equal(got, want)
+    else:
+        bad = np.argwhere(got != want)
+        assert bad.shape[0] == 0, "first mismatches %s (info %s)" % (bad[:5], run.info())
+
+
+F_CASES = [
+    (1, 12, 12, 16, 32, 3, 1, 1, 1),
+    (3, 21, 21, 8, 8, 3, 2, 1, 1),
+    (2, 24, 24, 64, 64, 1, 1, 0, 1),
+    (1, 36, 36, 32, 48, 3, 1, 2, 2),
+    (2, 28, 28, 128, 128, 3, 1, 1, 1),
+    (1, 56, 56, 64, 64, 1, 2, 0, 1),
+    (1, 40, 40, 4, 64, 7, 2, 3, 1),   # stem-like (3 real channels)
+]
+
+
+def _tf32_trunc(a):
+    return (np.ascontiguousarray(a, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@pytest.mark.parametrize("case", F_CASES)
+@pytest.mark.parametrize("math", ["f16", "tf32"])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv_float(case, math, with_res, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev, pad_channels
+    rng = np.random.default_rng(hash((case, math, with_res)) % (2 ** 31))
+    n, h, w, c, k, r, stride, pad, dil = case
+    if math == "f16" and c % 8:
+        c = 8
+    c_real = 3 if r == 7 else c
+    x = rng.uniform(-1, 1, (n, h, w, c_real)).astype(np.float32)
+    wt = (rng.standard_normal((k, c_real, r, r)) * np.sqrt(2.0 / (c_real * r * r))).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, k).astype(np.float32)
+    kw = dict(stride=(stride, stride), pad=(pad, pad), dil=(dil, dil), relu=True, neg_slope=0.1)
+    oh = oracle.conv_out_size(h, pad, dil, r, stride)
+    res = rng.uniform(-1, 1, (n, oh, oh, k)).astype(np.float32) if with_res else None
+    if math == "f16":
+        xs, ws = x.astype(np.float16), wt.astype(np.float16)
+        x_seen, w_seen = xs.astype(np.float32), ws.astype(np.float32)
+        mk, dt = A.MATH_F16, A.HALF
+        res_in = res.astype(np.float16) if with_res else None
+        res_seen = res_in.astype(np.float32) if with_res else None
+    else:
+        xs, ws = x, wt
+        x_seen, w_seen = _tf32_trunc(x), _tf32_trunc(wt)
+        mk, dt = A.MATH_TF32, A.FLOAT
+        res_in = res
+        res_seen = res
+    want = oracle.conv_f32_nhwc(x_seen, w_seen, bias, residual=res_seen, beta=1.0, **kw)
+    xin = pad_channels(xs, c)
+    run = ConvRunner(mk, xin.shape, dt, ws, bias, None, A.FLOAT, res_dtype=(dt if with_res else -1),
+                     sum_scale=1.0, **kw)
+    got = run.run(dev(xin), dev(res_in) if with_res else None)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    max_ratio, max_diff = oracle.tensor_cmp(want, got)
+    assert max_diff < 1e-3 or max_ratio <= 1e-3, (max_ratio, max_diff, run.info())

@@ -1,0 +1,238 @@
+"""GPU parity for the bandwidth-bound Saber ops (pool / softmax / eltwise / activation /
+scale / layout+quant transforms / depthwise conv) against the CPU oracle.
+Integer results must be bit-exact; fp32 pooling / eltwise are bit-exact too (same operation
+order); softmax / activation use the reference's 1e-5 default (test_saber_base.h:501)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POOL_CASES = [
+    # n, h, w, c, window, pad, stride, global
+    (2, 112, 112, 64, 3, 0, 2, False),   # ResNet stem pool (ceil mode 112 -> 56)
+    (1, 24, 24, 32, 2, 0, 2, False),     # VGG pool
+    (3, 21, 21, 16, 3, 1, 2, False),
+    (2, 13, 13, 16, 3, 1, 1, False),
+    (2, 7, 7, 2048, 7, 0, 1, True),      # global average
+    (1, 12, 36, 48, 3, 1, 3, False),
+]
+
+
+def _pool(dtype, case, ptype, x):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    lib = A.load()
+    n, h, w, c, win, pad, stride, glob = case
+    d = A.PoolDesc()
+    d.dtype, d.type, d.n, d.h, d.w, d.c = dtype, ptype, n, h, w, c
+    d.window_h = d.window_w = win
+    d.pad_h = d.pad_w = pad
+    d.stride_h = d.stride_w = stride
+    d.global_pooling = int(glob)
+    oh, ow = C.c_int32(), C.c_int32()
+    A.check(lib.b200_pool_out_hw(C.byref(d), C.byref(oh), C.byref(ow)))
+    xd = dev(x)
+    out = torch.zeros((n, oh.value, ow.value, c), dtype=xd.dtype, device="cuda")
+    A.check(lib.b200_pool_run(C.byref(d), ptr(xd), ptr(out), stream_ptr()), "pool")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", POOL_CASES)
+@pytest.mark.parametrize("ptype", [1, 2, 3])
+def test_pool_f32(case, ptype, oracle):
+    from anakin_b200 import saber_abi as A
+    n, h, w, c, win, pad, stride, glob = case
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-100, 100, (n, h, w, c)).astype(np.float32)
+    want = oracle.pool_f32(x, (win, win), (pad, pad), (stride, stride), ptype, nhwc=True, global_pooling=glob)
+    got = _pool(A.FLOAT, case, ptype, x)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("case", POOL_CASES)
+@pytest.mark.parametrize("ptype", [1, 2, 3])
+@pytest.mark.parametrize("unsigned", [False, True])
+def test_pool_int8(case, ptype, unsigned, oracle):
+    from anakin_b200 import saber_abi as A
+    n, h, w, c, win, pad, stride, glob = case
+    rng = np.random.default_rng(11)
+    x = (rng.integers(0, 256, (n, h, w, c)).astype(np.uint8) if unsigned
+         else rng.integers(-128, 128, (n, h, w, c)).astype(np.int8))
+    want = oracle.pool_s8_nhwc(x, (win, win), (pad, pad), (stride, stride), ptype, global_pooling=glob)
+    got = _pool(A.UINT8 if unsigned else A.INT8, case, ptype, x)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("rows,len_", [(1, 1000), (8, 1000), (32, 1000), (3, 10), (5, 4097)])
+def test_softmax(rows, len_, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-10, 10, (rows, len_)).astype(np.float32)
+    want = oracle.softmax_f32(x, rows, len_, 1)
+    xd = dev(x)
+    out = torch.empty_like(xd)
+    A.check(A.load().b200_softmax_run(ptr(xd), ptr(out), rows, len_, 1, stream_ptr()), "softmax")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    mr, md = oracle.tensor_cmp(want, got)
+    assert md < 1e-5 or mr <= 1e-5, (mr, md)
+    np.testing.assert_allclose(got.sum(axis=1), 1.0, rtol=1e-5)
+
+
+def test_softmax_inner(oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-5, 5, (3, 21, 7)).astype(np.float32)
+    want = oracle.softmax_f32(x, 3, 21, 7)
+    xd = dev(x)
+    out = torch.empty_like(xd)
+    A.check(A.load().b200_softmax_run(ptr(xd), ptr(out), 3, 21, 7, stream_ptr()))
+    torch.cuda.synchronize()
+    mr, md = oracle.tensor_cmp(want, out.cpu().numpy())
+    assert md < 1e-5 or mr <= 1e-5
+
+
+@pytest.mark.parametrize("op", [1, 2, 3])
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("count", [7, 4096, 100003])
+def test_eltwise_f32(op, relu, count, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-100, 100, count).astype(np.float32)
+    b = rng.uniform(-100, 100, count).astype(np.float32)
+    want = oracle.eltwise_f32(a, b, op, 0.7, -1.3, relu)
+    ad, bd = dev(a), dev(b)
+    out = torch.empty_like(ad)
+    A.check(A.load().b200_eltwise_run(A.FLOAT, A.FLOAT, A.FLOAT, op, ptr(ad), ptr(bd), ptr(out), count,
+                                      0.7, -1.3, int(relu), stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("ua,ub,uo", [(False, False, False), (True, False, True), (True, True, True)])
+@pytest.mark.parametrize("count", [16, 999, 65536])
+def test_eltwise_int8(ua, ub, uo, count, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(6)
+    mk = lambda u: (rng.integers(0, 256, count).astype(np.uint8) if u else rng.integers(-128, 128, count).astype(np.int8))
+    a, b = mk(ua), mk(ub)
+    dt = lambda u: A.UINT8 if u else A.INT8
+    want = oracle.eltwise_sum_q8(a, b, 0.61, 0.43, dt(uo), relu=True)
+    ad, bd = dev(a), dev(b)
+    out = torch.zeros(count, dtype=torch.uint8 if uo else torch.int8, device="cuda")
+    A.check(A.load().b200_eltwise_run(dt(ua), dt(ub), dt(uo), 2, ptr(ad), ptr(bd), ptr(out), count,
+                                      0.61, 0.43, 1, stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("act", [1, 2, 3, 4, 5])
+def test_activation(act, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-6, 6, 10007).astype(np.float32)
+    want = oracle.activation_f32(x, act, 0.25, 1.5)
+    xd = dev(x)
+    out = torch.empty_like(xd)
+    A.check(A.load().b200_activation_run(A.FLOAT, act, ptr(xd), ptr(out), x.size, 0.25, 1.5, stream_ptr()))
+    torch.cuda.synchronize()
+    mr, md = oracle.tensor_cmp(want, out.cpu().numpy())
+    assert md < 1e-5 or mr <= 1e-5, (mr, md)
+
+
+def test_scale(oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-3, 3, (50, 24)).astype(np.float32)
+    w = rng.uniform(0.5, 2, 24).astype(np.float32)
+    b = rng.uniform(-1, 1, 24).astype(np.float32)
+    want = oracle.scale_f32(x, 50, 24, 1, w, b)
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    out = torch.empty_like(xd)
+    A.check(A.load().b200_scale_run(A.FLOAT, ptr(xd), ptr(out), 50, 24, ptr(wd), ptr(bd), stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 224, 224), (1, 3, 17, 9), (2, 40, 5, 7)])
+@pytest.mark.parametrize("odt", ["f32", "s8", "u8", "f16"])
+def test_nchw_to_nhwc_and_back(shape, odt, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    n, c, h, w = shape
+    rng = np.random.default_rng(10)
+    x = rng.uniform(-1, 1, shape).astype(np.float32)
+    if odt == "u8":
+        x = np.abs(x)
+    c_pad = (c + 15) // 16 * 16
+    scale = np.float32(np.abs(x).max() / 127.0)
+    xt = np.transpose(x, (0, 2, 3, 1))
+    if odt == "f32":
+        dtc, tdt, inv = A.FLOAT, torch.float32, 1.0
+        want = xt
+    elif odt == "f16":
+        dtc, tdt, inv = A.HALF, torch.float16, 1.0
+        want = xt.astype(np.float16)
+    elif odt == "s8":
+        dtc, tdt, inv = A.INT8, torch.int8, float(np.float32(1.0) / scale)
+        want = oracle.quant_fp32_s8(xt, scale)
+    else:
+        dtc, tdt = A.UINT8, torch.uint8
+        inv = float(np.float32(1.0) / (scale * np.float32(127.0 / 255.0)))
+        want = oracle.quant_fp32_u8(xt, scale)
+    xd = dev(x)
+    out = torch.full((n, h, w, c_pad), 77, dtype=tdt, device="cuda")
+    A.check(A.load().b200_nchw_to_nhwc(ptr(xd), ptr(out), dtc, n, c, h, w, c_pad, inv, 0, stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    np.testing.assert_array_equal(got[..., :c], want)
+    assert (got[..., c:] == 0).all()
+    # and back (dequantise)
+    back = torch.zeros((n, c, h, w), dtype=torch.float32, device="cuda")
+    A.check(A.load().b200_nhwc_to_nchw(ptr(out), dtc, ptr(back), n, c, h, w, c_pad, 1.0, stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(back.cpu().numpy(), np.transpose(want.astype(np.float32), (0, 3, 1, 2)))
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_dwconv_f32(stride, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(12)
+    n, h, w, c = 2, 28, 28, 32
+    x = rng.uniform(-1, 1, (n, h, w, c)).astype(np.float32)
+    wt = rng.uniform(-1, 1, (c, 1, 3, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, c).astype(np.float32)
+    want = oracle.conv_f32_nhwc(x, wt, b, group=c, stride=(stride, stride), pad=(1, 1), relu=True)
+    d = A.ConvDesc()
+    d.math, d.in_dtype, d.out_dtype, d.res_dtype = A.MATH_TF32, A.FLOAT, A.FLOAT, -1
+    d.n, d.h, d.w, d.c, d.k, d.ldc, d.r, d.s = n, h, w, c, c, c, 3, 3
+    d.pad_h = d.pad_w = 1
+    d.stride_h = d.stride_w = stride
+    d.dil_h = d.dil_w = 1
+    d.relu = 1
+    wrsc = np.ascontiguousarray(np.transpose(wt[:, 0], (1, 2, 0)))
+    xd, wd, bd = dev(x), dev(wrsc), dev(b)
+    out = torch.zeros(want.shape, dtype=torch.float32, device="cuda")
+    A.check(A.load().b200_dwconv_run(C.byref(d), ptr(xd), ptr(wd), ptr(bd), None, ptr(out), stream_ptr()))
+    torch.cuda.synchronize()
+    mr, md = oracle.tensor_cmp(want, out.cpu().numpy())
+    assert md < 1e-3 or mr <= 1e-3
