@@ -1,0 +1,359 @@
+// Net / Worker implementation -- see net.h for the reference mapping.
+#include "net.h"
+
+#include <set>
+
+namespace anakin {
+
+using namespace saber;
+using graph::GraphCore;
+using graph::NodePtr;
+
+NetCore::NetCore() {}
+
+NetCore::~NetCore() {
+    drop_cuda_graph();
+    _exec.clear();
+    _owned.clear();
+    if (_stream) cudaStreamDestroy(_stream);
+}
+
+void NetCore::drop_cuda_graph() {
+    if (_graph_exec) { cudaGraphExecDestroy(_graph_exec); _graph_exec = nullptr; }
+    if (_graph) { cudaGraphDestroy(_graph); _graph = nullptr; }
+}
+
+void NetCore::set_use_cuda_graph(bool v) {
+    _use_cuda_graph = v;
+    if (!v) drop_cuda_graph();
+}
+
+namespace {
+
+bool op_supports_int8(const std::string& op) {
+    // who gets an INT8 kernel at all (ANAKIN_REGISTER_OP_HELPER(..., INT8))
+    static const std::set<std::string> s = {
+        "Convolution", "ConvRelu", "ConvBatchnorm", "ConvBatchnormScale", "ConvBatchnormScaleRelu", "ConvScale",
+        "ConvScaleRelu", "ConvEltwise", "Dense", "Pooling", "Eltwise", "EltwiseRelu", "Split", "Input"};
+    return s.count(op) != 0;
+}
+
+}  // namespace
+
+Status NetCore::init(GraphCore& graph, Precision precision, int device) {
+    if (device >= 0) {
+        if (cudaSetDevice(device) != cudaSuccess) return Status::ANAKINFAIL("cudaSetDevice failed");
+        _device = device;
+    } else {
+        cudaGetDevice(&_device);
+    }
+    if (!b200_device_ok(_device))
+        return Status::ANAKINFAIL("device is not an sm_100 (B200) GPU: no kernel of this build can run (no CPU fallback)");
+    if (!graph.is_optimized()) {
+        Status st = graph.Optimize();
+        if (!st) return st;
+    }
+    _precision = precision;
+    if (!_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking));
+    _ctx = Context<NV>(_device, _stream);
+    drop_cuda_graph();
+    _exec.clear(); _owned.clear(); _node_tensor.clear(); _eager_runs = 0;
+    _in_names = graph.get_ins();
+    _out_names = graph.get_outs();
+    const char* env = getenv("B200_ANAKIN_CUDA_GRAPH");
+    if (env && env[0] == '0') _use_cuda_graph = false;
+
+    // ---- 1. operators, precision per node (net.cpp:230-288, calibrator_factory.h:155-174)
+    struct Built {
+        NodePtr node;
+        ops::OperatorPtr op;
+        bool int8 = false;
+    };
+    std::vector<Built> built;
+    std::map<std::string, size_t> index;
+    for (auto& nm : graph.get_nodes_in_order()) {
+        NodePtr node = graph[nm];
+        Precision p = precision;
+        if (precision == Precision::INT8) {
+            const bool wants_int8 = node->bit_type == AK_INT8 || (node->bit_type == AK_INVALID && op_supports_int8(node->op));
+            p = wants_int8 && op_supports_int8(node->op) ? Precision::INT8 : Precision::FP32;
+        }
+        ops::OperatorBase* raw = ops::create_operator(node->op, p);
+        if (!raw && p == Precision::INT8) { p = Precision::FP32; raw = ops::create_operator(node->op, p); }
+        if (!raw) return Status::ANAKINFAIL("operator " + node->op + " (node " + nm + ") is not supported by this build");
+        Built b;
+        b.node = node;
+        b.op.reset(raw);
+        b.int8 = (p == Precision::INT8);
+        b.op->BindParam(node);
+        Status st = b.op->InitParam();
+        if (!st) return Status::ANAKINFAIL("InitParam(" + nm + "): " + st.info());
+        index[nm] = built.size();
+        built.push_back(b);
+    }
+
+    // ---- 2. one tensor per producing node; alias ops share their input's tensor
+    auto real_consumers = [&](const std::string& nm) {
+        std::vector<size_t> out;
+        std::vector<std::string> stack = {nm};
+        while (!stack.empty()) {
+            std::string cur = stack.back(); stack.pop_back();
+            for (auto& t : built[index[cur]].node->outs) {
+                const Built& c = built[index[t]];
+                if (c.op->is_alias() && c.node->op != "Output") stack.push_back(t);
+                else out.push_back(index[t]);
+            }
+        }
+        return out;
+    };
+    for (auto& b : built) {
+        const std::string& nm = b.node->name;
+        if (b.op->is_alias() && b.node->op != "Input") {
+            if (b.node->ins.empty()) return Status::ANAKINFAIL("alias op without input: " + nm);
+            _node_tensor[nm] = _node_tensor[b.node->ins[0]];
+            continue;
+        }
+        auto t = std::make_shared<DTensor>();
+        // dtype / layout / scale of the edge (net.h:228-260, calibrator_parse.cpp:82-128)
+        DataType dt = AK_FLOAT;
+        LayoutType layout = b.node->op == "Input" ? Layout_NCHW : Layout_NHWC;
+        std::vector<size_t> cons = real_consumers(nm);
+        bool consumer_needs_float = false;
+        bool all_cons_int8 = !cons.empty();
+        for (size_t ci : cons) {
+            const std::string& cop = built[ci].node->op;
+            if (cop == "Softmax" || cop == "Output") consumer_needs_float = true;
+            if (!built[ci].int8 || cop == "Output") all_cons_int8 = false;
+        }
+        if (b.node->op == "Input") {
+            dt = AK_FLOAT;
+        } else if (precision == Precision::INT8 && b.int8 && all_cons_int8) {
+            int sgn = b.op->output_signedness();
+            if (sgn < 0) {
+                DTensor* in0 = _node_tensor[b.node->ins[0]];
+                dt = in0->get_dtype();
+                if (dt != AK_INT8 && dt != AK_UINT8) dt = AK_INT8;
+            } else {
+                dt = sgn ? AK_UINT8 : AK_INT8;
+            }
+        } else if (precision == Precision::FP16 && !consumer_needs_float) {
+            dt = AK_HALF;
+        }
+        Shape s({1, 1, 1, 1}, layout);
+        t->re_alloc(s, dt);
+        t->set_scale(graph.node_out_scale(nm));
+        _owned[nm] = t;
+        _node_tensor[nm] = t.get();
+    }
+
+    // ---- 3. shapes, init (weights packed once per op), memory
+    for (auto& b : built) {
+        ExecOp e;
+        e.name = b.node->name;
+        e.op_name = b.node->op;
+        e.op = b.op;
+        for (auto& in : b.node->ins) e.ins.push_back(_node_tensor[in]);
+        e.outs.push_back(_node_tensor[b.node->name]);
+        Status st = b.op->InferShape(e.ins, e.outs);
+        if (!st) return Status::ANAKINFAIL("InferShape(" + e.name + "): " + st.info());
+        if (!b.op->is_alias()) {
+            if (e.outs[0]->storage_bytes())
+                CUDA_CHECK(cudaMemsetAsync(e.outs[0]->mutable_data(), 0, e.outs[0]->storage_bytes(), _stream));
+            st = b.op->Init(_ctx, e.ins, e.outs);
+            if (!st) return Status::ANAKINFAIL("Init(" + e.name + "): " + st.info());
+            _exec.push_back(e);
+        }
+    }
+    _act_bytes = 0;
+    for (auto& kv : _owned) _act_bytes += kv.second->storage_bytes();
+    CUDA_CHECK(cudaStreamSynchronize(_stream));
+    return Status::OK();
+}
+
+void NetCore::run_eager() {
+    for (auto& e : _exec) (*e.op)(_ctx, e.ins, e.outs);
+}
+
+void NetCore::prediction() {
+    cudaSetDevice(_device);
+    if (_graph_exec) {
+        CUDA_CHECK(cudaGraphLaunch(_graph_exec, _stream));
+        return;
+    }
+    if (_use_cuda_graph && _eager_runs >= 1) {
+        // static shapes: capture the whole op sequence once (one eager run has already built
+        // every plan / tensor map), then replay it.
+        cudaError_t e = cudaStreamBeginCapture(_stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            run_eager();
+            e = cudaStreamEndCapture(_stream, &_graph);
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&_graph_exec, _graph, 0);
+            if (e == cudaSuccess) {
+                CUDA_CHECK(cudaGraphLaunch(_graph_exec, _stream));
+                return;
+            }
+        }
+        fprintf(stderr, "[anakin_b200] CUDA graph capture failed (%s); staying eager\n", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        drop_cuda_graph();
+        _use_cuda_graph = false;
+    }
+    run_eager();
+    ++_eager_runs;
+}
+
+std::vector<float> NetCore::profile_ops(int iters) {
+    cudaSetDevice(_device);
+    const size_t n = _exec.size();
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+    std::vector<float> ms(n, 0.f);
+    for (int it = 0; it < iters + 1; ++it) {  // first pass is a warm-up
+        for (size_t i = 0; i < n; ++i) {
+            CUDA_CHECK(cudaEventRecord(ev[2 * i], _stream));
+            (*_exec[i].op)(_ctx, _exec[i].ins, _exec[i].outs);
+            CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], _stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(_stream));
+        if (it == 0) continue;
+        for (size_t i = 0; i < n; ++i) {
+            float t = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+            ms[i] += t / iters;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return ms;
+}
+
+void NetCore::sync() { CUDA_CHECK(cudaStreamSynchronize(_stream)); }
+
+NetCore::DTensor* NetCore::get_in(const std::string& in_name) { return get_tensor_from_node(in_name); }
+NetCore::DTensor* NetCore::get_out(const std::string& out_name) { return get_tensor_from_node(out_name); }
+
+NetCore::DTensor* NetCore::get_tensor_from_node(const std::string& node_name) {
+    auto it = _node_tensor.find(node_name);
+    return it == _node_tensor.end() ? nullptr : it->second;
+}
+
+std::vector<NetCore::DTensor*> NetCore::get_in_list() {
+    std::vector<DTensor*> v;
+    for (auto& n : _in_names) v.push_back(get_in(n));
+    return v;
+}
+std::vector<NetCore::DTensor*> NetCore::get_out_list() {
+    std::vector<DTensor*> v;
+    for (auto& n : _out_names) v.push_back(get_out(n));
+    return v;
+}
+
+std::vector<std::string> NetCore::get_exec_order() const {
+    std::vector<std::string> v;
+    for (auto& e : _exec) v.push_back(e.name + ":" + e.op_name);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+WorkerCore::WorkerCore(const std::string& model_path, Precision precision, int thread_num)
+    : _model_path(model_path), _precision(precision), _thread_num(thread_num) {}
+
+WorkerCore::~WorkerCore() {
+    {
+        std::lock_guard<std::mutex> lk(_mu);
+        _stop = true;
+    }
+    _cv.notify_all();
+    for (auto& t : _threads) if (t.joinable()) t.join();
+}
+
+void WorkerCore::launch() {
+    for (int i = 0; i < _thread_num; ++i) _threads.emplace_back([this, i] { thread_main(i); });
+}
+
+void WorkerCore::thread_main(int tid) {
+    const int device = _devices.empty() ? -1 : _devices[tid % _devices.size()];
+    NetCore net;
+    {
+        // first thread loads + optimises the graph, every thread builds its own Net (worker.cpp:13-39)
+        std::lock_guard<std::mutex> lk(_graph_mu);
+        if (!_graph) {
+            auto g = std::make_shared<graph::GraphCore>();
+            Status st = g->load(_model_path);
+            if (st) {
+                for (auto& kv : _reshape) g->Reshape(kv.first, kv.second);
+                st = g->Optimize();
+            }
+            if (!st) { _init_errors.push_back(st.info()); return; }
+            _graph = g;
+        }
+        Status st = net.init(*_graph, _precision, device);
+        if (!st) { _init_errors.push_back(st.info()); return; }
+        if (_inputs.empty()) _inputs = net.get_in_names();
+        if (_outputs.empty()) _outputs = net.get_out_names();
+    }
+    while (true) {
+        std::shared_ptr<Task> task;
+        {
+            std::unique_lock<std::mutex> lk(_mu);
+            _cv.wait(lk, [this] { return _stop || !_tasks.empty(); });
+            if (_stop && _tasks.empty()) return;
+            task = _tasks.front();
+            _tasks.pop_front();
+        }
+        std::vector<std::vector<float>> outs;
+        try {
+            for (size_t i = 0; i < _inputs.size() && i < task->ins.size(); ++i) {
+                NetCore::DTensor* d = net.get_in(_inputs[i]);
+                const size_t bytes = std::min(d->storage_bytes(), task->ins[i].size() * sizeof(float));
+                CUDA_CHECK(cudaMemcpyAsync(d->mutable_data(), task->ins[i].data(), bytes, cudaMemcpyHostToDevice, net.stream()));
+            }
+            net.prediction();
+            for (auto& on : _outputs) {
+                NetCore::DTensor* d = net.get_out(on);
+                std::vector<float> h(d->storage_bytes() / sizeof(float));
+                CUDA_CHECK(cudaMemcpyAsync(h.data(), d->data(), d->storage_bytes(), cudaMemcpyDeviceToHost, net.stream()));
+                outs.push_back(std::move(h));
+            }
+            net.sync();
+            task->done.set_value(std::move(outs));
+        } catch (...) {
+            task->done.set_exception(std::current_exception());
+        }
+    }
+}
+
+std::future<std::vector<std::vector<float>>> WorkerCore::sync_prediction(const std::vector<std::vector<float>>& host_ins) {
+    auto task = std::make_shared<Task>();
+    task->ins = host_ins;
+    auto fut = task->done.get_future();
+    {
+        std::lock_guard<std::mutex> lk(_mu);
+        _tasks.push_back(task);
+    }
+    _cv.notify_one();
+    return fut;
+}
+
+void WorkerCore::async_prediction(const std::vector<std::vector<float>>& host_ins) {
+    auto fut = sync_prediction(host_ins);
+    std::lock_guard<std::mutex> lk(_mu);
+    _async_que.push_back(std::move(fut));
+}
+
+std::vector<std::vector<float>> WorkerCore::async_get_result() {
+    std::future<std::vector<std::vector<float>>> fut;
+    {
+        std::lock_guard<std::mutex> lk(_mu);
+        if (_async_que.empty()) return {};
+        fut = std::move(_async_que.front());
+        _async_que.pop_front();
+    }
+    return fut.get();
+}
+
+bool WorkerCore::empty() {
+    std::lock_guard<std::mutex> lk(_mu);
+    return _async_que.empty();
+}
+
+}  // namespace anakin

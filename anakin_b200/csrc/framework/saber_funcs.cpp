@@ -1,0 +1,310 @@
+// ConvEngine: host-side preparation of one fused convolution for the C-ABI tcgen05 plan.
+// Replaces, for target NV, the host halves of the reference's
+//   SaberConv2D<NV,*>::{init,create,dispatch,trans_weights}  saber/funcs/impl/cuda/saber_conv.cpp:17-585
+//   SaberConvEltwise / SaberConv2DPooling / SaberFc           saber_conv_eltwise.cpp, saber_conv_pooling.cpp, saber_fc.cu
+// INT8 numerics follow the x86 Saber path (the designated oracle):
+//   weights   per-output-channel s_w = max|w|/127, truncating cast   x86_utils.h:293-323
+//   scales    kernel/jit_avx512_core_x8s8s32x_conv.cpp:226-255 (scale), :55-62 (bias), :174-192 (sum)
+#include "saber_funcs.h"
+
+#include <cuda_fp16.h>
+
+namespace anakin {
+namespace saber {
+
+struct ConvEngine::Impl {
+    Spec spec;
+    bool ready = false;
+    // change detection
+    Shape in_shape, out_shape;
+    DataType in_dtype = AK_INVALID, out_dtype = AK_INVALID, res_dtype = AK_INVALID;
+    std::vector<float> in_scale, out_scale;
+    float res_scale = 0.f;
+    const void* weights_id = nullptr;
+
+    b200_conv_desc_t desc;
+    b200_conv_plan_t* plan = nullptr;
+    DeviceBuffer w_dev, bias_dev, scale_dev;
+    bool need_in_transform = false;
+    Tensor<NV> in_scratch;
+    float in_inv_scale = 1.f;
+    bool depthwise = false;
+    Tensor<NV> conv_out_scratch;
+    b200_pool_desc_t pool_desc;
+
+    ~Impl() {
+        if (plan) b200_conv_plan_destroy(plan);
+    }
+};
+
+ConvEngine::ConvEngine() : _p(new Impl()) {}
+ConvEngine::~ConvEngine() { delete _p; }
+
+b200_pool_desc_t make_pool_desc(const Tensor<NV>& in, const PoolingParam<NV>& p) {
+    b200_pool_desc_t d;
+    memset(&d, 0, sizeof(d));
+    d.dtype = in.get_dtype();
+    d.type = p.pooling_type;
+    d.n = in.num(); d.h = in.height(); d.w = in.width(); d.c = in.channel_stored();
+    d.window_h = p.window_h; d.window_w = p.window_w;
+    d.pad_h = p.pad_h; d.pad_w = p.pad_w;
+    d.stride_h = p.stride_h; d.stride_w = p.stride_w;
+    d.global_pooling = p.global_pooling ? 1 : 0;
+    d.floor_as_conv = p.cmp_out_shape_floor_as_conv ? 1 : 0;
+    return d;
+}
+
+static SaberStatus upload(DeviceBuffer& buf, const void* src, size_t bytes) {
+    if (buf.re_alloc(bytes, false) != SaberSuccess) return SaberOutOfMem;
+    if (bytes && cudaMemcpy(buf.ptr, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return SaberUnKownError;
+    return SaberSuccess;
+}
+
+SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Tensor<NV>* residual,
+                                Tensor<NV>& out, Context<NV>& ctx) {
+    Impl& P = *_p;
+    (void)ctx;
+    const float res_scale = spec.residual_scale;
+    const DataType res_dt = residual ? residual->get_dtype() : AK_INVALID;
+    if (P.ready && P.in_shape == in.valid_shape() && P.out_shape == out.valid_shape() &&
+        P.in_dtype == in.get_dtype() && P.out_dtype == out.get_dtype() && P.res_dtype == res_dt &&
+        P.in_scale == in.get_scale() && P.out_scale == out.get_scale() && P.res_scale == res_scale &&
+        P.weights_id == spec.weights->data() && P.spec.relu == spec.relu && P.spec.neg_slope == spec.neg_slope)
+        return SaberSuccess;
+    P.ready = false;
+    P.spec = spec;
+    if (P.plan) { b200_conv_plan_destroy(P.plan); P.plan = nullptr; }
+
+    const DataType op = spec.op_dtype;
+    const int math = op == AK_INT8 ? B200_MATH_I8 : (op == AK_HALF ? B200_MATH_F16 : B200_MATH_TF32);
+
+    // ---- 1. the tensor the conv kernel reads (NHWC in the op's operand type)
+    const Tensor<NV>* cin = &in;
+    P.need_in_transform = false;
+    if (in.get_layout() == Layout_NCHW && !(in.height() == 1 && in.width() == 1 && in.get_dtype() != AK_FLOAT)) {
+        if (in.get_dtype() != AK_FLOAT) return SaberUnImplError;
+        // graph-input case: fp32 NCHW -> NHWC operand type (the reference quantises inside conv too:
+        // saber_conv.cpp:341-381 conv_calibrate_fp32_int8_c4 / x86_utils.h:325-347)
+        DataType sdt = op == AK_INT8 ? AK_INT8 : (op == AK_HALF ? AK_HALF : AK_FLOAT);
+        Shape s = in.valid_shape();
+        s.set_layout(Layout_NHWC);
+        if (P.in_scratch.re_alloc(s, sdt) != SaberSuccess) return SaberOutOfMem;
+        CUDA_CHECK(cudaMemset(P.in_scratch.mutable_data(), 0, P.in_scratch.storage_bytes()));
+        if (op == AK_INT8) {
+            if (in.get_scale().empty()) return SaberInvalidValue;
+            P.in_inv_scale = 1.f / in.get_scale()[0];
+            P.in_scratch.set_scale(in.get_scale());
+        } else {
+            P.in_inv_scale = 1.f;
+        }
+        P.need_in_transform = true;
+        cin = &P.in_scratch;
+    }
+    const DataType cin_dt = cin->get_dtype();
+    if (op == AK_INT8 && !(cin_dt == AK_INT8 || cin_dt == AK_UINT8)) return SaberUnImplError;
+    if (op == AK_HALF && cin_dt != AK_HALF) return SaberUnImplError;
+    if (op == AK_FLOAT && cin_dt != AK_FLOAT) return SaberUnImplError;
+    if (out.get_layout() != Layout_NHWC && !(out.height() == 1 && out.width() == 1)) return SaberInvalidValue;
+
+    // ---- 2. geometry
+    b200_conv_desc_t& d = P.desc;
+    memset(&d, 0, sizeof(d));
+    d.math = math;
+    d.in_dtype = cin_dt;
+    d.res_dtype = residual ? residual->get_dtype() : -1;
+    d.relu = spec.relu ? 1 : 0;
+    d.neg_slope = spec.neg_slope;
+    d.sum_scale = 1.f;
+    const int cs = cin->channel_stored();
+    int c_real;                 // real input channels per filter tap as the weights see them
+    std::vector<int> col_map;   // fc: weight column (NCHW flatten) for every stored K position, -1 = pad
+    if (spec.is_fc) {
+        const int H = cin->height(), W = cin->width(), C = cin->channel();
+        d.n = cin->num(); d.h = 1; d.w = 1; d.c = H * W * cs;
+        d.r = d.s = 1; d.stride_h = d.stride_w = 1; d.dil_h = d.dil_w = 1;
+        c_real = d.c;
+        if (spec.c_per_group != C * H * W) return SaberInvalidValue;
+        col_map.assign(d.c, -1);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+                for (int c = 0; c < C; ++c) col_map[(y * W + x) * cs + c] = (c * H + y) * W + x;
+    } else {
+        d.n = cin->num(); d.h = cin->height(); d.w = cin->width(); d.c = cs;
+        d.r = spec.r; d.s = spec.s;
+        d.pad_h = spec.pad_h; d.pad_w = spec.pad_w;
+        d.stride_h = spec.stride_h; d.stride_w = spec.stride_w;
+        d.dil_h = spec.dil_h; d.dil_w = spec.dil_w;
+        c_real = spec.c_per_group;
+    }
+    d.k = spec.k;
+    P.depthwise = !spec.is_fc && spec.group > 1 && spec.group == cin->channel() && spec.c_per_group == 1 &&
+                  spec.k == spec.group;
+    if (spec.group != 1 && !P.depthwise) return SaberUnImplError;
+    if (!spec.is_fc && !P.depthwise && c_real != cin->channel()) return SaberInvalidValue;
+
+    // ---- 3. where the conv writes
+    Tensor<NV>* cout = &out;
+    if (spec.has_pool) {
+        Shape s({d.n, spec.k, conv_out_size(d.h, d.pad_h, d.dil_h, d.r, d.stride_h),
+                 conv_out_size(d.w, d.pad_w, d.dil_w, d.s, d.stride_w)}, Layout_NHWC);
+        if (P.conv_out_scratch.re_alloc(s, out.get_dtype()) != SaberSuccess) return SaberOutOfMem;
+        CUDA_CHECK(cudaMemset(P.conv_out_scratch.mutable_data(), 0, P.conv_out_scratch.storage_bytes()));
+        P.conv_out_scratch.set_scale(out.get_scale());
+        cout = &P.conv_out_scratch;
+        P.pool_desc = make_pool_desc(P.conv_out_scratch, spec.pool);
+    }
+    d.out_dtype = cout->get_dtype();
+    d.ldc = cout->channel_stored();
+    if (residual && residual->channel_stored() != d.ldc) return SaberInvalidValue;
+
+    // ---- 4. weights, bias, scales
+    const float* w = static_cast<const float*>(spec.weights->data());
+    const size_t per_k = static_cast<size_t>(spec.is_fc ? spec.c_per_group : spec.c_per_group * spec.r * spec.s);
+    const bool has_bias = spec.bias && spec.bias->valid_size() >= spec.k && spec.bias->data();
+    const float* b = has_bias ? static_cast<const float*>(spec.bias->data()) : nullptr;
+    std::vector<float> bias_f(spec.k, 0.f), scale_f;
+
+    if (P.depthwise) {
+        if (op == AK_INT8) return SaberUnImplError;
+        // weights [c][1][r][s] -> [r][s][c_stored]
+        const int RS = spec.r * spec.s;
+        if (op == AK_HALF) {
+            std::vector<__half> ww(static_cast<size_t>(RS) * cs, __float2half(0.f));
+            for (int c = 0; c < spec.k; ++c)
+                for (int i = 0; i < RS; ++i) ww[static_cast<size_t>(i) * cs + c] = __float2half(w[c * RS + i]);
+            if (upload(P.w_dev, ww.data(), ww.size() * sizeof(__half)) != SaberSuccess) return SaberOutOfMem;
+        } else {
+            std::vector<float> ww(static_cast<size_t>(RS) * cs, 0.f);
+            for (int c = 0; c < spec.k; ++c)
+                for (int i = 0; i < RS; ++i) ww[static_cast<size_t>(i) * cs + c] = w[c * RS + i];
+            if (upload(P.w_dev, ww.data(), ww.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+        }
+        std::vector<float> bb(cs, 0.f);
+        for (int i = 0; i < spec.k; ++i) bb[i] = b ? b[i] : 0.f;
+        if (upload(P.bias_dev, bb.data(), bb.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+        d.c = cs; d.k = cs; d.ldc = cout->channel_stored();
+    } else {
+        // operand-typed KCRS image (fc: permuted into the stored-K order), then the tcgen05 pack
+        const int es = op == AK_INT8 ? 1 : (op == AK_HALF ? 2 : 4);
+        const int c_img = spec.is_fc ? d.c : c_real;
+        const int RS = spec.is_fc ? 1 : spec.r * spec.s;
+        std::vector<uint8_t> img(static_cast<size_t>(spec.k) * c_img * RS * es, 0);
+        std::vector<float> w_scale(spec.k, 1.f);
+        for (int oc = 0; oc < spec.k; ++oc) {
+            const float* wr = w + static_cast<size_t>(oc) * per_k;
+            float sw = 1.f;
+            if (op == AK_INT8) {
+                float mx = 0.f;
+                for (size_t i = 0; i < per_k; ++i) { float a = fabsf(wr[i]); mx = a > mx ? a : mx; }
+                sw = mx / 127.f;
+                if (sw == 0.f) sw = 1.f;
+                w_scale[oc] = sw;
+            }
+            for (int ci = 0; ci < c_img; ++ci) {
+                for (int rs = 0; rs < RS; ++rs) {
+                    float v;
+                    if (spec.is_fc) {
+                        const int col = col_map[ci];
+                        if (col < 0) continue;
+                        v = wr[col];
+                    } else {
+                        v = wr[static_cast<size_t>(ci) * RS + rs];
+                    }
+                    const size_t o = (static_cast<size_t>(oc) * c_img + ci) * RS + rs;
+                    if (op == AK_INT8) reinterpret_cast<int8_t*>(img.data())[o] = static_cast<int8_t>(v / sw);
+                    else if (op == AK_HALF) reinterpret_cast<__half*>(img.data())[o] = __float2half(v);
+                    else reinterpret_cast<float*>(img.data())[o] = v;
+                }
+            }
+        }
+        const size_t pbytes = b200_conv_packed_weight_bytes(&d);
+        if (pbytes == 0) return SaberInvalidValue;
+        std::vector<uint8_t> packed(pbytes);
+        SaberStatus st = static_cast<SaberStatus>(b200_conv_pack_weights(&d, img.data(), c_img, packed.data()));
+        if (st != SaberSuccess) return st;
+        if (upload(P.w_dev, packed.data(), pbytes) != SaberSuccess) return SaberOutOfMem;
+
+        if (op == AK_INT8) {
+            if (cin->get_scale().empty()) return SaberInvalidValue;
+            const float in_scale = cin->get_scale()[0];
+            const float u = 127.f / 255.f;
+            const DataType odt = cout->get_dtype();
+            float out_scale = 1.f;
+            if (odt != AK_FLOAT) {
+                if (cout->get_scale().empty()) return SaberInvalidValue;
+                out_scale = cout->get_scale()[0];
+            }
+            scale_f.assign(spec.k, 1.f);
+            for (int i = 0; i < spec.k; ++i) {
+                float s;
+                if (cin_dt == AK_INT8 && odt == AK_INT8) s = (w_scale[i] * in_scale) / out_scale;
+                else if (cin_dt == AK_UINT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale * u) / (out_scale * u);
+                else if (cin_dt == AK_UINT8 && odt == AK_INT8) s = (w_scale[i] * in_scale * u) / out_scale;
+                else if (cin_dt == AK_UINT8 && odt == AK_FLOAT) s = w_scale[i] * in_scale * u;
+                else if (cin_dt == AK_INT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale) / (out_scale * u);
+                else s = w_scale[i] * in_scale;
+                scale_f[i] = s;
+                const float inv = (cin_dt == AK_UINT8) ? (1.f / (w_scale[i] * in_scale * u))
+                                                       : (1.f / (w_scale[i] * in_scale));
+                bias_f[i] = b ? b[i] * inv : 0.f;
+            }
+            if (residual) {
+                const DataType rdt = residual->get_dtype();
+                if (rdt == AK_INT8 && odt == AK_UINT8) d.sum_scale = res_scale * (255.f / 127.f) / out_scale;
+                else if (rdt == AK_UINT8 && odt == AK_INT8) d.sum_scale = res_scale * (127.f / 255.f) / out_scale;
+                else d.sum_scale = res_scale / out_scale;
+            }
+            if (upload(P.scale_dev, scale_f.data(), scale_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+        } else {
+            for (int i = 0; i < spec.k; ++i) bias_f[i] = b ? b[i] : 0.f;
+            d.sum_scale = 1.f;  // eltwise coeff 1 (ConvEltwise fuses only Add with coeff {1,1})
+        }
+        if (upload(P.bias_dev, bias_f.data(), bias_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+
+        SaberStatus pst = static_cast<SaberStatus>(b200_conv_plan_create(
+            &d, P.w_dev.ptr, static_cast<const float*>(P.bias_dev.ptr),
+            op == AK_INT8 ? static_cast<const float*>(P.scale_dev.ptr) : nullptr, &P.plan));
+        if (pst != SaberSuccess) return pst;
+    }
+
+    P.in_shape = in.valid_shape();
+    P.out_shape = out.valid_shape();
+    P.in_dtype = in.get_dtype();
+    P.out_dtype = out.get_dtype();
+    P.res_dtype = res_dt;
+    P.in_scale = in.get_scale();
+    P.out_scale = out.get_scale();
+    P.res_scale = res_scale;
+    P.weights_id = spec.weights->data();
+    P.ready = true;
+    return SaberSuccess;
+}
+
+SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Tensor<NV>& out,
+                            cudaStream_t stream) {
+    Impl& P = *_p;
+    if (!P.ready) return SaberNotInitialized;
+    const void* src = in.data();
+    if (P.need_in_transform) {
+        SaberStatus st = static_cast<SaberStatus>(b200_nchw_to_nhwc(
+            static_cast<const float*>(in.data()), P.in_scratch.mutable_data(), P.in_scratch.get_dtype(), in.num(),
+            in.channel(), in.height(), in.width(), P.in_scratch.channel_stored(), P.in_inv_scale, 0, stream));
+        if (st != SaberSuccess) return st;
+        src = P.in_scratch.data();
+    }
+    void* dst = P.spec.has_pool ? P.conv_out_scratch.mutable_data() : out.mutable_data();
+    SaberStatus st;
+    if (P.depthwise) {
+        st = static_cast<SaberStatus>(b200_dwconv_run(&P.desc, src, P.w_dev.ptr,
+                                                      static_cast<const float*>(P.bias_dev.ptr), nullptr, dst, stream));
+    } else {
+        st = static_cast<SaberStatus>(b200_conv_plan_run(P.plan, src, residual ? residual->data() : nullptr, dst, stream));
+    }
+    if (st != SaberSuccess) return st;
+    if (P.spec.has_pool)
+        st = static_cast<SaberStatus>(b200_pool_run(&P.pool_desc, P.conv_out_scratch.data(), out.mutable_data(), stream));
+    return st;
+}
+
+}  // namespace saber
+}  // namespace anakin

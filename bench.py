@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: ResNet-50 INT8 images/s through Net<NV,INT8>::prediction().
+
+  python bench.py --gpus 1 --steps K --warmup W            (driver contract; N>1 under torchrun)
+  python bench.py --impl reference ...                      (the CPU path timed on the host cores)
+
+A "step" = one prediction() over one batch of synthetic 224x224 images per GPU.  At N=1 the
+workload is BASELINE.json configs[1]: ResNet-50 INT8 batch=8 on 1xB200.  Multi-GPU = one full
+replica per GPU (batch-sharded requests, weak scaling), model bytes broadcast from rank 0 over
+NCCL, no collective in the per-step path.
+
+JSON line keys: see DESIGN.md section "Measurement".  `value` is device-timed with the inputs
+resident in HBM and an L2 flush between timed steps; `e2e` goes through the public API with
+pinned host buffers (H2D + prediction + D2H every step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per image (BASELINE.md section 2 / SURVEY.md section 8d)
+GOP_PER_IMAGE = {"resnet50": 7.716, "resnet101": 15.140, "vgg16": 30.94, "mobilenet_v1": 1.137, "tiny_resnet": 0.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--precision", default="int8", choices=["int8", "fp32", "fp16"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, warmup=0):
+    """The CPU path (oracle port of the x86 Saber semantics) on the host cores; bounded sample."""
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    from oracle import pyoracle as O
+    O.build(ref=False)
+    hw = 32 if model == "tiny_resnet" else 224
+    g = modelzoo.build(model, batch=1, precision=precision if precision == "int8" else "fp32")
+    scales = None
+    if precision == "int8":
+        scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration(model).items()}
+    per_img = max(0.05, GOP_PER_IMAGE.get(model, 1.0) / 25.0)  # ~25 GOP/s expected on 8 cores
+    if steps is None:
+        n_img = max(1, min(batch, int(budget_s / per_img / 3)))
+        steps, warmup = 3, 0
+    else:
+        n_img = max(1, min(batch, int(120.0 / max(1, steps + warmup) / per_img)))
+    x = modelzoo.synthetic_input(n_img, hw)
+    run = (lambda: W.run_int8(g, x, scales)) if precision == "int8" else (lambda: W.run_fp32(g, x))
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    return {"value": n_img * steps / dt, "unit": "images/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "%d step(s) x %d image(s) of %s %s via oracle/model_walker.py (x86-semantics restatement, "
+                      "OpenMP, not Anakin's MKL/xbyak build)" % (steps, n_img, model, precision),
+            "ms_per_step": dt / steps * 1e3, "images_per_step": n_img}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_oracle_images_per_s(args.model, args.precision, args.batch, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "%s %s images/sec" % (args.model, args.precision.upper()),
+            "value": r["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8" if args.precision == "int8" else ("f32" if args.precision == "fp32" else "f16"),
+            "data": "synthetic",
+            "config": {"workload": "%s %s, CPU oracle port, %d image(s)/step" % (args.model, args.precision, r["images_per_step"]),
+                       "batch_per_step": r["images_per_step"]},
+            "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from anakin_b200 import anakin_bin, api, modelzoo, saber_abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sab = saber_abi.load()
+    model, prec, batch = args.model, args.precision, args.batch
+    hw = 32 if model == "tiny_resnet" else 224
+
+    # ---- model bytes: built on rank 0, broadcast to every replica over NCCL (NVLink)
+    if rank == 0:
+        blob = anakin_bin.dumps(modelzoo.build(model, batch=batch, precision=prec if prec == "int8" else "fp32"))
+    else:
+        blob = b""
+    bcast_ms = 0.0
+    if world > 1:
+        n = torch.tensor([len(blob)], dtype=torch.int64, device="cuda")
+        dist.broadcast(n, 0)
+        buf = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dist.broadcast(buf, 0)
+        torch.cuda.synchronize()
+        bcast_ms = (time.perf_counter() - t0) * 1e3
+        blob = bytes(buf.cpu().numpy())
+    G = api.Graph.from_bytes(blob)
+    G.ResetBatchSize("input_0", batch)
+    G.Optimize()
+    net = api.Net(G, prec, device=local_rank)
+    in_name, out_name = net.in_names[0], net.out_names[0]
+    stream = torch.cuda.ExternalStream(net.stream, device=torch.device("cuda", local_rank))
+
+    x = modelzoo.synthetic_input(batch, hw, seed=42 + rank * batch)
+    x_pinned = torch.from_numpy(x).pin_memory()
+    out_info = net.tensor_info(out_name)
+    out_pinned = torch.empty(out_info["bytes"] // 4, dtype=torch.float32).pin_memory()
+    net.set_input_ptr(in_name, x_pinned.data_ptr(), x_pinned.numel())
+    l0 = sab.b200_launch_count()
+    net.prediction()   # eager (builds tensor maps)
+    net.sync()
+    launches_per_step = int(sab.b200_launch_count() - l0)
+    net.prediction()   # captures the CUDA graph
+    net.sync()
+    top1 = net.get_output().argmax(1)
+
+    flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed steps, inputs resident, L2 flushed between steps (outside the event pairs)
+    for _ in range(max(3, args.warmup)):
+        net.prediction()
+    net.sync()
+    sampler = ClockSampler(local_rank)
+    K = args.steps
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    if rank == 0:
+        sampler.start()
+    with torch.cuda.stream(stream):
+        for i in range(K):
+            if flush is not None:
+                flush.zero_()
+            starts[i].record(stream)
+            net.prediction()
+            stops[i].record(stream)
+    barrier()
+    per_step = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+    total_ms = float(per_step.sum())
+
+    # ---- back-to-back (warm L2) replay, for context
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(K):
+            net.prediction()
+        e1.record(stream)
+    barrier()
+    warm_ms = e0.elapsed_time(e1)
+
+    # ---- end to end through the public API: pinned host in, H2D + prediction + D2H every step
+    h2d = x_pinned.numel() * 4
+    d2h = out_info["bytes"]
+    for _ in range(3):
+        net.set_input_ptr(in_name, x_pinned.data_ptr(), x_pinned.numel())
+        net.prediction()
+        net.read_tensor_into(out_name, out_pinned.data_ptr(), d2h)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(K):
+            net.set_input_ptr(in_name, x_pinned.data_ptr(), x_pinned.numel())   # H2D (async, net stream)
+            net.prediction()
+            net.read_tensor_into(out_name, out_pinned.data_ptr(), d2h)          # D2H + sync: result on host
+        e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-op device times (eager, event pair per op) -> roofline of the dominant kernel
+    prof = net.profile_ops(5)
+    conv_ms = sum(ms for _, op, ms in prof if op.startswith("Conv") or op == "Dense")
+    all_ms = sum(ms for _, _, ms in prof)
+
+    if world > 1:
+        t = torch.tensor([total_ms, warm_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, warm_ms, e2e_ms = [float(v) for v in t.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    P = peaks()
+    images = K * batch * world
+    value = images / (total_ms / 1e3)
+    gop_step = GOP_PER_IMAGE.get(model, 0.0) * batch
+    conv_launches = sum(1 for _, op, _ in prof if op.startswith("Conv") or op == "Dense")
+    # tensor roof: kind::i8 runs at twice the bf16 rate; the measured bf16 GEMM peak x2 is the denominator
+    mult = 2.0 if prec == "int8" else (1.0 if prec == "fp16" else 0.5)
+    peak_tops = P["bf16_tflops"] * mult
+    achieved_tops = (gop_step / 1e3) / (conv_ms / 1e3) if conv_ms > 0 else 0.0
+    line = {
+        "metric": "%s %s images/sec" % ({"resnet50": "ResNet-50", "resnet101": "ResNet-101", "vgg16": "VGG16",
+                                         "mobilenet_v1": "MobileNet-v1"}.get(model, model), prec.upper()),
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8" if prec == "int8" else ("f32" if prec == "fp32" else "f16"), "data": "synthetic",
+        "config": {"workload": "%s %s batch=%d per GPU, %dxB200, Net<NV,%s>::prediction() (CUDA-graph replay)" %
+                               (model, prec.upper(), batch, world, prec.upper()),
+                   "batch_per_gpu": batch, "global_batch": batch * world, "input": "fp32 NCHW [N,3,%d,%d]" % (hw, hw),
+                   "l2": "flushed (256 MiB memset) between timed steps" if flush is not None else "not flushed",
+                   "parallelism": "replica per GPU, batch-sharded; model bytes NCCL-broadcast (%.1f ms)" % bcast_ms},
+        "gpu_launches": launches_per_step * K,
+        "launches_per_step": launches_per_step,
+        "value_warm_l2": images / (warm_ms / 1e3),
+        "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p99": float(np.percentile(per_step, 99)),
+        "e2e": {"value": images / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K},
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % conv_launches,
+                     "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s" if prec == "int8" else "TFLOP/s",
+                     "frac": achieved_tops / peak_tops if peak_tops else None, "traffic": None,
+                     "peak_source": "%s bf16 dense x%.1f" % (P["src"], mult),
+                     "kernel_ms_per_step": conv_ms, "all_ops_ms_per_step_eager": all_ms,
+                     "kernel_share_of_step": conv_ms / all_ms if all_ms else None},
+        "clocks": clocks,
+        "top1_first": [int(v) for v in top1[:4]],
+        "cuda_graph": net.cuda_graph_active(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_oracle_images_per_s(model, prec, batch)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -129,9 +129,12 @@ ORACLE_API void oracle_conv_f32_nchw(const float* src, const float* weights, con
     }
 }
 
-/* Same computation on NHWC tensors (src [n,h,w,c], dst [n,ho,wo,k], weights KCRS),
- * accumulating in the same (ic, kh, kw) order -- used by the model-level walker so that
- * no layout shuffles are needed between layers. */
+/* Same computation on NHWC tensors (src [n,h,w,c], dst [n,ho,wo,k], weights KCRS) for the
+ * model-level walker and the CPU baseline: x86 epilogue order
+ * (saber/funcs/impl/x86/saber_im2col_conv.cpp:161-214): gemm (+ beta*prev) -> +bias -> relu.
+ * The dot product runs in (kh, kw, ic) order with ic contiguous and vectorised -- the
+ * im2col+GEMM order of the x86 path rather than the naive oracle's (ic, kh, kw); the two
+ * differ by float re-association only (tests/test_oracle.py bounds it at 1e-5 relative). */
 ORACLE_API void oracle_conv_f32_nhwc(const float* src, const float* weights, const float* bias,
                                      const float* residual, float* dst, int n, int c, int h, int w,
                                      int k, int group, int kernel_h, int kernel_w, int stride_h,
@@ -140,39 +143,45 @@ ORACLE_API void oracle_conv_f32_nhwc(const float* src, const float* weights, con
     const int out_h = oracle_conv_out_size(h, pad_h, dil_h, kernel_h, stride_h);
     const int out_w = oracle_conv_out_size(w, pad_w, dil_w, kernel_w, stride_w);
     const int out_c_group = k / group, in_c_group = c / group;
-#pragma omp parallel for collapse(3) schedule(static)
+    /* weights re-laid as [k][kh][kw][ic] so the inner loop is contiguous in both operands */
+    const size_t wsz = (size_t)k * in_c_group * kernel_h * kernel_w;
+    float* wt = (float*)malloc(wsz * sizeof(float));
+    for (int oc = 0; oc < k; ++oc)
+        for (int ic = 0; ic < in_c_group; ++ic)
+            for (int kh = 0; kh < kernel_h; ++kh)
+                for (int kw = 0; kw < kernel_w; ++kw)
+                    wt[(((size_t)oc * kernel_h + kh) * kernel_w + kw) * in_c_group + ic] =
+                        weights[(((size_t)oc * in_c_group + ic) * kernel_h + kh) * kernel_w + kw];
+#pragma omp parallel for collapse(2) schedule(static)
     for (int in_ = 0; in_ < n; ++in_) {
         for (int oh = 0; oh < out_h; ++oh) {
             for (int ow = 0; ow < out_w; ++ow) {
-                for (int g = 0; g < group; ++g) {
-                    for (int oc = 0; oc < out_c_group; ++oc) {
-                        const int och = g * out_c_group + oc;
-                        const size_t out_idx = (((size_t)in_ * out_h + oh) * out_w + ow) * k + och;
-                        /* x86 order (saber_im2col_conv.cpp:161-214): gemm (+ beta*prev) -> +bias -> relu */
-                        float acc = residual ? residual[out_idx] * beta : 0.f;
-                        for (int ic = 0; ic < in_c_group; ++ic) {
-                            for (int kh = 0; kh < kernel_h; ++kh) {
-                                const int ih = oh * stride_h - pad_h + kh * dil_h;
-                                if (ih < 0 || ih >= h) continue;
-                                for (int kw = 0; kw < kernel_w; ++kw) {
-                                    const int iw = ow * stride_w - pad_w + kw * dil_w;
-                                    if (iw < 0 || iw >= w) continue;
-                                    const size_t iidx =
-                                        (((size_t)in_ * h + ih) * w + iw) * c + g * in_c_group + ic;
-                                    const size_t widx =
-                                        (((size_t)och * in_c_group + ic) * kernel_h + kh) * kernel_w + kw;
-                                    acc += src[iidx] * weights[widx];
-                                }
-                            }
+                for (int och = 0; och < k; ++och) {
+                    const int g = och / out_c_group;
+                    const size_t out_idx = (((size_t)in_ * out_h + oh) * out_w + ow) * k + och;
+                    float acc = residual ? residual[out_idx] * beta : 0.f;
+                    for (int kh = 0; kh < kernel_h; ++kh) {
+                        const int ih = oh * stride_h - pad_h + kh * dil_h;
+                        if (ih < 0 || ih >= h) continue;
+                        for (int kw = 0; kw < kernel_w; ++kw) {
+                            const int iw = ow * stride_w - pad_w + kw * dil_w;
+                            if (iw < 0 || iw >= w) continue;
+                            const float* ip = src + (((size_t)in_ * h + ih) * w + iw) * c + g * in_c_group;
+                            const float* wp = wt + (((size_t)och * kernel_h + kh) * kernel_w + kw) * in_c_group;
+                            float part = 0.f;
+#pragma omp simd reduction(+ : part)
+                            for (int ic = 0; ic < in_c_group; ++ic) part += ip[ic] * wp[ic];
+                            acc += part;
                         }
-                        acc += flag_bias ? bias[och] : 0.f;
-                        if (flag_relu) acc = acc > 0.f ? acc : acc * neg_slope;
-                        dst[out_idx] = acc;
                     }
+                    acc += flag_bias ? bias[och] : 0.f;
+                    if (flag_relu) acc = acc > 0.f ? acc : acc * neg_slope;
+                    dst[out_idx] = acc;
                 }
             }
         }
     }
+    free(wt);
 }
 
 /* ------------------------------------------------------------------ int8 conv */
@@ -281,8 +290,10 @@ ORACLE_API void oracle_conv_s8_nhwc_x86(const void* src, int src_dtype, const in
                             const int8_t* wp = wt + (((size_t)oc * kernel_h + kh) * kernel_w + kw) * c;
                             int32_t part = 0;
                             if (src_dtype == DT_UINT8) {
+                                _Pragma("omp simd reduction(+ : part)")
                                 for (int ic = 0; ic < c; ++ic) part += (int32_t)src_u8[ibase + ic] * wp[ic];
                             } else {
+                                _Pragma("omp simd reduction(+ : part)")
                                 for (int ic = 0; ic < c; ++ic) part += (int32_t)src_s8[ibase + ic] * wp[ic];
                             }
                             acc += part;

@@ -1,0 +1,168 @@
+"""End-to-end GPU parity: Net<NV,P>::prediction() (C++ framework over the CUDA C ABI) against
+the model-level CPU oracle (oracle/model_walker.py) on the same seeded model and inputs.
+
+  FP32 : reference criterion (test_saber_base.h:470 / tensor_cmp_host) at 1e-3 on the
+         softmax output and on the logits.
+  INT8 : every int8 edge tensor bit-exact against the x86-semantics oracle, logits equal,
+         top-1 identical (BASELINE north_star: "exact top-1 class index for INT8").
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _build(name, batch, precision):
+    from anakin_b200 import anakin_bin, api, modelzoo
+    g = modelzoo.build(name, batch=batch, precision=precision)
+    G = api.Graph.from_bytes(anakin_bin.dumps(g))
+    G.ResetBatchSize("input_0", batch)
+    G.Optimize()
+    return g, G
+
+
+def _run(G, precision, x, graph=True):
+    from anakin_b200 import api
+    net = api.Net(G, precision)
+    if not graph:
+        net.set_cuda_graph(False)
+    net.set_input("input_0", x)
+    net.prediction()
+    net.sync()
+    return net
+
+
+def _valid(arr, info):
+    c = info["dims"][1]
+    return arr[..., :c] if info["layout"] == 9 else arr
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_tiny_resnet_fp32(batch, oracle):
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    g, G = _build("tiny_resnet", batch, "fp32")
+    x = modelzoo.synthetic_input(batch, 32)
+    want = W.run_fp32(g, x)["prob_out"]
+    net = _run(G, "fp32", x)
+    got = net.get_output()
+    mr, md = oracle.tensor_cmp(want, got)
+    assert md < 1e-3 or mr <= 1e-3, (mr, md)
+    assert (got.argmax(1) == want.argmax(1)).all()
+    # second + third call exercise the CUDA-graph replay path and must give the same answer
+    net.prediction(); net.prediction(); net.sync()
+    assert net.cuda_graph_active()
+    np.testing.assert_array_equal(net.get_output(), got)
+
+
+@pytest.mark.parametrize("batch", [1, 4])
+def test_tiny_resnet_int8_bit_exact(batch, oracle):
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    g, G = _build("tiny_resnet", batch, "int8")
+    scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration("tiny_resnet").items()}
+    x = modelzoo.synthetic_input(batch, 32)
+    want, trace = W.run_int8(g, x, scales, return_intermediate=True)
+    net = _run(G, "int8", x)
+    checked = 0
+    for name, op in net.exec_order():
+        if name not in trace:
+            continue
+        arr, info = net.read_tensor(name)
+        w_arr, w_dt, w_scale = trace[name]
+        assert info["dtype"] == w_dt, (name, op, info, w_dt)
+        got = _valid(arr, info)
+        if w_arr.ndim == 4 and got.shape != w_arr.shape:
+            got = got.reshape(w_arr.shape)
+        if w_dt == 1:
+            mr, md = oracle.tensor_cmp(w_arr, got)
+            assert md < 1e-5 or mr <= 1e-5, (name, op, mr, md)
+        else:
+            bad = np.argwhere(got != w_arr)
+            assert bad.shape[0] == 0, "%s (%s): %d mismatching codes, first %s" % (name, op, bad.shape[0], bad[:3])
+        checked += 1
+    assert checked >= 10
+    got = net.get_output()
+    assert (got.argmax(1) == want["prob_out"].argmax(1)).all()
+    mr, md = oracle.tensor_cmp(want["prob_out"], got)
+    assert md < 1e-5 or mr <= 1e-5
+
+
+def test_tiny_resnet_golden_fixture():
+    """Committed oracle outputs (tools/make_golden.py) -- does not need /root/reference."""
+    from anakin_b200 import modelzoo
+    gold = np.load(os.path.join(GOLD, "tiny_resnet_golden.npz"))
+    g, G = _build("tiny_resnet", 4, "int8")
+    net = _run(G, "int8", modelzoo.synthetic_input(4, 32))
+    got = net.get_output()
+    assert (got.argmax(1) == gold["top1_int8"]).all()
+    np.testing.assert_allclose(got, gold["prob_int8"], rtol=1e-4, atol=1e-6)
+    g, G = _build("tiny_resnet", 4, "fp32")
+    net = _run(G, "fp32", modelzoo.synthetic_input(4, 32))
+    np.testing.assert_allclose(net.get_output(), gold["prob_fp32"], rtol=2e-3, atol=1e-5)
+
+
+def test_resnet50_int8_golden_and_oracle(oracle):
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    batch = 2
+    gold = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
+    g, G = _build("resnet50", batch, "int8")
+    x = modelzoo.synthetic_input(batch)
+    net = _run(G, "int8", x)
+    got = net.get_output()
+    assert (got.argmax(1) == gold["top1_int8"][:batch]).all()
+    logits, info = net.read_tensor("fc1000")
+    np.testing.assert_array_equal(_valid(logits, info).reshape(batch, -1), gold["logits_int8"][:batch])
+    # full-depth bit-exactness of a late int8 edge against a fresh oracle run
+    scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration("resnet50").items()}
+    want, trace = W.run_int8(g, x, scales, return_intermediate=True)
+    for node in ("conv1", "res2a_branch2c", "res3d_branch2c", "res5c_branch2c", "pool5"):
+        arr, info = net.read_tensor(node)
+        np.testing.assert_array_equal(_valid(arr, info).reshape(trace[node][0].shape), trace[node][0], err_msg=node)
+    assert net.launched_ops() <= 60
+
+
+def test_resnet50_fp32_golden():
+    from anakin_b200 import modelzoo
+    gold = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
+    g, G = _build("resnet50", 1, "fp32")
+    net = _run(G, "fp32", modelzoo.synthetic_input(1))
+    got = net.get_output()
+    from oracle import pyoracle as O
+    mr, md = O.tensor_cmp(gold["prob_fp32"][:1], got)
+    assert md < 1e-3 or mr <= 1e-3, (mr, md)
+    assert got.argmax(1)[0] == gold["top1_fp32"][0]
+
+
+def test_graph_save_reload_runs_identically():
+    """Graph::save of the optimised graph reloads and runs (net_exec_test.cpp:107 flow)."""
+    from anakin_b200 import api, modelzoo
+    g, G = _build("tiny_resnet", 2, "int8")
+    x = modelzoo.synthetic_input(2, 32)
+    a = _run(G, "int8", x).get_output()
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "opt.anakin.bin")
+        G.save(p)
+        G2 = api.Graph.from_file(p)
+        G2.Optimize()
+        b = _run(G2, "int8", x).get_output()
+    np.testing.assert_array_equal(a, b)
+
+
+def test_eager_equals_cuda_graph():
+    from anakin_b200 import modelzoo
+    g, G = _build("tiny_resnet", 2, "int8")
+    x = modelzoo.synthetic_input(2, 32)
+    a = _run(G, "int8", x, graph=False)
+    a.prediction(); a.sync()
+    assert not a.cuda_graph_active()
+    b = _run(G, "int8", x, graph=True)
+    b.prediction(); b.sync()
+    assert b.cuda_graph_active()
+    np.testing.assert_array_equal(a.get_output(), b.get_output())
