@@ -209,11 +209,14 @@ public:
         if (x.get_dtype() != AK_FLOAT || out[0]->get_dtype() != AK_FLOAT) return SaberUnImplError;
         // logical NCHW axes -> (outer, axis, inner) of the stored layout
         const bool flat = x.height() == 1 && x.width() == 1;
+        _in_pitch = _out_pitch = 0;
         if (p.axis == 1 && (flat || x.get_layout() == Layout_NHWC)) {
-            if (x.channel_stored() != x.channel()) return SaberUnImplError;
+            // channels are innermost: one row per pixel, row pitch = stored (padded) channels
             _outer = x.num() * x.height() * x.width();
             _len = x.channel();
             _inner = 1;
+            _in_pitch = x.channel_stored();
+            _out_pitch = out[0]->channel_stored();
         } else if (x.get_layout() == Layout_NCHW) {
             _outer = static_cast<int>(x.count_valid(0, p.axis));
             _len = x.valid_shape()[p.axis];
@@ -224,13 +227,18 @@ public:
         return SaberSuccess;
     }
     SaberStatus dispatch(const TensorVec& in, TensorVec& out, SoftmaxParam<T>& p) override {
+        if (_in_pitch)
+            return static_cast<SaberStatus>(b200_softmax_rows(static_cast<const float*>(in[0]->data()),
+                                                              static_cast<float*>(out[0]->mutable_data()), _outer,
+                                                              _len, _in_pitch, _out_pitch,
+                                                              this->_ctx->get_compute_stream()));
         return static_cast<SaberStatus>(b200_softmax_run(static_cast<const float*>(in[0]->data()),
                                                          static_cast<float*>(out[0]->mutable_data()), _outer,
                                                          _len, _inner, this->_ctx->get_compute_stream()));
     }
 
 private:
-    int _outer = 0, _len = 0, _inner = 1;
+    int _outer = 0, _len = 0, _inner = 1, _in_pitch = 0, _out_pitch = 0;
 };
 
 template <typename T, DataType OpDtype>

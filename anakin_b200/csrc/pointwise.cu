@@ -205,12 +205,12 @@ __global__ void pool_q8_kernel(const uint4* __restrict__ in, uint4* __restrict__
 // ------------------------------------------------------------------ softmax
 // inner == 1: one warp per row, shuffle reductions (reference uses one thread per row).
 __global__ void softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
-                                    int len) {
+                                    int len, int in_pitch, int out_pitch) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const float* x = in + 1ll * warp * len;
-    float* y = out + 1ll * warp * len;
+    const float* x = in + 1ll * warp * in_pitch;
+    float* y = out + 1ll * warp * out_pitch;
     float mx = -3.402823466e+38f;
     for (int i = lane; i < len; i += 32) mx = fmaxf(mx, __ldg(x + i));
 #pragma unroll
@@ -556,14 +556,22 @@ int b200_pool_run(const b200_pool_desc_t* d, const void* in, void* out, void* st
     return check_launch("pool");
 }
 
+int b200_softmax_rows(const float* in, float* out, int32_t rows, int32_t len, int32_t in_pitch,
+                      int32_t out_pitch, void* stream) {
+    if (!in || !out || rows <= 0 || len <= 0 || in_pitch < len || out_pitch < len) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    const int block = 128;  // 4 rows per CTA
+    const unsigned grid = (static_cast<unsigned>(rows) * 32 + block - 1) / block;
+    softmax_rows_kernel<<<grid, block, 0, S(stream)>>>(in, out, rows, len, in_pitch, out_pitch);
+    return check_launch("softmax");
+}
+
 int b200_softmax_run(const float* in, float* out, int32_t outer, int32_t axis_size, int32_t inner,
                      void* stream) {
     if (!in || !out || outer <= 0 || axis_size <= 0 || inner <= 0) return B200_INVALID_VALUE;
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
     if (inner == 1) {
-        const int block = 128;  // 4 rows per CTA
-        const unsigned grid = (static_cast<unsigned>(outer) * 32 + block - 1) / block;
-        softmax_rows_kernel<<<grid, block, 0, S(stream)>>>(in, out, outer, axis_size);
+        return b200_softmax_rows(in, out, outer, axis_size, axis_size, axis_size, stream);
     } else {
         const int block = 128;
         softmax_strided_kernel<<<(outer * inner + block - 1) / block, block, 0, S(stream)>>>(

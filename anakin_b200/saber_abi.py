@@ -60,6 +60,7 @@ SYMBOLS = {
     "b200_pool_out_hw": (C.c_int, [C.POINTER(PoolDesc), C.POINTER(_i), C.POINTER(_i)]),
     "b200_pool_run": (C.c_int, [C.POINTER(PoolDesc), _vp, _vp, _vp]),
     "b200_softmax_run": (C.c_int, [_vp, _vp, _i, _i, _i, _vp]),
+    "b200_softmax_rows": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_eltwise_run": (C.c_int, [_i, _i, _i, _i, _vp, _vp, _vp, _sz, _f, _f, _i, _vp]),
     "b200_activation_run": (C.c_int, [_i, _i, _vp, _vp, _sz, _f, _f, _vp]),
     "b200_scale_run": (C.c_int, [_i, _vp, _vp, _sz, _i, _vp, _vp, _vp]),

@@ -206,6 +206,9 @@ B200_API int b200_pool_run(const b200_pool_desc_t* d, const void* in, void* out,
  * ------------------------------------------------------------------------ */
 B200_API int b200_softmax_run(const float* in, float* out, int32_t outer, int32_t axis_size, int32_t inner,
                      void* stream);
+/* Row softmax with explicit row pitches (elements): NHWC tensors whose channel count is padded. */
+B200_API int b200_softmax_rows(const float* in, float* out, int32_t rows, int32_t len, int32_t in_pitch,
+                      int32_t out_pitch, void* stream);
 
 /* ------------------------------------------------------------------------
  * Eltwise (2 inputs) with optional fused relu. Replaces SaberEltwise<NV,*>
