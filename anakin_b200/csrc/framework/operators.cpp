@@ -14,6 +14,15 @@ using namespace saber;
 using graph::Node;
 
 #define GET_PARAMETER(type, name) (_node->get_attr<type>(#name))
+// In Init() a failing Saber call is reported through Status (with node name and SaberStatus text)
+// instead of aborting; operator() keeps the reference's SABER_CHECK abort.
+#define SABER_INIT_CHECK(call)                                                                     \
+    do {                                                                                           \
+        ::anakin::saber::SaberStatus _s = static_cast<::anakin::saber::SaberStatus>(call);         \
+        if (_s != ::anakin::saber::SaberSuccess)                                                   \
+            return Status::ANAKINFAIL(std::string(#call) + " -> " + b200_status_string(_s) +      \
+                                      " (node " + _node->name + ", op " + _node->op + ")");       \
+    } while (0)
 
 namespace {
 
@@ -197,11 +206,11 @@ public:
             // beta = scale of the residual edge, beta_type its dtype (fusion_ops/conv_eltwise.cpp:182-188)
             _conv_elt.conv_param.beta = ins[1]->get_scale().empty() ? 1.f : ins[1]->get_scale()[0];
             _conv_elt.conv_param.beta_type = ins[1]->get_dtype();
-            SABER_CHECK(_f_elt.init(ins, outs, _conv_elt, SPECIFY, SABER_IMPL, ctx));
+            SABER_INIT_CHECK(_f_elt.init(ins, outs, _conv_elt, SPECIFY, SABER_IMPL, ctx));
         } else if (_has_pool) {
-            SABER_CHECK(_f_pool.init(ins, outs, _conv_pool, SPECIFY, SABER_IMPL, ctx));
+            SABER_INIT_CHECK(_f_pool.init(ins, outs, _conv_pool, SPECIFY, SABER_IMPL, ctx));
         } else {
-            SABER_CHECK(_f_conv.init(ins, outs, _conv, SPECIFY, SABER_IMPL, ctx));
+            SABER_INIT_CHECK(_f_conv.init(ins, outs, _conv, SPECIFY, SABER_IMPL, ctx));
         }
         return Status::OK();
     }
@@ -245,7 +254,7 @@ public:
                                                                             : Status::ANAKINFAIL("Dense InferShape");
     }
     Status Init(OpContext<NV>& ctx, const TensorVec& ins, TensorVec& outs) override {
-        SABER_CHECK(_f.init(ins, outs, _param, SPECIFY, SABER_IMPL, ctx));
+        SABER_INIT_CHECK(_f.init(ins, outs, _param, SPECIFY, SABER_IMPL, ctx));
         return Status::OK();
     }
     void operator()(OpContext<NV>& ctx, const TensorVec& ins, TensorVec& outs) override {
@@ -268,7 +277,7 @@ public:
                                                                             : Status::ANAKINFAIL("InferShape failed");
     }
     Status Init(OpContext<NV>& ctx, const TensorVec& ins, TensorVec& outs) override {
-        SABER_CHECK(_f.init(ins, outs, _param, SPECIFY, SABER_IMPL, ctx));
+        SABER_INIT_CHECK(_f.init(ins, outs, _param, SPECIFY, SABER_IMPL, ctx));
         return Status::OK();
     }
     void operator()(OpContext<NV>& ctx, const TensorVec& ins, TensorVec& outs) override {

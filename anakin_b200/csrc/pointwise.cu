@@ -202,6 +202,111 @@ __global__ void pool_q8_kernel(const uint4* __restrict__ in, uint4* __restrict__
     }
 }
 
+// Large windows (global average pooling: 7x7 = 49 taps): one WARP per output vector. The lanes
+// fetch 32 window taps at a time in parallel (the thread-per-output kernel above serialises 49
+// dependent L2 round trips), then every lane folds them in the reference's (kh, kw) order through
+// shuffles, so the result is bit-identical to the sequential kernels.
+template <int MODE>  // 0 f32 (4 ch), 1 f16 (8 ch), 2 s8 (16 ch), 3 u8 (16 ch)
+__global__ void pool_warp_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolP p) {
+    constexpr int VEC = MODE == 0 ? 4 : (MODE == 1 ? 8 : 16);
+    const int cv = p.c / VEC;
+    const long long total = 1ll * p.n * p.oh * p.ow * cv;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * 1ll * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (1ll * gridDim.x * blockDim.x) >> 5;
+    for (long long idx = warp0; idx < total; idx += nwarps) {
+        const int v = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int ow = static_cast<int>(t % p.ow); t /= p.ow;
+        const int oh = static_cast<int>(t % p.oh);
+        const int n = static_cast<int>(t / p.oh);
+        int sh = oh * p.sh, eh = sh + p.wh;
+        int sw = ow * p.sw, ew = sw + p.ww;
+        if (MODE < 2 || p.ph > 0) { sh = (sh - p.ph) < 0 ? 0 : sh - p.ph; eh = (eh - p.ph) > p.h ? p.h : eh - p.ph; }
+        if (MODE < 2 || p.pw > 0) { sw = (sw - p.pw) < 0 ? 0 : sw - p.pw; ew = (ew - p.pw) > p.w ? p.w : ew - p.pw; }
+        if (eh > p.h) eh = p.h;
+        if (ew > p.w) ew = p.w;
+        const int ww = ew - sw, taps = (eh - sh) * ww;
+        float r[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) r[i] = 0.f;
+        for (int base = 0; base < taps; base += 32) {
+            const int mine = base + lane;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (mine < taps) {
+                const int kh = sh + mine / ww, kw = sw + mine % ww;
+                x = __ldg(in + ((1ll * n * p.h + kh) * p.w + kw) * cv + v);
+            }
+            const int cnt = min(32, taps - base);
+            for (int i = 0; i < cnt; ++i) {
+                uint4 y;
+                y.x = __shfl_sync(0xffffffffu, x.x, i); y.y = __shfl_sync(0xffffffffu, x.y, i);
+                y.z = __shfl_sync(0xffffffffu, x.z, i); y.w = __shfl_sync(0xffffffffu, x.w, i);
+                float f[VEC];
+                if (MODE == 0) {
+                    f[0] = __uint_as_float(y.x); f[1] = __uint_as_float(y.y);
+                    f[2] = __uint_as_float(y.z); f[3] = __uint_as_float(y.w);
+                } else if (MODE == 1) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { float2 q = __half22float2(h[j]); f[2 * j] = q.x; f[2 * j + 1] = q.y; }
+                } else {
+                    const uint32_t w[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                        f[j] = MODE == 3 ? static_cast<float>(b) : static_cast<float>(static_cast<int8_t>(b));
+                    }
+                }
+                const bool first = (base + i) == 0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if (first) r[j] = f[j];
+                    else if (p.type == B200_POOL_MAX) r[j] = r[j] >= f[j] ? r[j] : f[j];
+                    else r[j] = __fadd_rn(r[j], f[j]);
+                }
+            }
+        }
+        float d = 1.f;
+        if (p.type == B200_POOL_AVG_INCLUDE_PAD) {
+            if (MODE < 2) {
+                int bh = p.wh, bw = p.ww;
+                if (ew == p.w) { bw = (sw + p.ww >= p.w + p.pw) ? p.w + p.pw : sw + p.ww; bw -= sw; }
+                if (eh == p.h) { bh = (sh + p.wh >= p.h + p.ph) ? p.h + p.ph : sh + p.wh; bh -= sh; }
+                d = static_cast<float>(bh * bw);
+            } else {
+                d = static_cast<float>(p.wh * p.ww);
+            }
+        } else if (p.type == B200_POOL_AVG_EXCLUDE_PAD) {
+            d = static_cast<float>((ew - sw) * (eh - sh));
+        }
+        if (lane == 0) {
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (MODE == 0) {
+                const bool avg = p.type != B200_POOL_MAX;
+                o.x = __float_as_uint(avg ? __fdiv_rn(r[0], d) : r[0]); o.y = __float_as_uint(avg ? __fdiv_rn(r[1], d) : r[1]);
+                o.z = __float_as_uint(avg ? __fdiv_rn(r[2], d) : r[2]); o.w = __float_as_uint(avg ? __fdiv_rn(r[3], d) : r[3]);
+            } else if (MODE == 1) {
+                __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ho[j] = __floats2half2_rn(__fdiv_rn(r[2 * j], d), __fdiv_rn(r[2 * j + 1], d));
+            } else {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float q = (p.type == B200_POOL_MAX) ? r[j] : __fdiv_rn(r[j], d);
+                    uint32_t code;
+                    if (MODE == 3) asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(code) : "f"(q));
+                    else { int32_t sc; asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(sc) : "f"(q)); code = static_cast<uint32_t>(sc) & 0xffu; }
+                    w[j >> 2] |= (code & 0xffu) << (8 * (j & 3));
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            out[((1ll * n * p.oh + oh) * p.ow + ow) * cv + v] = o;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ softmax
 // inner == 1: one warp per row, shuffle reductions (reference uses one thread per row).
 __global__ void softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
@@ -531,25 +636,42 @@ int b200_pool_run(const b200_pool_desc_t* d, const void* in, void* out, void* st
     p.type = d->type;
     if (p.type < B200_POOL_MAX || p.type > B200_POOL_AVG_EXCLUDE_PAD) return B200_INVALID_VALUE;
     const int block = 256;
+    const bool big_window = p.wh * p.ww >= 16;
     if (d->dtype == B200_FLOAT) {
         if (d->c % 4) return B200_INVALID_VALUE;
         const long long total = 1ll * p.n * oh * ow * (d->c / 4);
-        pool_f32_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
-            static_cast<const float4*>(in), static_cast<float4*>(out), p);
+        if (big_window)
+            pool_warp_kernel<0><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
+                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+        else
+            pool_f32_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
+                static_cast<const float4*>(in), static_cast<float4*>(out), p);
     } else if (d->dtype == B200_HALF) {
         if (d->c % 8) return B200_INVALID_VALUE;
         const long long total = 1ll * p.n * oh * ow * (d->c / 8);
-        pool_f16_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
-            static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+        if (big_window)
+            pool_warp_kernel<1><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
+                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+        else
+            pool_f16_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
+                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
     } else if (d->dtype == B200_INT8 || d->dtype == B200_UINT8) {
         if (d->c % 16) return B200_INVALID_VALUE;
         const long long total = 1ll * p.n * oh * ow * (d->c / 16);
-        if (d->dtype == B200_UINT8)
+        if (big_window) {
+            if (d->dtype == B200_UINT8)
+                pool_warp_kernel<3><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
+                    static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            else
+                pool_warp_kernel<2><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
+                    static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+        } else if (d->dtype == B200_UINT8) {
             pool_q8_kernel<true><<<grid_for(total, block), block, 0, S(stream)>>>(
                 static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
-        else
+        } else {
             pool_q8_kernel<false><<<grid_for(total, block), block, 0, S(stream)>>>(
                 static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+        }
     } else {
         return B200_UNIMPL_ERROR;
     }

@@ -65,11 +65,15 @@ def test_conv_int8_bit_exact(case, variant, oracle):
     want = oracle.conv_s8_nhwc_x86(x, wq, bias, scale, residual=res, sum_scale=sum_scale,
                                    out_dtype=out_dtype, **kw)
     xin = pad_channels(x, c)
+    # output / residual rows are padded to a 16-byte multiple, as the framework's NHWC tensors are
+    ldc = (k + 15) // 16 * 16 if out_dtype != A.FLOAT else (k + 3) // 4 * 4
     run = ConvRunner(A.MATH_I8, xin.shape, A.UINT8 if in_unsigned else A.INT8, wq, bias, scale,
-                     out_dtype, res_dtype=(A.UINT8 if res is not None else -1), sum_scale=sum_scale, **kw)
-    got = run.run(dev(xin), dev(res) if res is not None else None)
+                     out_dtype, res_dtype=(A.UINT8 if res is not None else -1), sum_scale=sum_scale, ldc=ldc, **kw)
+    got = run.run(dev(xin), dev(pad_channels(res, ldc)) if res is not None else None)
     torch.cuda.synchronize()
     got = got.cpu().numpy()
+    assert (got[..., k:] == 0).all(), "padding channels must stay untouched"
+    got = got[..., :k]
     assert got.shape == want.shape
     if out_dtype == A.FLOAT:
         np.testing.assert_array_equal(got, want)
