@@ -76,8 +76,11 @@ struct ConvKParams {
 //   [ residual tile 128 x BN x res_es ]   TMA-prefetched during the main loop
 //   [ bias BN f32 | scale BN f32 ]        epilogue tables
 //   [ full[MAX] empty[MAX] tmem_full res_full | tmem ptr ]
-__host__ __device__ constexpr int stage_bytes(int bn) { return A_STAGE_BYTES + bn * STAGE_K_BYTES; }
-__host__ __device__ constexpr int tail_bytes(int bn) { return 2 * bn * 4 + (2 * MAX_STAGES + 2) * 8 + 16; }
+// x3 = error-compensated fp32: every stage also holds the A-low tile and the W-low tile.
+__host__ __device__ constexpr int stage_bytes(int bn, bool x3 = false) {
+    return (x3 ? 2 : 1) * (A_STAGE_BYTES + bn * STAGE_K_BYTES);
+}
+__host__ __device__ constexpr int tail_bytes(int bn) { return 2 * bn * 4 + (3 * MAX_STAGES + 2) * 8 + 16; }
 
 __device__ __forceinline__ uint32_t layout_type_for_chunk(int chunk) {
     return chunk == 128 ? 2u : (chunk == 64 ? 4u : (chunk == 32 ? 6u : 0u));
@@ -214,7 +217,15 @@ __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                   const ConvKParams p, const uint32_t idesc) {
-    constexpr int SB = stage_bytes(BN);
+    // KIND_TF32X3: fp32 operands split as x = hi + lo (hi = top 19 bits); D += Ahi*Whi + Alo*Whi + Ahi*Wlo
+    // keeps ~fp32 accuracy on the tf32 tensor pipe. The epilogue warps do the A split in shared
+    // memory while they would otherwise idle; W is split on the host at pack time.
+    constexpr bool X3 = (KIND == KIND_TF32X3);
+    constexpr int MK = X3 ? KIND_TF32 : KIND;
+    constexpr int SB = stage_bytes(BN, X3);
+    constexpr int A_LO_OFF = A_STAGE_BYTES;                          // X3 only
+    constexpr int B_OFF = X3 ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
+    constexpr int B_LO_OFF = B_OFF + BN * STAGE_K_BYTES;             // X3 only
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -224,7 +235,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float* scale_s = bias_s + BN;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(scale_s + BN);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
+    uint64_t* conv_bar = empty_bar + MAX_STAGES;   // X3: "A split done" per stage
+    uint64_t* tmem_full_bar = conv_bar + MAX_STAGES;
     uint64_t* res_full_bar = tmem_full_bar + 1;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full_bar + 1);
 
@@ -243,6 +255,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
+            mbar_init(&conv_bar[i], 128);
         }
         mbar_init(tmem_full_bar, 1);
         mbar_init(res_full_bar, 1);
@@ -291,9 +304,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int it = 0; it < num_stage_iters; ++it) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 const int nsub = min(subs_per_stage, p.KS - ks);
-                mbar_arrive_expect_tx(&full_bar[stage], nsub * (a_sub_bytes + b_sub_bytes));
+                mbar_arrive_expect_tx(&full_bar[stage], nsub * (a_sub_bytes + (X3 ? 2 : 1) * b_sub_bytes));
                 uint8_t* a_dst = smem + stage * SB;
-                uint8_t* b_dst = a_dst + A_STAGE_BYTES;
+                uint8_t* b_dst = a_dst + B_OFF;
                 for (int j = 0; j < nsub; ++j) {
                     // the padding k-step (ks == KS_real) re-reads tap (0,0); its weights are zero
                     const bool pad_step = ks >= p.KS_real;
@@ -302,6 +315,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                        base_w, base_h, n_img, static_cast<uint16_t>(ss * p.dil_w),
                                        static_cast<uint16_t>(rr * p.dil_h));
                     tma_load_2d(&map_b, &full_bar[stage], b_dst + j * b_sub_bytes, ks * p.chunk_el, n0);
+                    if (X3)  // the W-low image follows the W-high image (row offset K)
+                        tma_load_2d(&map_b, &full_bar[stage], a_dst + B_LO_OFF + j * b_sub_bytes, ks * p.chunk_el,
+                                    p.K + n0);
                     ++ks;
                     if (++cc == p.CC) {
                         cc = 0;
@@ -322,11 +338,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t phase = 0;
             uint32_t accum = 0;
             for (int it = 0; it < num_stage_iters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait(X3 ? &conv_bar[stage] : &full_bar[stage], phase);
                 tc_fence_after();
                 const int nsub = min(subs_per_stage, p.KS - ks);
                 const uint32_t a_base = smem_u32(smem + stage * SB);
-                const uint32_t b_base = a_base + A_STAGE_BYTES;
+                const uint32_t b_base = a_base + B_OFF;
                 if (p.chunk >= 32) {
                     const uint32_t sbo = 8u * p.chunk;
                     const int mma_per_sub = p.chunk >> 5;
@@ -334,8 +350,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int q = 0; q < mma_per_sub; ++q) {
                             const uint64_t ad = make_smem_desc(a_base + j * a_sub_bytes + q * 32, 16, sbo, lt);
                             const uint64_t bd = make_smem_desc(b_base + j * b_sub_bytes + q * 32, 16, sbo, lt);
-                            tc_mma<KIND>(tmem_base, ad, bd, idesc, accum);
+                            tc_mma<MK>(tmem_base, ad, bd, idesc, accum);
                             accum = 1;
+                            if (X3) {
+                                const uint64_t al = make_smem_desc(a_base + A_LO_OFF + j * a_sub_bytes + q * 32, 16, sbo, lt);
+                                const uint64_t bl = make_smem_desc(a_base + B_LO_OFF + j * b_sub_bytes + q * 32, 16, sbo, lt);
+                                tc_mma<MK>(tmem_base, al, bd, idesc, 1);
+                                tc_mma<MK>(tmem_base, ad, bl, idesc, 1);
+                            }
                         }
                     }
                 } else {
@@ -343,8 +365,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     for (int j = 0; j < nsub; j += 2) {
                         const uint64_t ad = make_smem_desc(a_base + j * a_sub_bytes, a_sub_bytes, 128, 0);
                         const uint64_t bd = make_smem_desc(b_base + j * b_sub_bytes, b_sub_bytes, 128, 0);
-                        tc_mma<KIND>(tmem_base, ad, bd, idesc, accum);
+                        tc_mma<MK>(tmem_base, ad, bd, idesc, accum);
                         accum = 1;
+                        if (X3) {
+                            const uint64_t al = make_smem_desc(a_base + A_LO_OFF + j * a_sub_bytes, a_sub_bytes, 128, 0);
+                            const uint64_t bl = make_smem_desc(a_base + B_LO_OFF + j * b_sub_bytes, b_sub_bytes, 128, 0);
+                            tc_mma<MK>(tmem_base, al, bd, idesc, 1);
+                            tc_mma<MK>(tmem_base, ad, bl, idesc, 1);
+                        }
                     }
                 }
                 ks += nsub;
@@ -358,6 +386,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===================== epilogue warps =====================
         const int quarter = warp_idx & 3;
         const int row = quarter * 32 + lane;
+        if (X3) {
+            // split the landed fp32 A tile in place: hi = top 19 bits, lo = x - hi (exact in fp32)
+            const int etid = threadIdx.x - 64;
+            int ks = 0, stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < num_stage_iters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                const int nsub = min(subs_per_stage, p.KS - ks);
+                uint4* hi = reinterpret_cast<uint4*>(smem + stage * SB);
+                uint4* lo = reinterpret_cast<uint4*>(smem + stage * SB + A_LO_OFF);
+                const int nvec = nsub * BLOCK_M * p.chunk / 16;
+                for (int i = etid; i < nvec; i += 128) {
+                    uint4 x = hi[i], h, l;
+                    h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
+                    l.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(h.x)));
+                    l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y)));
+                    l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z)));
+                    l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w)));
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's smem reads
+                mbar_arrive(&conv_bar[stage]);
+                ks += nsub;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
         if (p.res_panels > 0) mbar_wait(res_full_bar, 0);
         mbar_wait(tmem_full_bar, 0);  // all MMAs retired: the operand ring is free -> output staging
         tc_fence_after();
@@ -370,8 +425,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tmem_ld_32x32b_x16(t_row + c0, v0);
             tmem_ld_32x32b_x16(t_row + c0 + 16, v1);
             tmem_ld_wait();
-            epilogue16<KIND>(p, v0, row, c0, bias_s, scale_s, res_tile, out_tile);
-            epilogue16<KIND>(p, v1, row, c0 + 16, bias_s, scale_s, res_tile, out_tile);
+            epilogue16<MK>(p, v0, row, c0, bias_s, scale_s, res_tile, out_tile);
+            epilogue16<MK>(p, v1, row, c0 + 16, bias_s, scale_s, res_tile, out_tile);
         }
         tc_fence_before();
         fence_proxy_async_smem();                              // staged tile -> visible to the TMA engine
@@ -594,7 +649,7 @@ size_t b200_conv_packed_weight_bytes(const b200_conv_desc_t* d) {
     if (!d) return 0;
     Geometry g = make_geometry(d);
     if (!g.ok) return 0;
-    return static_cast<size_t>(d->k) * g.KS * g.chunk;
+    return static_cast<size_t>(d->k) * g.KS * g.chunk * (d->math == B200_MATH_TF32X3 ? 2 : 1);
 }
 
 int b200_conv_pack_weights(const b200_conv_desc_t* d, const void* src_kcrs, int32_t c_real, void* dst_packed) {
@@ -602,7 +657,7 @@ int b200_conv_pack_weights(const b200_conv_desc_t* d, const void* src_kcrs, int3
     Geometry g = make_geometry(d);
     if (!g.ok || c_real > d->c || c_real <= 0) return B200_INVALID_VALUE;
     const size_t row_bytes = static_cast<size_t>(g.KS) * g.chunk;
-    memset(dst_packed, 0, row_bytes * d->k);
+    memset(dst_packed, 0, row_bytes * d->k * (d->math == B200_MATH_TF32X3 ? 2 : 1));
     const int es = g.es;
     const uint8_t* src = static_cast<const uint8_t*>(src_kcrs);
     uint8_t* dst = static_cast<uint8_t*>(dst_packed);
@@ -612,7 +667,20 @@ int b200_conv_pack_weights(const b200_conv_desc_t* d, const void* src_kcrs, int3
             for (int c = 0; c < c_real; ++c) {
                 const size_t s_off = ((static_cast<size_t>(ko) * c_real + c) * RS + rs) * es;
                 const size_t d_off = ko * row_bytes + (static_cast<size_t>(rs) * d->c + c) * es;
-                memcpy(dst + d_off, src + s_off, es);
+                if (d->math == B200_MATH_TF32X3) {
+                    // W = hi + lo, hi = top 19 bits; the low image follows the high image
+                    uint32_t u;
+                    memcpy(&u, src + s_off, 4);
+                    const uint32_t hu = u & 0xFFFFE000u;
+                    float x, h;
+                    memcpy(&x, &u, 4);
+                    memcpy(&h, &hu, 4);
+                    const float l = x - h;
+                    memcpy(dst + d_off, &h, 4);
+                    memcpy(dst + row_bytes * d->k + d_off, &l, 4);
+                } else {
+                    memcpy(dst + d_off, src + s_off, es);
+                }
             }
         }
     }
@@ -623,7 +691,9 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
                           const float* scale_dev, b200_conv_plan_t** plan_out) {
     if (!d || !packed_weights_dev || !plan_out) return B200_INVALID_VALUE;
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
-    if (d->math != B200_MATH_I8 && d->math != B200_MATH_F16 && d->math != B200_MATH_TF32) return B200_UNIMPL_ERROR;
+    if (d->math != B200_MATH_I8 && d->math != B200_MATH_F16 && d->math != B200_MATH_TF32 &&
+        d->math != B200_MATH_TF32X3)
+        return B200_UNIMPL_ERROR;
     if (d->fuse_pool != 0) return B200_UNIMPL_ERROR;
     load_driver_entry_points();
     if (!g_encode_tiled || !g_encode_im2col) return B200_NOT_INITIALIZED;
@@ -632,7 +702,7 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     // operand / epilogue dtype consistency
     if (d->math == B200_MATH_I8 && !(d->in_dtype == B200_INT8 || d->in_dtype == B200_UINT8)) return B200_INVALID_VALUE;
     if (d->math == B200_MATH_F16 && d->in_dtype != B200_HALF) return B200_INVALID_VALUE;
-    if (d->math == B200_MATH_TF32 && d->in_dtype != B200_FLOAT) return B200_INVALID_VALUE;
+    if ((d->math == B200_MATH_TF32 || d->math == B200_MATH_TF32X3) && d->in_dtype != B200_FLOAT) return B200_INVALID_VALUE;
     if (d->ldc < d->k) return B200_INVALID_VALUE;
     const int out_es = dtype_size(d->out_dtype);
     const int res_es = d->res_dtype >= 0 ? dtype_size(d->res_dtype) : 0;
@@ -685,6 +755,9 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     } else if (d->math == B200_MATH_F16) {
         ok = select_launch<KIND_F16>(pl);
         a_fmt = b_fmt = 0u;
+    } else if (d->math == B200_MATH_TF32X3) {
+        ok = select_launch<KIND_TF32X3>(pl);
+        a_fmt = b_fmt = 2u;
     } else {
         ok = select_launch<KIND_TF32>(pl);
         a_fmt = b_fmt = 2u;
@@ -694,7 +767,8 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
 
     // ---- weights tensor map: [k rows][KS*chunk_el] K-major, box {chunk_el, bn}
     {
-        cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.KS) * g.chunk_el, static_cast<cuuint64_t>(d->k)};
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.KS) * g.chunk_el,
+                              static_cast<cuuint64_t>(d->k) * (d->math == B200_MATH_TF32X3 ? 2 : 1)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(g.KS) * g.chunk};
         cuuint32_t box[2] = {static_cast<cuuint32_t>(g.chunk_el), static_cast<cuuint32_t>(bn)};
         cuuint32_t estr[2] = {1, 1};
@@ -733,7 +807,7 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     // ---- pipeline depth: as deep as the k loop needs, within the shared-memory budget. A grid that
     // exceeds one wave keeps two CTAs per SM resident (epilogue of one overlaps the main loop of the
     // other); a sub-wave grid takes the whole SM for latency hiding on its long k loop.
-    const int sb = stage_bytes(bn);
+    const int sb = stage_bytes(bn, d->math == B200_MATH_TF32X3);
     const int res_bytes = BLOCK_M * bn * res_es;
     const int fixed = res_bytes + tail_bytes(bn) + 1024;
     const int staging = BLOCK_M * bn * out_es;

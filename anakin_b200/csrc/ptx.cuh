@@ -125,7 +125,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                  : "memory");
 }
 
-enum MmaKind { KIND_I8 = 0, KIND_F16 = 1, KIND_TF32 = 2 };
+enum MmaKind { KIND_I8 = 0, KIND_F16 = 1, KIND_TF32 = 2, KIND_TF32X3 = 3 };
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]; single-thread issue.
 template <int kKind>

@@ -98,7 +98,7 @@ def _tf32_trunc(a):
 
 
 @pytest.mark.parametrize("case", F_CASES)
-@pytest.mark.parametrize("math", ["f16", "tf32"])
+@pytest.mark.parametrize("math", ["f16", "tf32", "tf32x3"])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_conv_float(case, math, with_res, oracle):
     import torch
@@ -121,6 +121,13 @@ def test_conv_float(case, math, with_res, oracle):
         mk, dt = A.MATH_F16, A.HALF
         res_in = res.astype(np.float16) if with_res else None
         res_seen = res_in.astype(np.float32) if with_res else None
+    elif math == "tf32x3":
+        # error-compensated split: compare against the exact-fp32 operands, fp32-grade tolerance
+        xs, ws = x, wt
+        x_seen, w_seen = x, wt
+        mk, dt = A.MATH_TF32X3, A.FLOAT
+        res_in = res
+        res_seen = res
     else:
         xs, ws = x, wt
         x_seen, w_seen = _tf32_trunc(x), _tf32_trunc(wt)
@@ -136,3 +143,6 @@ def test_conv_float(case, math, with_res, oracle):
     got = got.cpu().numpy()
     max_ratio, max_diff = oracle.tensor_cmp(want, got)
     assert max_diff < 1e-3 or max_ratio <= 1e-3, (max_ratio, max_diff, run.info())
+    if math == "tf32x3":
+        scale_ref = float(np.abs(want).max())
+        assert max_diff <= 2e-5 * max(1.0, scale_ref), (max_diff, scale_ref)
