@@ -46,7 +46,7 @@ SYMBOLS = {
     "anakin_net_set_cuda_graph": (_i, [_vp, _i]),
     "anakin_net_exec_order": (_sz, [_vp, _vp, _sz]),
     "anakin_net_activation_bytes": (_sz, [_vp]),
-    "anakin_net_profile_ops": (_i, [_vp, _i, C.POINTER(C.c_float), _i]),
+    "anakin_net_profile_ops": (_i, [_vp, _i, _i, C.POINTER(C.c_float), _i]),
     "anakin_net_destroy": (None, [_vp]),
     "anakin_worker_create": (_i, [_cp, _i, _i, C.POINTER(_i), _i, _i, C.POINTER(_vp)]),
     "anakin_worker_sync_prediction": (_i, [_vp, _vp, _sz, _vp, _sz]),
@@ -217,11 +217,12 @@ class Net:
     def exec_order(self):
         return [l.split(":") for l in _text(self._lib.anakin_net_exec_order, self._h).splitlines()]
 
-    def profile_ops(self, iters=5):
-        """[(node, op, ms)] device time per launched op (eager, CUDA-event pair per op)."""
+    def profile_ops(self, iters=5, reps=1):
+        """[(node, op, ms)] device time per launched op (eager, CUDA-event pair per op; reps > 1 =
+        that many back-to-back launches per pair, i.e. steady-state time)."""
         order = self.exec_order()
         buf = (C.c_float * len(order))()
-        _check(self._lib.anakin_net_profile_ops(self._h, iters, buf, len(order)), "profile_ops")
+        _check(self._lib.anakin_net_profile_ops(self._h, iters, reps, buf, len(order)), "profile_ops")
         return [(n, o, float(buf[i])) for i, (n, o) in enumerate(order)]
 
     def activation_bytes(self):

@@ -262,14 +262,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         fence_mbar_init();
     }
     if (warp_idx == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
-    if (warp_idx >= 2) {
-        // bias / scale tables: weights-side constants, safe to read before the PDL wait
-        for (int i = threadIdx.x - 64; i < BN; i += 128) {
-            const bool ok = (n0 + i) < p.K;
-            bias_s[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n0 + i) : 0.f;
-            scale_s[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0 + i) : 1.f;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -386,6 +378,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===================== epilogue warps =====================
         const int quarter = warp_idx & 3;
         const int row = quarter * 32 + lane;
+        // bias / scale tables (weights-side constants): filled while the main loop runs
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+            const bool ok = (n0 + i) < p.K;
+            bias_s[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n0 + i) : 0.f;
+            scale_s[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0 + i) : 1.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         if (X3) {
             // split the landed fp32 A tile in place: hi = top 19 bits, lo = x - hi (exact in fp32)
             const int etid = threadIdx.x - 64;
@@ -438,7 +437,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tma_store_2d(&map_out, out_tile + j * BLOCK_M * p.out_pw, n0 + j * cols_per_panel, m0);
             }
             tma_store_commit();
-            tma_store_wait_all();
+            tma_store_wait_read();  // smem may be released once the engine has read it; the writes
+                                    // complete before the grid is reported complete
         }
     }
 

@@ -177,9 +177,9 @@ size_t anakin_net_exec_order(anakin_net_t* n, char* buf, size_t cap) {
     for (auto& e : n->net.get_exec_order()) s += e + "\n";
     return emit(s, buf, cap);
 }
-int anakin_net_profile_ops(anakin_net_t* n, int iters, float* ms, int cap) {
+int anakin_net_profile_ops(anakin_net_t* n, int iters, int reps, float* ms, int cap) {
     if (!n || !ms || iters <= 0) return fail("bad argument");
-    std::vector<float> v = n->net.profile_ops(iters);
+    std::vector<float> v = n->net.profile_ops(iters, reps);
     for (int i = 0; i < cap && i < static_cast<int>(v.size()); ++i) ms[i] = v[i];
     return 0;
 }

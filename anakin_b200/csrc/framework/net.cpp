@@ -202,16 +202,18 @@ void NetCore::prediction() {
     ++_eager_runs;
 }
 
-std::vector<float> NetCore::profile_ops(int iters) {
+std::vector<float> NetCore::profile_ops(int iters, int reps) {
     cudaSetDevice(_device);
     const size_t n = _exec.size();
+    if (reps < 1) reps = 1;
     std::vector<cudaEvent_t> ev(2 * n);
     for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
     std::vector<float> ms(n, 0.f);
+    iters = iters * 1;
     for (int it = 0; it < iters + 1; ++it) {  // first pass is a warm-up
         for (size_t i = 0; i < n; ++i) {
             CUDA_CHECK(cudaEventRecord(ev[2 * i], _stream));
-            (*_exec[i].op)(_ctx, _exec[i].ins, _exec[i].outs);
+            for (int r = 0; r < reps; ++r) (*_exec[i].op)(_ctx, _exec[i].ins, _exec[i].outs);
             CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], _stream));
         }
         CUDA_CHECK(cudaStreamSynchronize(_stream));
@@ -219,7 +221,7 @@ std::vector<float> NetCore::profile_ops(int iters) {
         for (size_t i = 0; i < n; ++i) {
             float t = 0.f;
             CUDA_CHECK(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
-            ms[i] += t / iters;
+            ms[i] += t / iters / reps;
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);

@@ -56,7 +56,9 @@ public:
     size_t activation_bytes() const { return _act_bytes; }
     // Per-op device time (ms), averaged over `iters` eager runs with a CUDA-event pair around every
     // op on the compute stream (the reference's -DENABLE_OP_TIMER, net.cpp:445-449,494-506).
-    std::vector<float> profile_ops(int iters);
+    // reps > 1: each op is launched `reps` times back to back inside its event pair, which hides the
+    // host's launch rate and gives the op's steady-state device time.
+    std::vector<float> profile_ops(int iters, int reps = 1);
 
 private:
     struct ExecOp {

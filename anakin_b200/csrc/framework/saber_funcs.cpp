@@ -26,6 +26,8 @@ struct ConvEngine::Impl {
     b200_conv_plan_t* plan = nullptr;
     DeviceBuffer w_dev, bias_dev, scale_dev;
     bool need_in_transform = false;
+    bool stem = false;       // input transform = stem pack (R x S conv over RGB -> R x 1 conv over X2)
+    int stem_taps = 0;
     Tensor<NV> in_scratch;
     float in_inv_scale = 1.f;
     bool depthwise = false;
@@ -89,6 +91,7 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
     // ---- 1. the tensor the conv kernel reads (NHWC in the op's operand type)
     const Tensor<NV>* cin = &in;
     P.need_in_transform = false;
+    P.stem = false;
     if (in.get_layout() == Layout_NCHW && !(in.height() == 1 && in.width() == 1 && in.get_dtype() != AK_FLOAT)) {
         if (in.get_dtype() != AK_FLOAT) return SaberUnImplError;
         // graph-input case: fp32 NCHW -> NHWC operand type (the reference quantises inside conv too:
@@ -96,6 +99,15 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         DataType sdt = op == AK_INT8 ? AK_INT8 : (op == AK_HALF ? AK_HALF : AK_FLOAT);
         Shape s = in.valid_shape();
         s.set_layout(Layout_NHWC);
+        // RGB stem: pack S taps x 4 channels per output column (see b200_stem_pack)
+        static const bool stem_enabled = [] { const char* e = getenv("B200_SABER_STEM_PACK"); return !(e && e[0] == '0'); }();
+        P.stem = stem_enabled && !spec.is_fc && spec.group == 1 && in.channel() <= 4 && spec.s > 1 && spec.s <= 8 &&
+                 spec.dil_w == 1 && spec.dil_h == 1;
+        if (P.stem) {
+            P.stem_taps = spec.s <= 4 ? 4 : 8;
+            const int wo = conv_out_size(in.width(), spec.pad_w, 1, spec.s, spec.stride_w);
+            s = Shape({in.num(), P.stem_taps * 4, in.height() + 2 * spec.pad_h, wo}, Layout_NHWC);
+        }
         if (P.in_scratch.re_alloc(s, sdt) != SaberSuccess) return SaberOutOfMem;
         CUDA_CHECK(cudaMemset(P.in_scratch.mutable_data(), 0, P.in_scratch.storage_bytes()));
         if (op == AK_INT8) {
@@ -136,6 +148,13 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         for (int y = 0; y < H; ++y)
             for (int x = 0; x < W; ++x)
                 for (int c = 0; c < C; ++c) col_map[(y * W + x) * cs + c] = (c * H + y) * W + x;
+    } else if (P.need_in_transform && P.stem) {
+        d.n = cin->num(); d.h = cin->height(); d.w = cin->width(); d.c = cs;   // X2: c = taps*4
+        d.r = spec.r; d.s = 1;
+        d.pad_h = 0; d.pad_w = 0;
+        d.stride_h = spec.stride_h; d.stride_w = 1;
+        d.dil_h = 1; d.dil_w = 1;
+        c_real = cs;
     } else {
         d.n = cin->num(); d.h = cin->height(); d.w = cin->width(); d.c = cs;
         d.r = spec.r; d.s = spec.s;
@@ -144,11 +163,12 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         d.dil_h = spec.dil_h; d.dil_w = spec.dil_w;
         c_real = spec.c_per_group;
     }
+    const bool stem = P.need_in_transform && P.stem;
     d.k = spec.k;
     P.depthwise = !spec.is_fc && spec.group > 1 && spec.group == cin->channel() && spec.c_per_group == 1 &&
                   spec.k == spec.group;
     if (spec.group != 1 && !P.depthwise) return SaberUnImplError;
-    if (!spec.is_fc && !P.depthwise && c_real != cin->channel()) return SaberInvalidValue;
+    if (!spec.is_fc && !P.depthwise && !stem && c_real != cin->channel()) return SaberInvalidValue;
 
     // ---- 3. where the conv writes
     Tensor<NV>* cout = &out;
@@ -195,7 +215,7 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         // operand-typed KCRS image (fc: permuted into the stored-K order), then the tcgen05 pack
         const int es = op == AK_INT8 ? 1 : (op == AK_HALF ? 2 : 4);
         const int c_img = spec.is_fc ? d.c : c_real;
-        const int RS = spec.is_fc ? 1 : spec.r * spec.s;
+        const int RS = spec.is_fc ? 1 : (stem ? spec.r : spec.r * spec.s);
         std::vector<uint8_t> img(static_cast<size_t>(spec.k) * c_img * RS * es, 0);
         std::vector<float> w_scale(spec.k, 1.f);
         for (int oc = 0; oc < spec.k; ++oc) {
@@ -215,6 +235,11 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
                         const int col = col_map[ci];
                         if (col < 0) continue;
                         v = wr[col];
+                    } else if (stem) {
+                        // ci = tap*4 + ch, rs = filter row: w[oc][ch][r][tap]
+                        const int tap = ci >> 2, ch = ci & 3;
+                        if (tap >= spec.s || ch >= spec.c_per_group) continue;
+                        v = wr[(static_cast<size_t>(ch) * spec.r + rs) * spec.s + tap];
                     } else {
                         v = wr[static_cast<size_t>(ci) * RS + rs];
                     }
@@ -293,7 +318,14 @@ SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Te
     Impl& P = *_p;
     if (!P.ready) return SaberNotInitialized;
     const void* src = in.data();
-    if (P.need_in_transform) {
+    if (P.need_in_transform && P.stem) {
+        SaberStatus st = static_cast<SaberStatus>(b200_stem_pack(
+            static_cast<const float*>(in.data()), P.in_scratch.mutable_data(), P.in_scratch.get_dtype(), in.num(),
+            in.channel(), in.height(), in.width(), P.spec.pad_h, P.spec.pad_w, P.spec.s, P.spec.stride_w,
+            P.stem_taps, P.in_inv_scale, stream));
+        if (st != SaberSuccess) return st;
+        src = P.in_scratch.data();
+    } else if (P.need_in_transform) {
         SaberStatus st = static_cast<SaberStatus>(b200_nchw_to_nhwc(
             static_cast<const float*>(in.data()), P.in_scratch.mutable_data(), P.in_scratch.get_dtype(), in.num(),
             in.channel(), in.height(), in.width(), P.in_scratch.channel_stored(), P.in_inv_scale, 0, stream));

@@ -22,6 +22,29 @@ namespace b200 {
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch for the pointwise kernels that sit between tensor-core convs: the
+// kernel signals its dependents at once and waits for its predecessor before touching memory, so
+// launch latency and the neighbours' prologues overlap along the whole chain.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename Kern, typename... Args>
+static void launch_pdl(Kern kern, unsigned grid, unsigned block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static int check_launch(const char* what) {
     count_launch();
     cudaError_t e = cudaPeekAtLastError();
@@ -43,6 +66,7 @@ struct PoolP {
 // Window logic = reference test/saber/test_saber_pooling.cpp:14-104 (incl. the
 // include-padding divisor rule).
 __global__ void pool_f32_kernel(const float4* __restrict__ in, float4* __restrict__ out, PoolP p) {
+    pdl_enter();
     const int cv = p.c >> 2;
     const long long total = 1ll * p.n * p.oh * p.ow * cv;
     for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
@@ -89,6 +113,7 @@ __global__ void pool_f32_kernel(const float4* __restrict__ in, float4* __restric
 
 // fp16: 8 channels per thread, accumulate in fp32.
 __global__ void pool_f16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolP p) {
+    pdl_enter();
     const int cv = p.c >> 3;
     const long long total = 1ll * p.n * p.oh * p.ow * cv;
     for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
@@ -146,6 +171,7 @@ __global__ void pool_f16_kernel(const uint4* __restrict__ in, uint4* __restrict_
 // codes, avg-incl divides by window_h*window_w, nearbyintf (RNE), saturate.
 template <bool kUnsigned>
 __global__ void pool_q8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolP p) {
+    pdl_enter();
     const int cv = p.c >> 4;
     const long long total = 1ll * p.n * p.oh * p.ow * cv;
     for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
@@ -208,6 +234,7 @@ __global__ void pool_q8_kernel(const uint4* __restrict__ in, uint4* __restrict__
 // shuffles, so the result is bit-identical to the sequential kernels.
 template <int MODE>  // 0 f32 (4 ch), 1 f16 (8 ch), 2 s8 (16 ch), 3 u8 (16 ch)
 __global__ void pool_warp_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolP p) {
+    pdl_enter();
     constexpr int VEC = MODE == 0 ? 4 : (MODE == 1 ? 8 : 16);
     const int cv = p.c / VEC;
     const long long total = 1ll * p.n * p.oh * p.ow * cv;
@@ -311,6 +338,7 @@ __global__ void pool_warp_kernel(const uint4* __restrict__ in, uint4* __restrict
 // inner == 1: one warp per row, shuffle reductions (reference uses one thread per row).
 __global__ void softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
                                     int len, int in_pitch, int out_pitch) {
+    pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -510,6 +538,91 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, void* __restri
         }
     }
 }
+// Graph inputs have C <= 4 (RGB): one thread per pixel reads C planes (coalesced along hw) and
+// writes its whole padded pixel with 16-byte stores.
+template <int OUT>  // 0 f32, 1 f16, 2 s8, 3 u8
+__global__ void nchw_to_nhwc_smallc_kernel(const float* __restrict__ in, void* __restrict__ out, int n, int c,
+                                           int hw, int c_pad, float inv_scale) {
+    const long long total = 1ll * n * hw;
+    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
+         idx += 1ll * gridDim.x * blockDim.x) {
+        const int b = static_cast<int>(idx / hw);
+        const int px = static_cast<int>(idx - 1ll * b * hw);
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ch = 0; ch < c; ++ch) x[ch] = __ldg(in + (1ll * b * c + ch) * hw + px);
+        if (OUT == 0) {
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(out) + idx * c_pad);
+            o[0] = make_float4(x[0], x[1], x[2], x[3]);
+            for (int q = 1; q < c_pad / 4; ++q) o[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (OUT == 1) {
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__half*>(out) + idx * c_pad);
+            __half2 a = __floats2half2_rn(x[0], x[1]), bq = __floats2half2_rn(x[2], x[3]);
+            o[0] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bq), 0, 0);
+            for (int q = 1; q < c_pad / 8; ++q) o[q] = make_uint4(0, 0, 0, 0);
+        } else {
+            uint32_t w = 0;
+            for (int ch = 0; ch < 4; ++ch) {
+                float t = __fmul_rn(x[ch], inv_scale);
+                int code;
+                if (OUT == 2) { t = fminf(fmaxf(roundf(t), -128.f), 127.f); code = static_cast<int>(t); }
+                else { t = fminf(fmaxf(t, 0.f), 255.f); code = static_cast<int>(t); }
+                w |= (static_cast<uint32_t>(code) & 0xffu) << (8 * ch);
+            }
+            uint4* o = reinterpret_cast<uint4*>(static_cast<uint8_t*>(out) + idx * c_pad);
+            o[0] = make_uint4(w, 0, 0, 0);
+            for (int q = 1; q < c_pad / 16; ++q) o[q] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// Stem pack: the first conv of a CNN has C <= 4 input channels, so an NHWC pixel is far below
+// the 16-byte TMA / 32-byte MMA granules. This kernel turns the fp32 NCHW graph input into
+//   X2[n][h + 2*pad_h][wo][taps][4]      (taps = filter width rounded up to 4 or 8)
+// i.e. for every (padded) input row and every OUTPUT column the S horizontal taps x 4 channels the
+// filter row touches, already quantised / converted. The R x S conv then runs on the tensor-core
+// kernel as an R x 1 conv over X2 with c = taps*4, stride_w = 1, no padding.
+template <int OUT>  // 0 f32, 1 f16, 2 s8, 3 u8
+__global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict__ out, int n, int c, int h,
+                                 int w, int pad_h, int pad_w, int s, int stride_w, int taps, int wo,
+                                 float inv_scale) {
+    pdl_enter();
+    const int hp = h + 2 * pad_h;
+    const long long total = 1ll * n * hp * wo;
+    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
+         idx += 1ll * gridDim.x * blockDim.x) {
+        const int q = static_cast<int>(idx % wo);
+        long long t = idx / wo;
+        const int hr = static_cast<int>(t % hp);
+        const int b = static_cast<int>(t / hp);
+        const int y = hr - pad_h;
+        const bool row_ok = y >= 0 && y < h;
+        for (int tap = 0; tap < taps; ++tap) {
+            const int x = q * stride_w - pad_w + tap;
+            const bool ok = row_ok && tap < s && x >= 0 && x < w;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok)
+                for (int ch = 0; ch < c; ++ch) v[ch] = __ldg(in + ((1ll * b * c + ch) * h + y) * w + x);
+            const long long o = idx * taps + tap;  // index of this tap's 4-channel group
+            if (OUT == 0) {
+                reinterpret_cast<float4*>(out)[o] = make_float4(v[0], v[1], v[2], v[3]);
+            } else if (OUT == 1) {
+                __half2 a = __floats2half2_rn(v[0], v[1]), bq = __floats2half2_rn(v[2], v[3]);
+                reinterpret_cast<uint2*>(out)[o] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bq));
+            } else {
+                uint32_t wd = 0;
+                for (int ch = 0; ch < 4; ++ch) {
+                    float f = __fmul_rn(v[ch], inv_scale);
+                    int code;
+                    if (OUT == 2) { f = fminf(fmaxf(roundf(f), -128.f), 127.f); code = static_cast<int>(f); }
+                    else { f = fminf(fmaxf(f, 0.f), 255.f); code = static_cast<int>(f); }
+                    wd |= (static_cast<uint32_t>(code) & 0xffu) << (8 * ch);
+                }
+                reinterpret_cast<uint32_t*>(out)[o] = wd;
+            }
+        }
+    }
+}
+
 template <int IN>  // 0 f32, 1 f16, 2 s8, 3 u8
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ in, float* __restrict__ out, int c, int hw,
                                     int c_pad, float scale) {
@@ -641,36 +754,36 @@ int b200_pool_run(const b200_pool_desc_t* d, const void* in, void* out, void* st
         if (d->c % 4) return B200_INVALID_VALUE;
         const long long total = 1ll * p.n * oh * ow * (d->c / 4);
         if (big_window)
-            pool_warp_kernel<0><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
-                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            launch_pdl(pool_warp_kernel<0>, grid_for(total * 32, block), block, S(stream),
+                       static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
         else
-            pool_f32_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
-                static_cast<const float4*>(in), static_cast<float4*>(out), p);
+            launch_pdl(pool_f32_kernel, grid_for(total, block), block, S(stream),
+                       static_cast<const float4*>(in), static_cast<float4*>(out), p);
     } else if (d->dtype == B200_HALF) {
         if (d->c % 8) return B200_INVALID_VALUE;
         const long long total = 1ll * p.n * oh * ow * (d->c / 8);
         if (big_window)
-            pool_warp_kernel<1><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
-                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            launch_pdl(pool_warp_kernel<1>, grid_for(total * 32, block), block, S(stream),
+                       static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
         else
-            pool_f16_kernel<<<grid_for(total, block), block, 0, S(stream)>>>(
-                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            launch_pdl(pool_f16_kernel, grid_for(total, block), block, S(stream),
+                       static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
     } else if (d->dtype == B200_INT8 || d->dtype == B200_UINT8) {
         if (d->c % 16) return B200_INVALID_VALUE;
         const long long total = 1ll * p.n * oh * ow * (d->c / 16);
         if (big_window) {
             if (d->dtype == B200_UINT8)
-                pool_warp_kernel<3><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
-                    static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+                launch_pdl(pool_warp_kernel<3>, grid_for(total * 32, block), block, S(stream),
+                           static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
             else
-                pool_warp_kernel<2><<<grid_for(total * 32, block), block, 0, S(stream)>>>(
-                    static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+                launch_pdl(pool_warp_kernel<2>, grid_for(total * 32, block), block, S(stream),
+                           static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
         } else if (d->dtype == B200_UINT8) {
-            pool_q8_kernel<true><<<grid_for(total, block), block, 0, S(stream)>>>(
-                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            launch_pdl(pool_q8_kernel<true>, grid_for(total, block), block, S(stream),
+                       static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
         } else {
-            pool_q8_kernel<false><<<grid_for(total, block), block, 0, S(stream)>>>(
-                static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            launch_pdl(pool_q8_kernel<false>, grid_for(total, block), block, S(stream),
+                       static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
         }
     } else {
         return B200_UNIMPL_ERROR;
@@ -684,7 +797,7 @@ int b200_softmax_rows(const float* in, float* out, int32_t rows, int32_t len, in
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
     const int block = 128;  // 4 rows per CTA
     const unsigned grid = (static_cast<unsigned>(rows) * 32 + block - 1) / block;
-    softmax_rows_kernel<<<grid, block, 0, S(stream)>>>(in, out, rows, len, in_pitch, out_pitch);
+    launch_pdl(softmax_rows_kernel, grid, block, S(stream), in, out, rows, len, in_pitch, out_pitch);
     return check_launch("softmax");
 }
 
@@ -766,6 +879,19 @@ int b200_nchw_to_nhwc(const float* in, void* out, int32_t out_dtype, int32_t n, 
     if (split_hi_lo) return B200_UNIMPL_ERROR;
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
     const int hw = h * w;
+    const int es = out_dtype == B200_FLOAT ? 4 : (out_dtype == B200_HALF ? 2 : 1);
+    if (c <= 4 && (c_pad * es) % 16 == 0 && (out_dtype == B200_FLOAT || out_dtype == B200_HALF ||
+                                             out_dtype == B200_INT8 || out_dtype == B200_UINT8)) {
+        const long long total = 1ll * n * hw;
+        const unsigned g = grid_for(total, 256);
+        switch (out_dtype) {
+            case B200_FLOAT: nchw_to_nhwc_smallc_kernel<0><<<g, 256, 0, S(stream)>>>(in, out, n, c, hw, c_pad, inv_scale); break;
+            case B200_HALF: nchw_to_nhwc_smallc_kernel<1><<<g, 256, 0, S(stream)>>>(in, out, n, c, hw, c_pad, inv_scale); break;
+            case B200_INT8: nchw_to_nhwc_smallc_kernel<2><<<g, 256, 0, S(stream)>>>(in, out, n, c, hw, c_pad, inv_scale); break;
+            default: nchw_to_nhwc_smallc_kernel<3><<<g, 256, 0, S(stream)>>>(in, out, n, c, hw, c_pad, inv_scale); break;
+        }
+        return check_launch("nchw_to_nhwc");
+    }
     dim3 grid((hw + 31) / 32, (c_pad + 31) / 32, n), block(32, 8);
     switch (out_dtype) {
         case B200_FLOAT: nchw_to_nhwc_kernel<0><<<grid, block, 0, S(stream)>>>(in, out, c, hw, c_pad, inv_scale); break;
@@ -775,6 +901,27 @@ int b200_nchw_to_nhwc(const float* in, void* out, int32_t out_dtype, int32_t n, 
         default: return B200_UNIMPL_ERROR;
     }
     return check_launch("nchw_to_nhwc");
+}
+
+int b200_stem_pack(const float* in, void* out, int32_t out_dtype, int32_t n, int32_t c, int32_t h, int32_t w,
+                   int32_t pad_h, int32_t pad_w, int32_t s, int32_t stride_w, int32_t taps, float inv_scale,
+                   void* stream) {
+    if (!in || !out || n <= 0 || c <= 0 || c > 4 || h <= 0 || w <= 0 || s <= 0 || s > taps || stride_w <= 0 ||
+        (taps != 4 && taps != 8) || pad_h < 0 || pad_w < 0)
+        return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    const int wo = (w + 2 * pad_w - s) / stride_w + 1;
+    if (wo <= 0) return B200_INVALID_VALUE;
+    const long long total = 1ll * n * (h + 2 * pad_h) * wo;
+    const unsigned g = grid_for(total, 256);
+    switch (out_dtype) {
+        case B200_FLOAT: launch_pdl(stem_pack_kernel<0>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        case B200_HALF: launch_pdl(stem_pack_kernel<1>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        case B200_INT8: launch_pdl(stem_pack_kernel<2>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        case B200_UINT8: launch_pdl(stem_pack_kernel<3>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        default: return B200_UNIMPL_ERROR;
+    }
+    return check_launch("stem_pack");
 }
 
 int b200_nhwc_to_nchw(const void* in, int32_t in_dtype, float* out, int32_t n, int32_t c, int32_t h,

@@ -94,6 +94,9 @@ __device__ __forceinline__ void tma_store_commit() {
 __device__ __forceinline__ void tma_store_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -182,17 +182,12 @@ def main():
         blob = b""
     bcast_ms = 0.0
     if world > 1:
-        n = torch.tensor([len(blob)], dtype=torch.int64, device="cuda")
-        dist.broadcast(n, 0)
-        buf = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        from anakin_b200 import dist as adist
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        dist.broadcast(buf, 0)
+        blob = adist.broadcast_bytes(blob, 0, device="cuda")
         torch.cuda.synchronize()
         bcast_ms = (time.perf_counter() - t0) * 1e3
-        blob = bytes(buf.cpu().numpy())
     G = api.Graph.from_bytes(blob)
     G.ResetBatchSize("input_0", batch)
     G.Optimize()
@@ -273,7 +268,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-op device times (eager, event pair per op) -> roofline of the dominant kernel
-    prof = net.profile_ops(5)
+    prof = net.profile_ops(5, 20)
     conv_ms = sum(ms for _, op, ms in prof if op.startswith("Conv") or op == "Dense")
     all_ms = sum(ms for _, _, ms in prof)
 

@@ -77,8 +77,9 @@ ANAKIN_API int anakin_net_set_cuda_graph(anakin_net_t* n, int enable);
 ANAKIN_API size_t anakin_net_exec_order(anakin_net_t* n, char* buf, size_t cap); /* "name:op\n" per launched op */
 ANAKIN_API size_t anakin_net_activation_bytes(anakin_net_t* n);
 /* Per-op device time in ms (same order as anakin_net_exec_order), mean of `iters` eager runs with a
- * CUDA-event pair around every op -- the reference's ENABLE_OP_TIMER (net.cpp:445-449,494-506). */
-ANAKIN_API int anakin_net_profile_ops(anakin_net_t* n, int iters, float* ms, int cap);
+ * CUDA-event pair around every op -- the reference's ENABLE_OP_TIMER (net.cpp:445-449,494-506).
+ * reps > 1 launches each op `reps` times back to back inside its pair (steady-state device time). */
+ANAKIN_API int anakin_net_profile_ops(anakin_net_t* n, int iters, int reps, float* ms, int cap);
 ANAKIN_API void anakin_net_destroy(anakin_net_t* n);
 
 /* ---- Worker (reference framework/core/net/worker.h:69-190): thread pool of per-thread Nets.

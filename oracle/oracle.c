@@ -652,12 +652,15 @@ ORACLE_API void oracle_scale_f32(const float* in, float* out, int outer, int c, 
  * error 2*|a-b|/(a+b+1e-6) *of that element*. */
 ORACLE_API void oracle_tensor_cmp(const float* a, const float* b, size_t count, double* max_ratio,
                                   double* max_diff) {
+    const double eps = 1e-6f;
     double md = 0, mr = 0;
     for (size_t i = 0; i < count; ++i) {
-        double d = fabs((double)a[i] - (double)b[i]);
-        if (d > md) {
+        const float df = a[i] - b[i]; /* float subtraction, as tensor_cmp_host<float> does */
+        const double d = fabs(df);
+        if (md < d) {
             md = d;
-            mr = fabs(2.0 * d / ((double)a[i] + (double)b[i] + (double)1e-6f));
+            const float sf = a[i] + b[i];
+            mr = fabs(2.0 * md / (sf + eps));
         }
     }
     *max_diff = md;

@@ -1,0 +1,198 @@
+"""CPU suite (-m "not gpu"): host logic that needs no GPU -- the C ABI libraries load and export
+every declared symbol, the .anakin.bin codec round-trips (Python writer <-> C++ parser/writer),
+Graph::Optimize fuses the way the independent oracle walker groups, calls on a GPU-less box fail
+loudly instead of falling back, and the N>1 plumbing works under gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header, prefix):
+    with open(os.path.join(ROOT, "include", header)) as f:
+        src = f.read()
+    return sorted(set(re.findall(r"\b(%s\w+)\s*\(" % prefix, src)))
+
+
+def test_saber_abi_exports_every_declared_symbol():
+    from anakin_b200 import saber_abi
+    lib = saber_abi.load()
+    names = _declared("b200_saber.h", "b200_")
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libb200saber.so does not export %s" % n
+        assert n in saber_abi.SYMBOLS, "saber_abi.py does not bind %s" % n
+    assert lib.b200_abi_version() == 1
+    assert saber_abi.status_string(-1) == "SaberSuccess"
+
+
+def test_framework_abi_exports_every_declared_symbol():
+    from anakin_b200 import api
+    lib = api.load()
+    names = _declared("anakin_b200.h", "anakin_")
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libanakin_b200.so does not export %s" % n
+        assert n in api.SYMBOLS, "api.py does not bind %s" % n
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without an sm_100 GPU the product refuses to run instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from anakin_b200 import anakin_bin, api, modelzoo, saber_abi
+    lib = saber_abi.load()
+    assert lib.b200_device_ok(0) == 0
+    d = saber_abi.PoolDesc()
+    d.dtype, d.type, d.n, d.h, d.w, d.c = saber_abi.FLOAT, 1, 1, 4, 4, 4
+    d.window_h = d.window_w = d.stride_h = d.stride_w = 2
+    buf = (C.c_float * 64)()
+    assert lib.b200_pool_run(C.byref(d), buf, buf, None) == saber_abi.WRONG_DEVICE
+    assert lib.b200_softmax_run(buf, buf, 1, 4, 1, None) == saber_abi.WRONG_DEVICE
+    G = api.Graph.from_bytes(anakin_bin.dumps(modelzoo.tiny_resnet(1)))
+    G.Optimize()
+    with pytest.raises(api.AnakinError, match="no CPU fallback"):
+        api.Net(G, "fp32")
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under anakin_b200/ may reference it."""
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "anakin_b200")):
+        if "build" in dp.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                with open(os.path.join(dp, f), errors="ignore") as fh:
+                    txt = fh.read()
+                if re.search(r"(from|import)\s+oracle|oracle/|liboracle|pyoracle", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_anakin_bin_python_roundtrip():
+    from anakin_b200 import anakin_bin, modelzoo
+    g = modelzoo.tiny_resnet(2)
+    g2 = anakin_bin.loads(anakin_bin.dumps(g))
+    assert [n["name"] for n in g2["nodes"]] == [n["name"] for n in g["nodes"]]
+    assert g2["ins"] == ["input_0"] and g2["outs"] == ["prob_out"]
+    for a, b in zip(g["nodes"], g2["nodes"]):
+        assert a["op"] == b["op"] and a["ins"] == b["ins"] and a["outs"] == b["outs"]
+        for k, v in a["attrs"].items():
+            w = b["attrs"][k]
+            if isinstance(v, np.ndarray):
+                np.testing.assert_array_equal(v.ravel(), np.asarray(w).ravel())
+            elif isinstance(v, float):
+                assert w == pytest.approx(v, rel=1e-6)
+            else:
+                assert w == v, (a["name"], k)
+
+
+def test_cpp_parser_fusion_and_save_match_the_walker():
+    from anakin_b200 import anakin_bin, api, modelzoo
+    from oracle import model_walker as W
+    g = modelzoo.build("tiny_resnet", batch=2, precision="int8")
+    G = api.Graph.from_bytes(anakin_bin.dumps(g))
+    G.ResetBatchSize("input_0", 5)
+    G.Optimize()
+    desc = {n: (op, ins, outs) for n, op, ins, outs in G.describe()}
+    groups = W.plan(g)
+    head_of = {m["name"]: gr.head["name"] for gr in groups for m in gr.nodes}
+    for gr in groups:
+        head = gr.head["name"]
+        assert head in desc, head
+        op = desc[head][0]
+        if gr.kind == "conv":
+            want = "ConvEltwise" if gr.elt is not None else (
+                "Conv" + ("Batchnorm" if gr.bn else "") + ("Scale" if gr.scale else "") + ("Relu" if gr.relu else ""))
+            want = "Convolution" if want == "Conv" else want
+            assert op == want, (head, op, want)
+            if gr.elt is not None:
+                assert desc[head][1][1] == head_of[gr.residual]   # residual is the second input
+    assert len(desc) == len(groups)
+    # INT8 graphs keep Conv*Pool unfused (graph.cpp:378-386); an fp32 graph fuses the stem pool
+    Gf = api.Graph.from_bytes(anakin_bin.dumps(modelzoo.tiny_resnet(2)))
+    Gf.Optimize()
+    assert dict((n, op) for n, op, _, _ in Gf.describe())["conv1"] == "ConvBatchnormScaleReluPool"
+    # Graph::save of the optimised graph: attrs merged under "<patternNode>_" names, scales kept
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "opt.anakin.bin")
+        G.save(p)
+        g2 = anakin_bin.load(p)
+    nodes = {n["name"]: n for n in g2["nodes"]}
+    n = nodes["res2a_branch2c"]
+    assert n["op"] == "ConvEltwise" and n["bit_type"] == "INT8"
+    for k in ("batchnorm_0_epsilon", "batchnorm_0_weight_1", "scale_0_weight_1", "merge_type", "merge_coeff",
+              "merge_relu_0_alpha", "weight_1"):
+        assert k in n["attrs"], k
+    assert nodes["input_0"]["attrs"]["input_shape"][0] == 5
+    src = {x["name"]: x for x in g["nodes"]}
+    np.testing.assert_array_equal(np.asarray(n["attrs"]["weight_1"]).ravel(),
+                                  np.asarray(src["res2a_branch2c"]["attrs"]["weight_1"]).ravel())
+    cal = modelzoo.load_calibration("tiny_resnet")
+    sc = dict((t, s) for t, s in g2["edges_out"]["res2a_branch2c"])
+    assert list(sc.values())[0][0] == pytest.approx(cal["res2a_relu"], rel=1e-6)
+
+
+def test_malformed_model_is_rejected():
+    from anakin_b200 import api
+    with pytest.raises(api.AnakinError):
+        api.Graph.from_bytes(b"\x12\xff\xff\xff\xff\x0f garbage")
+    with pytest.raises(api.AnakinError):
+        api.Graph.from_file("/nonexistent/model.anakin.bin")
+
+
+def test_shard_range_covers_every_request_once():
+    from anakin_b200.dist import shard_range
+    for total in (1, 7, 8, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+_GLOO_WORKER = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from anakin_b200 import anakin_bin, api, dist as adist, modelzoo
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+rank = dist.get_rank()
+blob = anakin_bin.dumps(modelzoo.build("tiny_resnet", batch=2, precision="int8")) if rank == 0 else b""
+got = adist.broadcast_bytes(blob, 0)
+G = api.Graph.from_bytes(got)          # every rank parses + optimises the broadcast model
+G.Optimize()
+lo, hi = adist.shard_range(5, rank, 2)
+rows = np.full((hi - lo, 3), float(rank), np.float32)
+allrows = adist.gather_rows(rows)
+assert allrows.shape == (5, 3) and (allrows[:3] == 0).all() and (allrows[3:] == 1).all()
+import hashlib
+print("RANK%%d %%d %%s %%d" %% (rank, len(got), hashlib.sha1(got).hexdigest(), len(G.describe())))
+dist.destroy_process_group()
+'''
+
+
+def test_model_broadcast_and_sharding_world_size_2_gloo():
+    """The N>1 path on CPU: rank 0 builds the model, gloo broadcasts the bytes, both ranks load
+    bit-identical graphs; the request batch is sharded with no per-step collective."""
+    port = 29500 + (os.getpid() % 500)
+    with tempfile.TemporaryDirectory() as d:
+        script = os.path.join(d, "w.py")
+        with open(script, "w") as f:
+            f.write(_GLOO_WORKER % ROOT)
+        procs = [subprocess.Popen([sys.executable, script, str(port), str(r)], stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True) for r in range(2)]
+        outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    lines = sorted(l for o in outs for l in o.splitlines() if l.startswith("RANK"))
+    assert len(lines) == 2
+    a, b = lines[0].split()[1:], lines[1].split()[1:]
+    assert a == b and int(a[0]) > 100000

@@ -1,0 +1,185 @@
+"""CPU suite (-m "not gpu"): pins the oracle restatement to the reference's own naive test oracle
+(oracle/_ref, compiled from /root/reference -- skipped where that tree is absent) and to the
+committed golden fixtures; property tests of the oracle itself."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _need_ref(oracle):
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+
+
+# shape sweep of reference test/saber/test_saber_conv.cpp:886-901,1000-1015
+@pytest.mark.parametrize("k,pad,stride,dil", [(1, 0, 1, 1), (3, 1, 1, 1), (3, 1, 2, 1), (3, 0, 1, 2), (3, 1, 2, 2)])
+@pytest.mark.parametrize("cin,cout,hw,n", [(4, 4, 12, 1), (8, 32, 21, 3), (16, 8, 24, 1)])
+@pytest.mark.parametrize("bias,relu", [(True, True), (False, False)])
+def test_conv_f32_matches_reference_oracle(oracle, k, pad, stride, dil, cin, cout, hw, n, bias, relu):
+    _need_ref(oracle)
+    rng = np.random.default_rng(k * 100 + cin)
+    x = rng.uniform(-5, 5, (n, cin, hw, hw)).astype(np.float32)
+    w = rng.uniform(-1, 1, (cout, cin, k, k)).astype(np.float32)
+    b = rng.uniform(-1, 1, cout).astype(np.float32) if bias else None
+    kw = dict(stride=(stride, stride), pad=(pad, pad), dil=(dil, dil), relu=relu)
+    a = oracle.conv_f32_nchw(x, w, b, **kw)
+    r = oracle.ref_conv_f32_nchw(x, w, b, **kw)
+    np.testing.assert_array_equal(a, r)
+    # the vectorised NHWC variant only re-associates the dot product
+    fast = oracle.conv_f32_nhwc(np.transpose(x, (0, 2, 3, 1)), w, b, **kw)
+    mr, md = oracle.tensor_cmp(np.transpose(a, (0, 2, 3, 1)), fast)
+    assert md <= 1e-5 * max(1.0, float(np.abs(a).max())), (mr, md)
+
+
+def test_conv_f32_real_model_shape(oracle):
+    """test_saber_conv.cpp:868-883: 1x3x224x224 -> 64, 3x3, pad 1, bias + relu."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-5, 5, (1, 3, 224, 224)).astype(np.float32)
+    w = rng.uniform(-1, 1, (64, 3, 3, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, 64).astype(np.float32)
+    np.testing.assert_array_equal(oracle.conv_f32_nchw(x, w, b, pad=(1, 1), relu=True),
+                                  oracle.ref_conv_f32_nchw(x, w, b, pad=(1, 1), relu=True))
+
+
+def test_conv_f32_groups_beta_alpha(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-2, 2, (2, 8, 9, 9)).astype(np.float32)
+    w = rng.uniform(-1, 1, (8, 2, 3, 3)).astype(np.float32)
+    dst = rng.uniform(-1, 1, (2, 8, 9, 9)).astype(np.float32)
+    kw = dict(group=4, pad=(1, 1), beta=0.5, alpha=1.5, dst=dst)
+    np.testing.assert_array_equal(oracle.conv_f32_nchw(x, w, None, **kw), oracle.ref_conv_f32_nchw(x, w, None, **kw))
+
+
+@pytest.mark.parametrize("unsigned", [False, True])
+@pytest.mark.parametrize("k,pad,stride", [(1, 0, 1), (3, 1, 1), (3, 1, 2)])
+@pytest.mark.parametrize("elt,relu,down", [(False, True, False), (True, True, False), (True, False, True)])
+def test_conv_int8_basic_matches_reference_oracle(oracle, unsigned, k, pad, stride, elt, relu, down):
+    _need_ref(oracle)
+    rng = np.random.default_rng(7 + k + stride)
+    x = (rng.integers(0, 256, (2, 10, 10, 8)).astype(np.uint8) if unsigned
+         else rng.integers(-128, 128, (2, 10, 10, 8)).astype(np.int8))
+    w = rng.integers(-127, 128, (16, 8, k, k)).astype(np.int8)
+    b = rng.integers(-500, 500, 16).astype(np.int32)
+    sc = rng.uniform(0.001, 0.01, 16).astype(np.float32)
+    oh = oracle.conv_out_size(10, pad, 1, k, stride)
+    dst = rng.integers(-128, 128, (2, oh, oh, 16)).astype(np.int8)
+    kw = dict(pad=(pad, pad), stride=(stride, stride), relu=relu, has_elt_sum=elt, sum_scale=0.7, dst=dst,
+              round_down=down)
+    a = oracle.conv_s8_nhwc_basic(x, w, b, sc, **kw)
+    r = oracle.conv_s8_nhwc_basic(x, w, b, sc, use_ref=True, **kw)
+    np.testing.assert_array_equal(a, r)
+
+
+def test_x86_semantics_agree_with_reference_oracle_on_shared_subset(oracle):
+    """The x86-JIT restatement and conv_basic_check_int8 coincide when the bias is integral, the
+    output is s8 and there is no residual -- pins oracle_conv_s8_nhwc_x86 to the reference."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(11)
+    x = rng.integers(-128, 128, (2, 9, 9, 16)).astype(np.int8)
+    w = rng.integers(-127, 128, (32, 16, 3, 3)).astype(np.int8)
+    b = rng.integers(-1000, 1000, 32).astype(np.int32)
+    sc = rng.uniform(0.0005, 0.005, 32).astype(np.float32)
+    for relu in (False, True):
+        r = oracle.conv_s8_nhwc_basic(x, w, b, sc, pad=(1, 1), relu=relu, use_ref=True)
+        j = oracle.conv_s8_nhwc_x86(x, w, b.astype(np.float32), sc, pad=(1, 1), relu=relu, out_dtype=oracle.DT_INT8)
+        np.testing.assert_array_equal(j, r)
+
+
+@pytest.mark.parametrize("ptype", [1, 2, 3])
+@pytest.mark.parametrize("unsigned", [False, True])
+def test_pool_int8_matches_reference_oracle(oracle, ptype, unsigned):
+    _need_ref(oracle)
+    rng = np.random.default_rng(3)
+    x = (rng.integers(0, 128, (2, 13, 13, 8)).astype(np.uint8) if unsigned
+         else rng.integers(0, 128, (2, 13, 13, 8)).astype(np.int8))
+    a = oracle.pool_s8_nhwc(x, (3, 3), (1, 1), (2, 2), ptype)
+    r = oracle.pool_s8_nhwc(x, (3, 3), (1, 1), (2, 2), ptype, use_ref=True)
+    np.testing.assert_array_equal(a, r)
+
+
+def test_tensor_cmp_matches_reference(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-3, 3, 1000).astype(np.float32)
+    b = a + rng.uniform(-1e-3, 1e-3, 1000).astype(np.float32)
+    assert oracle.tensor_cmp(a, b) == pytest.approx(oracle.tensor_cmp(a, b, use_ref=True), rel=1e-12)
+
+
+def test_pool_shape_rule(oracle):
+    # Caffe ceil mode with the pad clamp (saber/funcs/pooling.h:96-125)
+    assert oracle.pool_out_size(112, 112, 3, 3, 0, 0, 2, 2) == (56, 56)
+    assert oracle.pool_out_size(224, 224, 2, 2, 0, 0, 2, 2) == (112, 112)
+    assert oracle.pool_out_size(7, 7, 3, 3, 1, 1, 2, 2) == (4, 4)
+    assert oracle.pool_out_size(6, 6, 3, 3, 1, 1, 2, 2) == (4, 4)
+    assert oracle.pool_out_size(5, 5, 2, 2, 1, 1, 2, 2) == (3, 3)      # ceil gives 4, the clamp drops one
+    assert oracle.pool_out_size(13, 13, 3, 3, 0, 0, 2, 2, floor_as_conv=True) == (6, 6)
+    assert oracle.pool_out_size(7, 7, 7, 7, 0, 0, 1, 1, global_pooling=True) == (1, 1)
+
+
+def test_bn_fold_equals_unfused_ops(oracle):
+    """parameter_fusion.cpp:86-131: conv -> BN -> Scale equals the folded conv."""
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1, 1, (1, 6, 6, 4)).astype(np.float32)
+    w = rng.uniform(-1, 1, (8, 4, 3, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, 8).astype(np.float32)
+    mean, var = rng.uniform(-0.2, 0.2, 8).astype(np.float32), rng.uniform(0.5, 1.5, 8).astype(np.float32)
+    gamma, beta = rng.uniform(0.5, 1.5, 8).astype(np.float32), rng.uniform(-0.3, 0.3, 8).astype(np.float32)
+    wf, bf = oracle.fold_bn_scale(w, b, 2.0, 1e-5, mean, var, gamma, beta)
+    fused = oracle.conv_f32_nhwc(x, wf, bf, pad=(1, 1))
+    y = oracle.conv_f32_nhwc(x, w, b, pad=(1, 1))
+    y = (y - mean / 2.0) / np.sqrt(var / 2.0 + 1e-5) * gamma + beta
+    np.testing.assert_allclose(fused, y, rtol=2e-5, atol=2e-5)
+
+
+def test_int8_conv_linearity_property(oracle):
+    """Size-independent property: with fp32 output and unit scale the x86 int8 conv is exactly
+    linear in its input (s32 accumulation is exact)."""
+    rng = np.random.default_rng(13)
+    a = rng.integers(-60, 60, (1, 14, 14, 32)).astype(np.int8)
+    b = rng.integers(-60, 60, (1, 14, 14, 32)).astype(np.int8)
+    w = rng.integers(-127, 128, (16, 32, 3, 3)).astype(np.int8)
+    f = lambda t: oracle.conv_s8_nhwc_x86(t, w, None, None, pad=(1, 1), out_dtype=oracle.DT_FLOAT)
+    np.testing.assert_array_equal(f(a) + f(b), f((a.astype(np.int16) + b).astype(np.int8)))
+
+
+def test_quantisation_rules(oracle):
+    x = np.array([0.0, 0.49, 0.5, 1.5, -0.5, -1.5, 200.0, -200.0], np.float32)
+    # secur_cast2char: roundf (half away from zero) then clamp (x86_utils.h:318-324)
+    np.testing.assert_array_equal(oracle.quant_fp32_s8(x, 1.0), np.array([0, 0, 1, 2, -1, -2, 127, -128], np.int8))
+    # weights: truncating static_cast<char>(w / (max|w|/127)) (x86_utils.h:293-323)
+    q, s = oracle.quant_weights_per_oc(np.array([[1.0, -0.999, 0.5, 0.004]], np.float32))
+    assert s[0] == np.float32(1.0 / 127.0)
+    np.testing.assert_array_equal(q, np.array([[127, -126, 63, 0]], np.int8))
+
+
+@pytest.mark.parametrize("model", ["tiny_resnet", "resnet50"])
+def test_model_walker_reproduces_golden(model, oracle):
+    """The committed golden outputs are what the oracle produces today (guards oracle drift)."""
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    gold = np.load(os.path.join(GOLD, "%s_golden.npz" % model))
+    hw = 32 if model == "tiny_resnet" else 224
+    n = 2
+    g = modelzoo.BUILDERS[model](batch=1)
+    x = modelzoo.synthetic_input(n, hw)
+    np.testing.assert_array_equal(W.run_fp32(g, x)["prob_out"], gold["prob_fp32"][:n])
+    scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration(model).items()}
+    got = W.run_int8(g, x, scales)["prob_out"]
+    np.testing.assert_array_equal(got, gold["prob_int8"][:n])
+    assert (got.argmax(1) == gold["top1_int8"][:n]).all()
+
+
+def test_softmax_eltwise_activation_oracles(oracle):
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-5, 5, (4, 10)).astype(np.float32)
+    p = oracle.softmax_f32(x, 4, 10, 1)
+    e = np.exp(x - x.max(1, keepdims=True))
+    np.testing.assert_allclose(p, e / e.sum(1, keepdims=True), rtol=1e-6)
+    a, b = rng.uniform(-1, 1, 50).astype(np.float32), rng.uniform(-1, 1, 50).astype(np.float32)
+    np.testing.assert_array_equal(oracle.eltwise_f32(a, b, 2, 1.0, 1.0, True), np.maximum(a + b, 0))
+    np.testing.assert_array_equal(oracle.activation_f32(a, 2, 0.0), np.maximum(a, 0))

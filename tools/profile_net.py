@@ -15,7 +15,8 @@ def main():
     ap.add_argument("--model", default="resnet50")
     ap.add_argument("--precision", default="int8")
     ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=20)
     a = ap.parse_args()
     from anakin_b200 import anakin_bin, api, modelzoo
     hw = 32 if a.model == "tiny_resnet" else 224
@@ -27,7 +28,7 @@ def main():
     net.set_input("input_0", modelzoo.synthetic_input(a.batch, hw))
     net.prediction()
     net.sync()
-    prof = net.profile_ops(a.iters)
+    prof = net.profile_ops(a.iters, a.reps)
     nodes = {n[0]: n for n in G.describe()}
     total = sum(ms for _, _, ms in prof)
     print("%-22s %-26s %9s  %-18s %-18s" % ("node", "op", "us", "in", "out"))
