@@ -87,50 +87,98 @@ __device__ __forceinline__ uint32_t layout_type_for_chunk(int chunk) {
 }
 
 // ----------------------------------------------------------------- swizzled panel access
-// A panel is [128 rows x pw bytes] written / read by TMA with SWIZZLE_{32,64,128}B:
-// the 16-byte chunk index is XOR-ed with address bits [7, 7+B).
-__device__ __forceinline__ uint32_t panel_off(int pw, int row, int byte_in_row) {
-    const int panel = byte_in_row / pw;
-    const int inner = byte_in_row - panel * pw;
-    const int c16 = inner >> 4;
-    const int sw = pw == 128 ? (row & 7) : (pw == 64 ? ((row >> 1) & 3) : (pw == 32 ? ((row >> 2) & 1) : 0));
-    return static_cast<uint32_t>(panel * (BLOCK_M * pw) + row * pw + ((c16 ^ sw) << 4));
-}
-__device__ __forceinline__ uint4 lds128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
-__device__ __forceinline__ void sts128(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
-
-__device__ __forceinline__ int32_t sat_s8(float f) {
-    // cvt.rni.sat.s8.f32 == round-to-nearest-even + saturate (vcvtps2dq RN + vpmovsdb)
-    int32_t r;
-    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(f));
+// A panel is [128 rows x pw bytes] (pw = 1 << lg, 32|64|128) written / read by TMA with
+// SWIZZLE_{32,64,128}B: the 16-byte chunk index is XOR-ed with address bits [7, 7+lg-4).
+struct PanelRow {       // everything about one thread's row of a panelled tile, precomputed once
+    uint32_t base;      // shared-space address of the tile + row * pw
+    int lg;             // log2(panel width in bytes)
+    int sw;             // swizzle XOR of this row
+};
+__device__ __forceinline__ PanelRow make_panel_row(uint32_t tile_saddr, int lg, int row) {
+    PanelRow r;
+    r.lg = lg;
+    r.base = tile_saddr + (static_cast<uint32_t>(row) << lg);
+    r.sw = (row >> (7 - lg)) & ((1 << (lg - 4)) - 1);
     return r;
 }
-__device__ __forceinline__ int32_t sat_u8(float f) {
-    uint32_t r;
-    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(f));
-    return static_cast<int32_t>(r);
+__device__ __forceinline__ uint32_t panel_addr(const PanelRow& r, int byte_in_row) {
+    const int panel = byte_in_row >> r.lg;
+    const int c16 = (byte_in_row & ((1 << r.lg) - 1)) >> 4;
+    return r.base + (static_cast<uint32_t>(panel) << (7 + r.lg)) + (static_cast<uint32_t>(c16 ^ r.sw) << 4);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void lds_f32x16(uint32_t saddr, float (&f)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 t = lds128(saddr + q * 16);
+        f[4 * q] = __uint_as_float(t.x); f[4 * q + 1] = __uint_as_float(t.y);
+        f[4 * q + 2] = __uint_as_float(t.z); f[4 * q + 3] = __uint_as_float(t.w);
+    }
+}
+
+// round-to-nearest-even + saturation == vcvtps2dq(RN) + vpmovsdb / vpmovusdb; four lanes -> one word
+__device__ __forceinline__ uint32_t pack4_s8(float a, float b, float c, float d) {
+    int32_t ia, ib, ic, id;
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ia) : "f"(a));
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ib) : "f"(b));
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ic) : "f"(c));
+    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(id) : "f"(d));
+    uint32_t lo, hi;
+    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(lo) : "r"(ia), "r"(ib));   // b0 = ia.b0, b1 = ib.b0
+    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(hi) : "r"(ic), "r"(id));
+    uint32_t w;
+    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(w) : "r"(lo), "r"(hi));    // lo.b0 lo.b1 hi.b0 hi.b1
+    return w;
+}
+__device__ __forceinline__ uint32_t pack4_u8(float a, float b, float c, float d) {
+    uint32_t ia, ib, ic, id;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(ia) : "f"(a));
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(ib) : "f"(b));
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(ic) : "f"(c));
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(id) : "f"(d));
+    uint32_t lo, hi, w;
+    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(lo) : "r"(ia), "r"(ib));
+    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(hi) : "r"(ic), "r"(id));
+    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(w) : "r"(lo), "r"(hi));
+    return w;
+}
+// byte lane of a word -> float (exact)
+__device__ __forceinline__ float u8_lane(uint32_t w, int lane) {
+    uint32_t b;
+    asm("bfe.u32 %0, %1, %2, 8;" : "=r"(b) : "r"(w), "r"(8 * lane));
+    return __uint2float_rn(b);
+}
+__device__ __forceinline__ float s8_lane(uint32_t w, int lane) {
+    int32_t b;
+    asm("bfe.s32 %0, %1, %2, 8;" : "=r"(b) : "r"(w), "r"(8 * lane));
+    return __int2float_rn(b);
 }
 
 // One thread, one output row, 16 consecutive channels starting at tile-local column cl.
 template <int KIND>
-__device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t (&v)[16], int row, int cl,
-                                           const float* bias_s, const float* scale_s,
-                                           const uint8_t* res_tile, uint8_t* out_tile) {
-    float f[16];
+__device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t (&v)[16], int cl, uint32_t bias_sa,
+                                           uint32_t scale_sa, const PanelRow& res_row, const PanelRow& out_row) {
+    float f[16], r[16];
     const bool has_res = p.res_panels > 0;
-    float r[16];
     if (has_res) {
         if (p.res_dtype == B200_FLOAT) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 t = lds128(res_tile + panel_off(p.res_pw, row, cl * 4 + q * 16));
+                const uint4 t = lds128(panel_addr(res_row, cl * 4 + q * 16));
                 r[4 * q] = __uint_as_float(t.x); r[4 * q + 1] = __uint_as_float(t.y);
                 r[4 * q + 2] = __uint_as_float(t.z); r[4 * q + 3] = __uint_as_float(t.w);
             }
         } else if (p.res_dtype == B200_HALF) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const uint4 t = lds128(res_tile + panel_off(p.res_pw, row, cl * 2 + q * 16));
+                const uint4 t = lds128(panel_addr(res_row, cl * 2 + q * 16));
                 const __half2* h = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -139,25 +187,26 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
                 }
             }
         } else {
-            const uint4 t = lds128(res_tile + panel_off(p.res_pw, row, cl));
+            const uint4 t = lds128(panel_addr(res_row, cl));
             const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+            if (p.res_dtype == B200_INT8) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                r[i] = (p.res_dtype == B200_INT8) ? static_cast<float>(static_cast<int8_t>(byte))
-                                                  : static_cast<float>(byte);
+                for (int i = 0; i < 16; ++i) r[i] = s8_lane(w[i >> 2], i & 3);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = u8_lane(w[i >> 2], i & 3);
             }
         }
     }
+    float bias[16];
+    lds_f32x16(bias_sa + cl * 4, bias);
     if constexpr (KIND == KIND_I8) {
         // x86 Saber int8 epilogue: (acc + bias) * scale, [relu], [+ res*sum_scale], [relu], rne+sat
+        float scale[16];
+        lds_f32x16(scale_sa + cl * 4, scale);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            f[i] = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int32_t>(v[i])), bias_s[cl + i]), scale_s[cl + i]);
-        if (p.relu && !has_res) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
+            f[i] = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int32_t>(v[i])), bias[i]), scale[i]);
         if (has_res) {
             if (p.sum_scale == 1.f) {
 #pragma unroll
@@ -166,10 +215,10 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) f[i] = __fmaf_rn(r[i], p.sum_scale, f[i]);
             }
-            if (p.relu) {
+        }
+        if (p.relu) {   // relu-before-sum only exists when there is no sum, so one clamp covers both
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
         }
     } else {
         // float epilogue: acc (+ beta*res) + bias, relu(neg_slope)
@@ -177,7 +226,7 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
         for (int i = 0; i < 16; ++i) {
             float x = __uint_as_float(v[i]);
             if (has_res) x = __fmaf_rn(p.sum_scale, r[i], x);
-            x = __fadd_rn(x, bias_s[cl + i]);
+            x = __fadd_rn(x, bias[i]);
             if (p.relu) x = x > 0.f ? x : __fmul_rn(x, p.neg_slope);
             f[i] = x;
         }
@@ -186,7 +235,7 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
     if (p.out_dtype == B200_FLOAT) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            sts128(out_tile + panel_off(p.out_pw, row, cl * 4 + q * 16),
+            sts128(panel_addr(out_row, cl * 4 + q * 16),
                    make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
                               __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
     } else if (p.out_dtype == B200_HALF) {
@@ -198,16 +247,16 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
                 __half2 h = __floats2half2_rn(f[8 * q + 2 * i], f[8 * q + 2 * i + 1]);
                 w[i] = *reinterpret_cast<uint32_t*>(&h);
             }
-            sts128(out_tile + panel_off(p.out_pw, row, cl * 2 + q * 16), make_uint4(w[0], w[1], w[2], w[3]));
+            sts128(panel_addr(out_row, cl * 2 + q * 16), make_uint4(w[0], w[1], w[2], w[3]));
         }
+    } else if (p.out_dtype == B200_INT8) {
+        sts128(panel_addr(out_row, cl),
+               make_uint4(pack4_s8(f[0], f[1], f[2], f[3]), pack4_s8(f[4], f[5], f[6], f[7]),
+                          pack4_s8(f[8], f[9], f[10], f[11]), pack4_s8(f[12], f[13], f[14], f[15])));
     } else {
-        uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int32_t q = (p.out_dtype == B200_INT8) ? sat_s8(f[i]) : sat_u8(f[i]);
-            w[i >> 2] |= (static_cast<uint32_t>(q) & 0xffu) << (8 * (i & 3));
-        }
-        sts128(out_tile + panel_off(p.out_pw, row, cl), make_uint4(w[0], w[1], w[2], w[3]));
+        sts128(panel_addr(out_row, cl),
+               make_uint4(pack4_u8(f[0], f[1], f[2], f[3]), pack4_u8(f[4], f[5], f[6], f[7]),
+                          pack4_u8(f[8], f[9], f[10], f[11]), pack4_u8(f[12], f[13], f[14], f[15])));
     }
 }
 
@@ -415,6 +464,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (p.res_panels > 0) mbar_wait(res_full_bar, 0);
         mbar_wait(tmem_full_bar, 0);  // all MMAs retired: the operand ring is free -> output staging
         tc_fence_after();
+        auto lg2 = [](int pw) { return pw == 128 ? 7 : (pw == 64 ? 6 : 5); };
+        const PanelRow out_row = make_panel_row(smem_u32(smem), lg2(p.out_pw), row);
+        const PanelRow res_row = make_panel_row(smem_u32(res_tile), lg2(p.res_pw ? p.res_pw : 128), row);
+        const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
         uint8_t* out_tile = smem;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
@@ -424,8 +477,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tmem_ld_32x32b_x16(t_row + c0, v0);
             tmem_ld_32x32b_x16(t_row + c0 + 16, v1);
             tmem_ld_wait();
-            epilogue16<MK>(p, v0, row, c0, bias_s, scale_s, res_tile, out_tile);
-            epilogue16<MK>(p, v1, row, c0 + 16, bias_s, scale_s, res_tile, out_tile);
+            epilogue16<MK>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
+            epilogue16<MK>(p, v1, c0 + 16, bias_sa, scale_sa, res_row, out_row);
         }
         tc_fence_before();
         fence_proxy_async_smem();                              // staged tile -> visible to the TMA engine
