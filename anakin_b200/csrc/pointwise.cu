@@ -228,6 +228,100 @@ __global__ void pool_q8_kernel(const uint4* __restrict__ in, uint4* __restrict__
     }
 }
 
+// ---- int8 / uint8 pooling with SIMD-in-register integer arithmetic.
+// Sums of 8-bit codes are exact in any order (taps * 255 < 2^16 for up to 257 taps), so the float
+// reference (sum in fp32, divide, nearbyintf, saturate) is reproduced bit-exactly from integer
+// partial sums: bytes are accumulated as packed 16-bit lanes (even / odd bytes of each word), max
+// uses the byte-wise video instructions. s8 codes are biased by 0x80 to unsigned and un-biased at
+// the end. LANES threads cooperate on one 16-channel output vector (1 for small windows, 8 for
+// global pooling) and combine through xor-shuffles.
+template <bool kUnsigned, int LANES>
+__global__ void pool_q8_simd_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, PoolP p) {
+    pdl_enter();
+    const int cv = p.c >> 4;
+    const long long total = 1ll * p.n * p.oh * p.ow * cv;
+    const long long tid0 = blockIdx.x * 1ll * blockDim.x + threadIdx.x;
+    const int sub = static_cast<int>(tid0 % LANES);
+    const long long nthreads = 1ll * gridDim.x * blockDim.x;
+    // all 32 lanes of a warp run the same number of iterations (the shuffles below use the full
+    // mask); groups past the end just carry zero taps and skip the store
+    const long long warp_first = (tid0 - (threadIdx.x & 31)) / LANES;
+    for (long long it = 0; warp_first + it * (nthreads / LANES) < total; ++it) {
+        const long long idx = tid0 / LANES + it * (nthreads / LANES);
+        const bool valid = idx < total;
+        const long long cidx = valid ? idx : 0;
+        const int v = static_cast<int>(cidx % cv);
+        long long t = cidx / cv;
+        const int ow = static_cast<int>(t % p.ow); t /= p.ow;
+        const int oh = static_cast<int>(t % p.oh);
+        const int n = static_cast<int>(t / p.oh);
+        int sh = oh * p.sh, eh = sh + p.wh;
+        int sw = ow * p.sw, ew = sw + p.ww;
+        if (p.ph > 0) { sh = (sh - p.ph) < 0 ? 0 : sh - p.ph; eh = (eh - p.ph) > p.h ? p.h : eh - p.ph; }
+        if (p.pw > 0) { sw = (sw - p.pw) < 0 ? 0 : sw - p.pw; ew = (ew - p.pw) > p.w ? p.w : ew - p.pw; }
+        if (eh > p.h) eh = p.h;
+        if (ew > p.w) ew = p.w;
+        const int ww = ew - sw, taps = valid ? (eh - sh) * ww : 0;
+        uint32_t mx[4] = {0u, 0u, 0u, 0u};                    // biased-unsigned byte max
+        uint32_t se[4] = {0, 0, 0, 0}, so[4] = {0, 0, 0, 0};  // packed 16-bit sums of even / odd bytes
+        const bool is_max = p.type == B200_POOL_MAX;
+#pragma unroll 4
+        for (int tp = sub; tp < taps; tp += LANES) {
+            const int kh = sh + tp / ww, kw = sw + tp % ww;
+            const uint4 x = __ldg(in + ((1ll * n * p.h + kh) * p.w + kw) * cv + v);
+            uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!kUnsigned) w[i] ^= 0x80808080u;
+                if (is_max) {
+                    mx[i] = __vmaxu4(mx[i], w[i]);
+                } else {
+                    se[i] += w[i] & 0x00FF00FFu;
+                    so[i] += (w[i] >> 8) & 0x00FF00FFu;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = LANES >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                mx[i] = __vmaxu4(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], o));
+                se[i] += __shfl_xor_sync(0xffffffffu, se[i], o);
+                so[i] += __shfl_xor_sync(0xffffffffu, so[i], o);
+            }
+        }
+        if (sub != 0 || !valid) continue;
+        uint32_t ow_[4];
+        if (is_max) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ow_[i] = kUnsigned ? mx[i] : (mx[i] ^ 0x80808080u);
+        } else {
+            const float d = (p.type == B200_POOL_AVG_INCLUDE_PAD) ? static_cast<float>(p.wh * p.ww)
+                                                                  : static_cast<float>((ew - sw) * (eh - sh));
+            const int unbias = kUnsigned ? 0 : 128 * taps;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s0 = static_cast<int>(se[i] & 0xFFFFu) - unbias, s2 = static_cast<int>(se[i] >> 16) - unbias;
+                const int s1 = static_cast<int>(so[i] & 0xFFFFu) - unbias, s3 = static_cast<int>(so[i] >> 16) - unbias;
+                const float q0 = __fdiv_rn(static_cast<float>(s0), d), q1 = __fdiv_rn(static_cast<float>(s1), d);
+                const float q2 = __fdiv_rn(static_cast<float>(s2), d), q3 = __fdiv_rn(static_cast<float>(s3), d);
+                uint32_t c0, c1, c2, c3;
+                if (kUnsigned) {
+                    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(c0) : "f"(q0)); asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(c1) : "f"(q1));
+                    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(c2) : "f"(q2)); asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(c3) : "f"(q3));
+                } else {
+                    int32_t t0, t1, t2, t3;
+                    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(t0) : "f"(q0)); asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(t1) : "f"(q1));
+                    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(t2) : "f"(q2)); asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(t3) : "f"(q3));
+                    c0 = t0 & 0xff; c1 = t1 & 0xff; c2 = t2 & 0xff; c3 = t3 & 0xff;
+                }
+                ow_[i] = (c0 & 0xffu) | ((c1 & 0xffu) << 8) | ((c2 & 0xffu) << 16) | ((c3 & 0xffu) << 24);
+            }
+        }
+        out[((1ll * n * p.oh + oh) * p.ow + ow) * cv + v] = make_uint4(ow_[0], ow_[1], ow_[2], ow_[3]);
+    }
+}
+
 // Large windows (global average pooling: 7x7 = 49 taps): one WARP per output vector. The lanes
 // fetch 32 window taps at a time in parallel (the thread-per-output kernel above serialises 49
 // dependent L2 round trips), then every lane folds them in the reference's (kh, kw) order through
@@ -596,6 +690,7 @@ __global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict_
         const int b = static_cast<int>(t / hp);
         const int y = hr - pad_h;
         const bool row_ok = y >= 0 && y < h;
+        uint32_t words[8];
         for (int tap = 0; tap < taps; ++tap) {
             const int x = q * stride_w - pad_w + tap;
             const bool ok = row_ok && tap < s && x >= 0 && x < w;
@@ -617,7 +712,10 @@ __global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict_
                     else { f = fminf(fmaxf(f, 0.f), 255.f); code = static_cast<int>(f); }
                     wd |= (static_cast<uint32_t>(code) & 0xffu) << (8 * ch);
                 }
-                reinterpret_cast<uint32_t*>(out)[o] = wd;
+                words[tap & 7] = wd;
+                if ((tap & 3) == 3)   // four taps = one 16-byte store
+                    reinterpret_cast<uint4*>(out)[o >> 2] =
+                        make_uint4(words[(tap & 7) - 3], words[(tap & 7) - 2], words[(tap & 7) - 1], words[tap & 7]);
             }
         }
     }
@@ -771,7 +869,18 @@ int b200_pool_run(const b200_pool_desc_t* d, const void* in, void* out, void* st
     } else if (d->dtype == B200_INT8 || d->dtype == B200_UINT8) {
         if (d->c % 16) return B200_INVALID_VALUE;
         const long long total = 1ll * p.n * oh * ow * (d->c / 16);
-        if (big_window) {
+        if (p.wh * p.ww <= 256) {
+            // grid covers (outputs x LANES) threads, rounded so that LANES-groups never straddle the loop bound
+            if (big_window) {
+                const unsigned g = grid_for(total * 8, block);
+                if (d->dtype == B200_UINT8) launch_pdl(pool_q8_simd_kernel<true, 8>, g, block, S(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+                else launch_pdl(pool_q8_simd_kernel<false, 8>, g, block, S(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            } else {
+                const unsigned g = grid_for(total, block);
+                if (d->dtype == B200_UINT8) launch_pdl(pool_q8_simd_kernel<true, 1>, g, block, S(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+                else launch_pdl(pool_q8_simd_kernel<false, 1>, g, block, S(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
+            }
+        } else if (big_window) {
             if (d->dtype == B200_UINT8)
                 launch_pdl(pool_warp_kernel<3>, grid_for(total * 32, block), block, S(stream),
                            static_cast<const uint4*>(in), static_cast<uint4*>(out), p);
