@@ -166,3 +166,48 @@ def test_eager_equals_cuda_graph():
     b.prediction(); b.sync()
     assert b.cuda_graph_active()
     np.testing.assert_array_equal(a.get_output(), b.get_output())
+
+
+def test_resnet101_int8_golden():
+    """BASELINE config C4 model (per-GPU shard of 4 images)."""
+    from anakin_b200 import modelzoo
+    gold = np.load(os.path.join(GOLD, "resnet101_golden.npz"))
+    g, G = _build("resnet101", 4, "int8")
+    net = _run(G, "int8", modelzoo.synthetic_input(4))
+    got = net.get_output()
+    assert (got.argmax(1) == gold["top1_int8"]).all()
+    logits, info = net.read_tensor("fc1000")
+    np.testing.assert_array_equal(_valid(logits, info).reshape(4, -1), gold["logits_int8"])
+
+
+def test_vgg16_fp32_golden():
+    """BASELINE config C3 model: 3x3 convs + the 25088x4096 fc (NCHW-flatten order)."""
+    from anakin_b200 import modelzoo
+    from oracle import pyoracle as O
+    gold = np.load(os.path.join(GOLD, "vgg16_golden.npz"))
+    g, G = _build("vgg16", 2, "fp32")
+    net = _run(G, "fp32", modelzoo.synthetic_input(2))
+    got = net.get_output()
+    mr, md = O.tensor_cmp(gold["prob_fp32"], got)
+    assert md < 1e-3 or mr <= 1e-3, (mr, md)
+    assert (got.argmax(1) == gold["top1_fp32"]).all()
+
+
+def test_mobilenet_v1_fp16_vs_fp32_oracle():
+    """BASELINE config C5 model: depthwise + 1x1 path in FP16. The reference has no FP16 NV kernels
+    (every AK_HALF impl is SaberUnImplError), so the oracle is the fp32 CPU result with an fp16-sized
+    tolerance on the probabilities; FP32 through the same graph must meet the 1e-3 criterion."""
+    from anakin_b200 import modelzoo
+    from oracle import pyoracle as O
+    gold = np.load(os.path.join(GOLD, "mobilenet_v1_golden.npz"))
+    x = modelzoo.synthetic_input(4)
+    g, G = _build("mobilenet_v1", 4, "fp32")
+    got32 = _run(G, "fp32", x).get_output()
+    mr, md = O.tensor_cmp(gold["prob_fp32"], got32)
+    assert md < 1e-3 or mr <= 1e-3, (mr, md)
+    g, G = _build("mobilenet_v1", 4, "fp16")
+    got16 = _run(G, "fp16", x).get_output()
+    assert np.isfinite(got16).all()
+    rel = np.abs(got16 - gold["prob_fp32"]).max() / gold["prob_fp32"].max()
+    assert rel < 5e-2, rel
+    assert (got16.argmax(1) == gold["top1_fp32"]).all()
