@@ -23,8 +23,9 @@
 // memory (the freed operand ring) and one thread hands it to TMA for a fully
 // coalesced store (which also clips the ragged M / N edges).
 //
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM owner + MMA
-// issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quarter = warp_idx % 4; the two warps of a quarter
+// split the tile's columns).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -46,6 +47,9 @@ constexpr int BLOCK_M = 128;
 constexpr int STAGE_K_BYTES = 128;  // K bytes per pipeline stage (4 MMAs of 32 B)
 constexpr int A_STAGE_BYTES = BLOCK_M * STAGE_K_BYTES;
 constexpr int MAX_STAGES = 12;
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each half of the columns
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int NUM_THREADS = 64 + EPI_THREADS;      // warp0 TMA, warp1 MMA, then the epilogue warps
 constexpr int MAX_SMEM = 227 * 1024;
 
 struct ConvKParams {
@@ -262,7 +266,7 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
 
 // ----------------------------------------------------------------- the kernel
 template <int KIND, int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                   const ConvKParams p, const uint32_t idesc) {
@@ -304,7 +308,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
-            mbar_init(&conv_bar[i], 128);
+            mbar_init(&conv_bar[i], EPI_THREADS);
         }
         mbar_init(tmem_full_bar, 1);
         mbar_init(res_full_bar, 1);
@@ -428,12 +432,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int quarter = warp_idx & 3;
         const int row = quarter * 32 + lane;
         // bias / scale tables (weights-side constants): filled while the main loop runs
-        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
             const bool ok = (n0 + i) < p.K;
             bias_s[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n0 + i) : 0.f;
             scale_s[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0 + i) : 1.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         if (X3) {
             // split the landed fp32 A tile in place: hi = top 19 bits, lo = x - hi (exact in fp32)
             const int etid = threadIdx.x - 64;
@@ -445,7 +449,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 uint4* hi = reinterpret_cast<uint4*>(smem + stage * SB);
                 uint4* lo = reinterpret_cast<uint4*>(smem + stage * SB + A_LO_OFF);
                 const int nvec = nsub * BLOCK_M * p.chunk / 16;
-                for (int i = etid; i < nvec; i += 128) {
+                for (int i = etid; i < nvec; i += EPI_THREADS) {
                     uint4 x = hi[i], h, l;
                     h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
                     l.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(h.x)));
@@ -470,19 +474,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
         uint8_t* out_tile = smem;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        // warps sharing a lane quarter split the tile's columns between them
+        constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+        const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
             if (n0 + c0 >= p.K) break;  // warp-uniform; TMA clips the unwritten columns anyway
             uint32_t v0[16], v1[16];
+            const bool two = (c0 + 16) < cend;   // compile-time false only for 16-column slices
             tmem_ld_32x32b_x16(t_row + c0, v0);
-            tmem_ld_32x32b_x16(t_row + c0 + 16, v1);
+            if (two) tmem_ld_32x32b_x16(t_row + c0 + 16, v1);
             tmem_ld_wait();
             epilogue16<MK>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
-            epilogue16<MK>(p, v1, c0 + 16, bias_sa, scale_sa, res_row, out_row);
+            if (two) epilogue16<MK>(p, v1, c0 + 16, bias_sa, scale_sa, res_row, out_row);
         }
         tc_fence_before();
-        fence_proxy_async_smem();                              // staged tile -> visible to the TMA engine
-        asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
+        fence_proxy_async_smem();                                          // staged tile -> visible to the TMA engine
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");    // the epilogue warps only
         if (warp_idx == 2 && lane == 0) {
             const int cols_per_panel = p.out_pw / p.out_es;
             for (int j = 0; j < p.out_panels; ++j) {
@@ -605,7 +613,7 @@ static void launch_conv(b200_conv_plan* pl, void* stream) {
     std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM); });
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = pl->grid;
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = pl->smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[1];

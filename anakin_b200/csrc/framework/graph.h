@@ -23,7 +23,7 @@ enum class Precision : int { INT4 = -10, INT8 = -2, FP16 = -1, FP32 = 0, FP64 };
 enum class OpRunType : int { SYNC, ASYNC };
 
 // framework/core/base.h:27-48
-class Status {
+class ANAKIN_EXPORT Status {
 public:
     Status() : _ok(true) {}
     Status(bool ok, const std::string& msg) : _ok(ok), _msg(msg) {}
@@ -100,7 +100,7 @@ struct Edge {
     std::string name() const { return bottom + "_" + top; }
 };
 
-class GraphCore {
+class ANAKIN_EXPORT GraphCore {
 public:
     GraphCore() {}
     const std::string& name() const { return _name; }

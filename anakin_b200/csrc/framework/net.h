@@ -24,7 +24,7 @@
 
 namespace anakin {
 
-class NetCore {
+class ANAKIN_EXPORT NetCore {
 public:
     typedef saber::Tensor<saber::NV> DTensor;
     NetCore();
@@ -98,7 +98,7 @@ public:
 
 // ---------------------------------------------------------------------------------------------
 // Worker (worker.h:69-190): thread pool, one Net per thread.
-class WorkerCore {
+class ANAKIN_EXPORT WorkerCore {
 public:
     typedef saber::Tensor<saber::NVHX86> HTensor;
     WorkerCore(const std::string& model_path, Precision precision, int thread_num);

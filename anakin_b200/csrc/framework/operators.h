@@ -23,7 +23,7 @@ using OpContext = saber::Context<Ttype>;
 
 namespace ops {
 
-class OperatorBase {
+class ANAKIN_EXPORT OperatorBase {
 public:
     typedef std::vector<saber::Tensor<saber::NV>*> TensorVec;
     virtual ~OperatorBase() {}
@@ -45,7 +45,7 @@ protected:
 typedef std::shared_ptr<OperatorBase> OperatorPtr;
 
 // OpFactory<Ttype, Ptype>::Global()[name] -> new operator (operator.h:210-257)
-class OpFactoryCore {
+class ANAKIN_EXPORT OpFactoryCore {
 public:
     typedef std::function<OperatorBase*()> Creator;
     void Register(const std::string& name, Creator c) { _creators[name] = c; }
@@ -75,10 +75,10 @@ public:
 
 // Registers every operator of this build into the three precision factories (static-init in the
 // reference via ANAKIN_REGISTER_OP_HELPER; explicit and idempotent here).
-void register_all_operators();
+ANAKIN_EXPORT void register_all_operators();
 
 // precision -> factory lookup with the reference's fallback (an INT8 net may hold fp32 nodes)
-OperatorBase* create_operator(const std::string& op_name, Precision p);
+ANAKIN_EXPORT OperatorBase* create_operator(const std::string& op_name, Precision p);
 
 }  // namespace ops
 }  // namespace anakin

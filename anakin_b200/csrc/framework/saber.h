@@ -24,6 +24,10 @@
 
 #include "../../../include/b200_saber.h"
 
+// C++ classes that user code links against are exported from libanakin_b200.so explicitly
+// (the library is built with -fvisibility=hidden).
+#define ANAKIN_EXPORT __attribute__((visibility("default")))
+
 namespace anakin {
 namespace saber {
 

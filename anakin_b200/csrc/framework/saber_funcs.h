@@ -14,7 +14,7 @@ inline int conv_out_size(int in, int pad, int dil, int k, int stride) {
 
 // One fused convolution (conv | conv+act | conv+eltwise | conv+pool | fc) bound to the
 // tcgen05 plan of the C ABI. Owns the packed weights, bias / scale tables and any scratch.
-class ConvEngine {
+class ANAKIN_EXPORT ConvEngine {
 public:
     ConvEngine();
     ~ConvEngine();
@@ -172,7 +172,7 @@ private:
 };
 
 // ------------------------------------------------------------------------------------- pointwise impls
-b200_pool_desc_t make_pool_desc(const Tensor<NV>& in, const PoolingParam<NV>& p);
+ANAKIN_EXPORT b200_pool_desc_t make_pool_desc(const Tensor<NV>& in, const PoolingParam<NV>& p);
 
 template <typename T, DataType OpDtype>
 class SaberPooling : public ImplBase<PoolingParam<T>> {

@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic work per image (BASELINE.md section 2 / SURVEY.md section 8d)
+MODEL_NAMES = {"resnet50": "ResNet-50", "resnet101": "ResNet-101", "vgg16": "VGG16", "mobilenet_v1": "MobileNet-v1"}
 GOP_PER_IMAGE = {"resnet50": 7.716, "resnet101": 15.140, "vgg16": 30.94, "mobilenet_v1": 1.137, "tiny_resnet": 0.0}
 
 
@@ -111,6 +112,8 @@ def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, 
     from oracle import model_walker as W
     from oracle import pyoracle as O
     O.build(ref=False)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use the host's cores
+    O.set_threads(min(os.cpu_count() or 1, 64))
     hw = 32 if model == "tiny_resnet" else 224
     g = modelzoo.build(model, batch=1, precision=precision if precision == "int8" else "fp32")
     scales = None
@@ -141,7 +144,7 @@ def run_reference(args):
     if rank != 0:
         return
     r = cpu_oracle_images_per_s(args.model, args.precision, args.batch, steps=args.steps, warmup=args.warmup)
-    line = {"impl": "reference", "metric": "%s %s images/sec" % (args.model, args.precision.upper()),
+    line = {"impl": "reference", "metric": "%s %s images/sec" % (MODEL_NAMES.get(args.model, args.model), args.precision.upper()),
             "value": r["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8" if args.precision == "int8" else ("f32" if args.precision == "fp32" else "f16"),
@@ -291,8 +294,7 @@ def main():
     peak_tops = P["bf16_tflops"] * mult
     achieved_tops = (gop_step / 1e3) / (conv_ms / 1e3) if conv_ms > 0 else 0.0
     line = {
-        "metric": "%s %s images/sec" % ({"resnet50": "ResNet-50", "resnet101": "ResNet-101", "vgg16": "VGG16",
-                                         "mobilenet_v1": "MobileNet-v1"}.get(model, model), prec.upper()),
+        "metric": "%s %s images/sec" % (MODEL_NAMES.get(model, model), prec.upper()),
         "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8" if prec == "int8" else ("f32" if prec == "fp32" else "f16"), "data": "synthetic",

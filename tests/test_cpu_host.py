@@ -196,3 +196,28 @@ def test_model_broadcast_and_sharding_world_size_2_gloo():
     assert len(lines) == 2
     a, b = lines[0].split()[1:], lines[1].split()[1:]
     assert a == b and int(a[0]) > 100000
+
+
+def _build_example(tmpdir):
+    exe = os.path.join(tmpdir, "example_nv_cnn_net")
+    cmd = ["g++", "-std=c++17", "-O1", "-I/usr/local/cuda/include", os.path.join(ROOT, "examples", "example_nv_cnn_net.cpp"),
+           "-L" + os.path.join(ROOT, "anakin_b200", "lib"), "-lanakin_b200", "-lb200saber", "-L/usr/local/cuda/lib64",
+           "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "anakin_b200", "lib"), "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return exe
+
+
+def test_cpp_api_example_builds_and_refuses_without_gpu():
+    """The reference's own user program (examples/cuda/example_nv_cnn_net.cpp) compiles against the
+    C++ headers (Graph<NV,P>, Net<NV,P>) and, on a GPU-less box, fails loudly at Net::init."""
+    import torch
+    from anakin_b200 import modelzoo
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d)
+        model = os.path.join(d, "tiny.anakin.bin")
+        modelzoo.save(modelzoo.build("tiny_resnet", 1, "int8"), model)
+        if torch.cuda.is_available():
+            pytest.skip("covered by the gpu test")
+        r = subprocess.run([exe, model, "2", "int8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stdout, r.stdout

@@ -211,3 +211,33 @@ def test_mobilenet_v1_fp16_vs_fp32_oracle():
     rel = np.abs(got16 - gold["prob_fp32"]).max() / gold["prob_fp32"].max()
     assert rel < 5e-2, rel
     assert (got16.argmax(1) == gold["top1_fp32"]).all()
+
+
+def test_cpp_example_program_runs():
+    """examples/example_nv_cnn_net.cpp (the reference's user program) end to end in C++."""
+    import subprocess
+    from anakin_b200 import modelzoo
+    from test_cpu_host import _build_example
+    gold = np.load(os.path.join(GOLD, "tiny_resnet_golden.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_example(d)
+        model = os.path.join(d, "tiny.anakin.bin")
+        modelzoo.save(modelzoo.build("tiny_resnet", 1, "int8"), model)
+        r = subprocess.run([exe, model, "2", "int8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    assert "aveage time" in r.stdout and r.stdout.count("top-1 class") == 2, r.stdout
+
+
+def test_worker_sync_prediction_two_threads():
+    """Worker<NV,INT8>(model, 2): per-thread Nets built from one loaded graph (worker.cpp:10-151)."""
+    from anakin_b200 import api, modelzoo
+    gold = np.load(os.path.join(GOLD, "tiny_resnet_golden.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        model = os.path.join(d, "tiny.anakin.bin")
+        modelzoo.save(modelzoo.build("tiny_resnet", 4, "int8"), model)
+        w = api.Worker(model, "int8", threads=2, devices=(0,), batch=4)
+        x = modelzoo.synthetic_input(4, 32)
+        for _ in range(6):
+            out = w.sync_prediction(x, 4 * 12).reshape(4, 12)[:, :10]
+            np.testing.assert_allclose(out, gold["prob_int8"], rtol=1e-4, atol=1e-6)
+        del w
