@@ -71,6 +71,8 @@ struct ConvKParams {
     int32_t out_pw;      // output panel width in bytes (32|64|128) = TMA-store box inner extent
     int32_t out_panels;  // BN*out_es / out_pw
     int32_t res_es, res_pw, res_panels;  // same for the residual tile (0 panels = no residual)
+    int32_t split;       // split-K factor = cluster size along z (1, 2 or 4)
+    int32_t part_off;    // byte offset (from the smem base) of the partial-accumulator buffers in rank 0
     const float* bias;
     const float* scale;
 };
@@ -299,6 +301,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int num_stage_iters = (p.KS + subs_per_stage - 1) / subs_per_stage;
     const int m0 = blockIdx.x * BLOCK_M;
     const int n0 = blockIdx.y * BN;
+    // split-K: the `split` CTAs of a cluster (along z) each take a contiguous range of the k loop and
+    // rank 0 folds the partial accumulators it receives through distributed shared memory.
+    const int split = p.split;
+    const int rank = split > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int it_begin = num_stage_iters * rank / split;
+    const int it_end = num_stage_iters * (rank + 1) / split;
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -328,7 +336,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp_idx == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
-            if (p.res_panels > 0) {
+            if (p.res_panels > 0 && rank == 0) {
                 mbar_arrive_expect_tx(res_full_bar, p.res_panels * BLOCK_M * p.res_pw);
                 const int cols_per_panel = p.res_pw / p.res_es;
                 for (int j = 0; j < p.res_panels; ++j)
@@ -343,10 +351,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int base_h = p0 * p.stride_h - p.pad_h;
             const uint32_t a_sub_bytes = BLOCK_M * p.chunk;
             const uint32_t b_sub_bytes = BN * p.chunk;
-            int ks = 0, r = 0, s = 0, cc = 0;
+            int ks = it_begin * subs_per_stage;
+            int cc = ks % p.CC;
+            const int tap0 = ks / p.CC;
+            int r = tap0 / p.S, s = tap0 - r * p.S;
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < num_stage_iters; ++it) {
+            for (int it = it_begin; it < it_end; ++it) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 const int nsub = min(subs_per_stage, p.KS - ks);
                 mbar_arrive_expect_tx(&full_bar[stage], nsub * (a_sub_bytes + (X3 ? 2 : 1) * b_sub_bytes));
@@ -378,11 +389,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t lt = layout_type_for_chunk(p.chunk);
             const uint32_t a_sub_bytes = BLOCK_M * p.chunk;
             const uint32_t b_sub_bytes = BN * p.chunk;
-            int ks = 0;
+            int ks = it_begin * subs_per_stage;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t accum = 0;
-            for (int it = 0; it < num_stage_iters; ++it) {
+            for (int it = it_begin; it < it_end; ++it) {
                 mbar_wait(X3 ? &conv_bar[stage] : &full_bar[stage], phase);
                 tc_fence_after();
                 const int nsub = min(subs_per_stage, p.KS - ks);
@@ -429,8 +440,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         __syncwarp();
     } else {
         // ===================== epilogue warps =====================
-        const int quarter = warp_idx & 3;
-        const int row = quarter * 32 + lane;
         // bias / scale tables (weights-side constants): filled while the main loop runs
         for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
             const bool ok = (n0 + i) < p.K;
@@ -441,9 +450,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (X3) {
             // split the landed fp32 A tile in place: hi = top 19 bits, lo = x - hi (exact in fp32)
             const int etid = threadIdx.x - 64;
-            int ks = 0, stage = 0;
+            int ks = it_begin * subs_per_stage, stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < num_stage_iters; ++it) {
+            for (int it = it_begin; it < it_end; ++it) {
                 mbar_wait(&full_bar[stage], phase);
                 const int nsub = min(subs_per_stage, p.KS - ks);
                 uint4* hi = reinterpret_cast<uint4*>(smem + stage * SB);
@@ -465,18 +474,73 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
+        mbar_wait(tmem_full_bar, 0);  // all of this CTA's MMAs retired: its operand ring is free
+        tc_fence_after();
+    }
+
+    constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);   // warps sharing a lane quarter split the columns
+    constexpr uint32_t PART_BYTES = BLOCK_M * BN * 4;     // one CTA's raw 32-bit accumulator tile
+    if (split > 1) {
+        tc_fence_before();
+        __syncwarp();         // the cluster barrier is warp-aligned: reconverge the single-lane role warps
+        cluster_sync_all();   // every CTA of the cluster has finished its MMAs -> rank 0's ring may be written
+        if (rank > 0 && warp_idx >= 2) {
+            // ship this CTA's partial accumulators into rank 0's shared memory:
+            // layout [16-column group][row][16 x 32 bit], 64 contiguous bytes per thread
+            const int quarter = warp_idx & 3;
+            const int row = quarter * 32 + lane;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+            const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
+            const uint32_t dst0 = map_to_cta(smem_u32(smem) + p.part_off + (rank - 1) * PART_BYTES, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                if (n0 + c0 >= p.K) break;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(t_row + c0, v);
+                tmem_ld_wait();
+                const uint32_t d = dst0 + (static_cast<uint32_t>((c0 >> 4) * BLOCK_M + row) << 6);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    st_cluster_v4(d + q4 * 16, v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+            }
+            tc_fence_before();
+        }
+        __syncwarp();
+        cluster_sync_all();   // partials have landed in rank 0
+    }
+
+    if (warp_idx >= 2 && rank == 0) {
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;
         if (p.res_panels > 0) mbar_wait(res_full_bar, 0);
-        mbar_wait(tmem_full_bar, 0);  // all MMAs retired: the operand ring is free -> output staging
         tc_fence_after();
         auto lg2 = [](int pw) { return pw == 128 ? 7 : (pw == 64 ? 6 : 5); };
         const PanelRow out_row = make_panel_row(smem_u32(smem), lg2(p.out_pw), row);
         const PanelRow res_row = make_panel_row(smem_u32(res_tile), lg2(p.res_pw ? p.res_pw : 128), row);
         const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
+        const uint32_t part_sa = smem_u32(smem) + p.part_off;
         uint8_t* out_tile = smem;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        // warps sharing a lane quarter split the tile's columns between them
-        constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
         const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
+        // fold the other ranks' partial sums into 16 accumulator columns (rank order: deterministic)
+        auto add_partials = [&](uint32_t (&v)[16], int c0) {
+            for (int r2 = 1; r2 < split; ++r2) {
+                const uint32_t src = part_sa + (r2 - 1) * PART_BYTES + (static_cast<uint32_t>((c0 >> 4) * BLOCK_M + row) << 6);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint4 t = lds128(src + q4 * 16);
+                    if (MK == KIND_I8) {
+                        v[4 * q4] += t.x; v[4 * q4 + 1] += t.y; v[4 * q4 + 2] += t.z; v[4 * q4 + 3] += t.w;
+                    } else {
+                        v[4 * q4] = __float_as_uint(__fadd_rn(__uint_as_float(v[4 * q4]), __uint_as_float(t.x)));
+                        v[4 * q4 + 1] = __float_as_uint(__fadd_rn(__uint_as_float(v[4 * q4 + 1]), __uint_as_float(t.y)));
+                        v[4 * q4 + 2] = __float_as_uint(__fadd_rn(__uint_as_float(v[4 * q4 + 2]), __uint_as_float(t.z)));
+                        v[4 * q4 + 3] = __float_as_uint(__fadd_rn(__uint_as_float(v[4 * q4 + 3]), __uint_as_float(t.w)));
+                    }
+                }
+            }
+        };
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
             if (n0 + c0 >= p.K) break;  // warp-uniform; TMA clips the unwritten columns anyway
@@ -485,6 +549,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tmem_ld_32x32b_x16(t_row + c0, v0);
             if (two) tmem_ld_32x32b_x16(t_row + c0 + 16, v1);
             tmem_ld_wait();
+            if (split > 1) {
+                add_partials(v0, c0);
+                if (two) add_partials(v1, c0 + 16);
+            }
             epilogue16<MK>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
             if (two) epilogue16<MK>(p, v1, c0 + 16, bias_sa, scale_sa, res_row, out_row);
         }
@@ -616,11 +684,18 @@ static void launch_conv(b200_conv_plan* pl, void* stream) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = pl->smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (pl->kp.split > 1) {   // split-K: the z-CTAs of one tile form a cluster
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 1;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = static_cast<unsigned>(pl->kp.split);
+        cfg.numAttrs = 2;
+    }
     cudaLaunchKernelEx(&cfg, kern, pl->map_a, pl->map_b, pl->map_out, pl->map_res, pl->kp, pl->idesc);
     count_launch();
 }
@@ -874,11 +949,25 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     const int staging = BLOCK_M * bn * out_es;
     const int subs = STAGE_K_BYTES / g.chunk;
     const int k_iters = (g.KS + subs - 1) / subs;
-    const int budget = (ctas > sms) ? (MAX_SMEM / 2 - 2048) : MAX_SMEM;
+    // split-K for sub-wave grids with a long k loop (deep 3x3 / wide 1x1 layers on small feature maps):
+    // one SM's TMA engine cannot feed such a loop fast enough, so 2 or 4 CTAs (a cluster) share it.
+    int split = 1;
+    static const bool split_enabled = [] { const char* e = getenv("B200_SABER_SPLITK"); return !(e && e[0] == '0'); }();
+    if (split_enabled && k_iters >= 6 && ctas * 2 <= sms) {
+        split = 4;
+        while (split > 1 && (ctas * split > sms + sms / 4 || k_iters / split < 3)) split >>= 1;
+    }
+    kp.split = split;
+    const int part_bytes = (split - 1) * BLOCK_M * bn * 4;
+    const int staging_al = (staging + 1023) & ~1023;
+    kp.part_off = staging_al;
+    pl->grid.z = split;
+    const int k_iters_local = (k_iters + split - 1) / split;
+    const int budget = (ctas * split > sms) ? (MAX_SMEM / 2 - 2048) : MAX_SMEM;
     int stages = (budget - fixed) / sb;
-    if (stages > k_iters) stages = k_iters;
+    if (stages > k_iters_local) stages = k_iters_local;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    const int min_stages = (staging + sb - 1) / sb;
+    const int min_stages = (staging_al + part_bytes + sb - 1) / sb;
     if (stages < min_stages) stages = min_stages;
     if (stages < 1) stages = 1;
     if (stages < 2 && k_iters >= 2 && 2 * sb + fixed <= MAX_SMEM) stages = 2;  // never serialise load / MMA
