@@ -877,6 +877,10 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
         bn = 32;
         if (kr32 >= 64 && tiles_m * ((d->k + 63) / 64) == tiles_m * ((d->k + 31) / 32)) bn = 64;
     }
+    if (const char* e = getenv("B200_SABER_FORCE_BN")) {   // tuning experiments only
+        const int fb = atoi(e);
+        if ((fb == 32 || fb == 64 || fb == 128 || fb == 256) && fb <= max_bn) bn = fb;
+    }
     pl->bn = bn;
     pl->grid = dim3(tiles_m, (d->k + bn - 1) / bn, 1);
     const int ctas = tiles_m * static_cast<int>(pl->grid.y);
@@ -956,6 +960,10 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     if (split_enabled && k_iters >= 6 && ctas * 2 <= sms) {
         split = 4;
         while (split > 1 && (ctas * split > sms + sms / 4 || k_iters / split < 3)) split >>= 1;
+    }
+    if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) {   // tuning experiments only
+        const int fs = atoi(e);
+        if ((fs == 1 || fs == 2 || fs == 4) && k_iters >= fs) split = fs;
     }
     kp.split = split;
     const int part_bytes = (split - 1) * BLOCK_M * bn * 4;
