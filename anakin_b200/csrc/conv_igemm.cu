@@ -351,89 +351,87 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int base_h = p0 * p.stride_h - p.pad_h;
             const uint32_t a_sub_bytes = BLOCK_M * p.chunk;
             const uint32_t b_sub_bytes = BN * p.chunk;
+            const uint32_t tx_per_sub = a_sub_bytes + (X3 ? 2 : 1) * b_sub_bytes;
+            // lean single-thread loop: 32-bit shared addresses and running coordinates only
+            const uint32_t ring_sa = smem_u32(smem), full_sa0 = smem_u32(full_bar), empty_sa0 = smem_u32(empty_bar);
             int ks = it_begin * subs_per_stage;
             int cc = ks % p.CC;
             const int tap0 = ks / p.CC;
             int r = tap0 / p.S, s = tap0 - r * p.S;
+            int c_coord = cc * p.chunk_el, k_coord = ks * p.chunk_el;
+            int off_w = s * p.dil_w, off_h = r * p.dil_h;
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, stage_sa = ring_sa, full_sa = full_sa0, empty_sa = empty_sa0;
+            const bool may_pad = p.KS != p.KS_real;
             for (int it = it_begin; it < it_end; ++it) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_wait_sa(empty_sa, phase ^ 1);
                 const int nsub = min(subs_per_stage, p.KS - ks);
-                mbar_arrive_expect_tx(&full_bar[stage], nsub * (a_sub_bytes + (X3 ? 2 : 1) * b_sub_bytes));
-                uint8_t* a_dst = smem + stage * SB;
-                uint8_t* b_dst = a_dst + B_OFF;
+                mbar_arrive_expect_tx_sa(full_sa, nsub * tx_per_sub);
+                uint32_t a_dst = stage_sa, b_dst = stage_sa + B_OFF, bl_dst = stage_sa + B_LO_OFF;
                 for (int j = 0; j < nsub; ++j) {
                     // the padding k-step (ks == KS_real) re-reads tap (0,0); its weights are zero
-                    const bool pad_step = ks >= p.KS_real;
-                    const int rr = pad_step ? 0 : r, ss = pad_step ? 0 : s, c_ = pad_step ? 0 : cc;
-                    tma_load_im2col_4d(&map_a, &full_bar[stage], a_dst + j * a_sub_bytes, c_ * p.chunk_el,
-                                       base_w, base_h, n_img, static_cast<uint16_t>(ss * p.dil_w),
-                                       static_cast<uint16_t>(rr * p.dil_h));
-                    tma_load_2d(&map_b, &full_bar[stage], b_dst + j * b_sub_bytes, ks * p.chunk_el, n0);
+                    const bool pad_step = may_pad && ks >= p.KS_real;
+                    tma_load_im2col_4d_sa(&map_a, full_sa, a_dst, pad_step ? 0 : c_coord, base_w, base_h, n_img,
+                                          static_cast<uint16_t>(pad_step ? 0 : off_w),
+                                          static_cast<uint16_t>(pad_step ? 0 : off_h));
+                    tma_load_2d_sa(&map_b, full_sa, b_dst, k_coord, n0);
                     if (X3)  // the W-low image follows the W-high image (row offset K)
-                        tma_load_2d(&map_b, &full_bar[stage], a_dst + B_LO_OFF + j * b_sub_bytes, ks * p.chunk_el,
-                                    p.K + n0);
+                        tma_load_2d_sa(&map_b, full_sa, bl_dst, k_coord, p.K + n0);
+                    a_dst += a_sub_bytes; b_dst += b_sub_bytes; bl_dst += b_sub_bytes;
                     ++ks;
+                    k_coord += p.chunk_el;
+                    c_coord += p.chunk_el;
                     if (++cc == p.CC) {
-                        cc = 0;
-                        if (++s == p.S) { s = 0; ++r; }
+                        cc = 0; c_coord = 0;
+                        off_w += p.dil_w;
+                        if (++s == p.S) { s = 0; off_w = 0; ++r; off_h += p.dil_h; }
                     }
                 }
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                stage_sa += SB; full_sa += 8; empty_sa += 8;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; stage_sa = ring_sa; full_sa = full_sa0; empty_sa = empty_sa0; }
             }
         }
     } else if (warp_idx == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
+            // descriptors as (lo, hi) words: lo = addr>>4 | LBO>>4 << 16, hi = SBO>>4 | version 1 << 14 | layout << 29;
+            // between MMAs only `lo` moves, by 32-bit adds
             const uint32_t lt = layout_type_for_chunk(p.chunk);
-            const uint32_t a_sub_bytes = BLOCK_M * p.chunk;
-            const uint32_t b_sub_bytes = BN * p.chunk;
+            const uint32_t a_sub16 = (BLOCK_M * p.chunk) >> 4, b_sub16 = (BN * p.chunk) >> 4;
+            const bool swz = p.chunk >= 32;
+            const uint32_t hi = (swz ? (8u * p.chunk) >> 4 : 128u >> 4) | (1u << 14) | (lt << 29);
+            const uint32_t a_lbo = (swz ? 1u : a_sub16) << 16, b_lbo = (swz ? 1u : b_sub16) << 16;
+            const int mma_per_sub = swz ? (p.chunk >> 5) : 1;
+            const int sub_step = swz ? 1 : 2;   // 16-byte chunks: one K=32B MMA spans two sub-tiles (LBO = sub-tile)
+            const uint32_t ring16 = smem_u32(smem) >> 4;
+            const uint32_t full_sa0 = smem_u32(X3 ? conv_bar : full_bar), empty_sa0 = smem_u32(empty_bar);
             int ks = it_begin * subs_per_stage;
             int stage = 0;
-            uint32_t phase = 0;
-            uint32_t accum = 0;
+            uint32_t phase = 0, accum = 0, stage16 = ring16, full_sa = full_sa0, empty_sa = empty_sa0;
             for (int it = it_begin; it < it_end; ++it) {
-                mbar_wait(X3 ? &conv_bar[stage] : &full_bar[stage], phase);
+                mbar_wait_sa(full_sa, phase);
                 tc_fence_after();
                 const int nsub = min(subs_per_stage, p.KS - ks);
-                const uint32_t a_base = smem_u32(smem + stage * SB);
-                const uint32_t b_base = a_base + B_OFF;
-                if (p.chunk >= 32) {
-                    const uint32_t sbo = 8u * p.chunk;
-                    const int mma_per_sub = p.chunk >> 5;
-                    for (int j = 0; j < nsub; ++j) {
-                        for (int q = 0; q < mma_per_sub; ++q) {
-                            const uint64_t ad = make_smem_desc(a_base + j * a_sub_bytes + q * 32, 16, sbo, lt);
-                            const uint64_t bd = make_smem_desc(b_base + j * b_sub_bytes + q * 32, 16, sbo, lt);
-                            tc_mma<MK>(tmem_base, ad, bd, idesc, accum);
-                            accum = 1;
-                            if (X3) {
-                                const uint64_t al = make_smem_desc(a_base + A_LO_OFF + j * a_sub_bytes + q * 32, 16, sbo, lt);
-                                const uint64_t bl = make_smem_desc(a_base + B_LO_OFF + j * b_sub_bytes + q * 32, 16, sbo, lt);
-                                tc_mma<MK>(tmem_base, al, bd, idesc, 1);
-                                tc_mma<MK>(tmem_base, ad, bl, idesc, 1);
-                            }
-                        }
-                    }
-                } else {
-                    // 16-byte chunks: one K=32B MMA spans two sub-tiles (no-swizzle, LBO = sub-tile)
-                    for (int j = 0; j < nsub; j += 2) {
-                        const uint64_t ad = make_smem_desc(a_base + j * a_sub_bytes, a_sub_bytes, 128, 0);
-                        const uint64_t bd = make_smem_desc(b_base + j * b_sub_bytes, b_sub_bytes, 128, 0);
-                        tc_mma<MK>(tmem_base, ad, bd, idesc, accum);
+                uint32_t a16 = stage16, b16 = stage16 + (B_OFF >> 4);
+                for (int j = 0; j < nsub; j += sub_step) {
+                    for (int q = 0; q < mma_per_sub; ++q) {
+                        const uint32_t a_lo = ((a16 + 2 * q) & 0x3FFFu) | a_lbo, b_lo = ((b16 + 2 * q) & 0x3FFFu) | b_lbo;
+                        tc_mma_lohi<MK>(tmem_base, a_lo, hi, b_lo, hi, idesc, accum);
                         accum = 1;
                         if (X3) {
-                            const uint64_t al = make_smem_desc(a_base + A_LO_OFF + j * a_sub_bytes, a_sub_bytes, 128, 0);
-                            const uint64_t bl = make_smem_desc(a_base + B_LO_OFF + j * b_sub_bytes, b_sub_bytes, 128, 0);
-                            tc_mma<MK>(tmem_base, al, bd, idesc, 1);
-                            tc_mma<MK>(tmem_base, ad, bl, idesc, 1);
+                            const uint32_t al_lo = ((a16 + (A_LO_OFF >> 4) + 2 * q) & 0x3FFFu) | a_lbo;
+                            const uint32_t bl_lo = ((b16 + ((B_LO_OFF - B_OFF) >> 4) + 2 * q) & 0x3FFFu) | b_lbo;
+                            tc_mma_lohi<MK>(tmem_base, al_lo, hi, b_lo, hi, idesc, 1);
+                            tc_mma_lohi<MK>(tmem_base, a_lo, hi, bl_lo, hi, idesc, 1);
                         }
                     }
+                    a16 += sub_step * a_sub16;
+                    b16 += sub_step * b_sub16;
                 }
                 ks += nsub;
-                tc_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                tc_commit_sa(empty_sa);  // frees this smem stage once the MMAs retire
+                stage16 += SB >> 4; full_sa += 8; empty_sa += 8;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; stage16 = ring16; full_sa = full_sa0; empty_sa = empty_sa0; }
             }
             tc_commit(tmem_full_bar);
         }
