@@ -11,7 +11,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libanakin_b200.so")
+# ANAKIN_B200_LIBDIR: alternative directory holding both .so files (A/B experiments between builds)
+_LIBDIR = os.environ.get("ANAKIN_B200_LIBDIR") or os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(_LIBDIR, "libanakin_b200.so")
 
 FP32, FP16, INT8 = 0, -1, -2
 PRECISIONS = {"fp32": FP32, "fp16": FP16, "int8": INT8}

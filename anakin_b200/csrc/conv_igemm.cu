@@ -955,9 +955,12 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     // one SM's TMA engine cannot feed such a loop fast enough, so 2 or 4 CTAs (a cluster) share it.
     int split = 1;
     static const bool split_enabled = [] { const char* e = getenv("B200_SABER_SPLITK"); return !(e && e[0] == '0'); }();
-    if (split_enabled && k_iters >= 6 && ctas * 2 <= sms) {
-        split = 4;
-        while (split > 1 && (ctas * split > sms + sms / 4 || k_iters / split < 3)) split >>= 1;
+    // Measured (tools/tile_tune.py): a CTA's k loop advances at ~0.25 us per 128-byte k-iteration -- one
+    // SM ingests only ~42 B/clk from L2 -- and the two cluster barriers + DSMEM hop cost ~1.5 us, so
+    // splitting pays only for long loops on grids that stay within one wave.
+    if (split_enabled && k_iters >= 24 && ctas * 2 <= sms) {
+        split = 2;
+        if (k_iters >= 32 && ctas * 4 <= sms) split = 4;
     }
     if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) {   // tuning experiments only
         const int fs = atoi(e);

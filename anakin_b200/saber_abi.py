@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200saber.so")
+# ANAKIN_B200_LIBDIR: alternative directory holding both .so files (A/B experiments between builds)
+_LIBDIR = os.environ.get("ANAKIN_B200_LIBDIR") or os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(_LIBDIR, "libb200saber.so")
 
 # SaberStatus (reference saber/saber_types.h:223-233)
 SUCCESS = -1
