@@ -267,7 +267,7 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
 }
 
 // ----------------------------------------------------------------- the kernel
-template <int KIND, int BN>
+template <int KIND, int BN, bool SPLITK>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
@@ -303,10 +303,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int n0 = blockIdx.y * BN;
     // split-K: the `split` CTAs of a cluster (along z) each take a contiguous range of the k loop and
     // rank 0 folds the partial accumulators it receives through distributed shared memory.
-    const int split = p.split;
-    const int rank = split > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-    const int it_begin = num_stage_iters * rank / split;
-    const int it_end = num_stage_iters * (rank + 1) / split;
+    // (compiled out of the SPLITK = false instantiations, which most layers use)
+    const int split = SPLITK ? p.split : 1;
+    const int rank = SPLITK ? static_cast<int>(cluster_ctarank()) : 0;
+    const int it_begin = SPLITK ? num_stage_iters * rank / split : 0;
+    const int it_end = SPLITK ? num_stage_iters * (rank + 1) / split : num_stage_iters;
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -478,7 +479,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);   // warps sharing a lane quarter split the columns
     constexpr uint32_t PART_BYTES = BLOCK_M * BN * 4;     // one CTA's raw 32-bit accumulator tile
-    if (split > 1) {
+    if (SPLITK) {
         tc_fence_before();
         __syncwarp();         // the cluster barrier is warp-aligned: reconverge the single-lane role warps
         cluster_sync_all();   // every CTA of the cluster has finished its MMAs -> rank 0's ring may be written
@@ -547,7 +548,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tmem_ld_32x32b_x16(t_row + c0, v0);
             if (two) tmem_ld_32x32b_x16(t_row + c0 + 16, v1);
             tmem_ld_wait();
-            if (split > 1) {
+            if (SPLITK) {
                 add_partials(v0, c0);
                 if (two) add_partials(v1, c0 + 16);
             }
@@ -672,9 +673,9 @@ struct b200_conv_plan {
     void (*launch)(b200_conv_plan*, void* stream);
 };
 
-template <int KIND, int BN>
+template <int KIND, int BN, bool SPLITK>
 static void launch_conv(b200_conv_plan* pl, void* stream) {
-    auto kern = conv_igemm_kernel<KIND, BN>;
+    auto kern = conv_igemm_kernel<KIND, BN, SPLITK>;
     static std::once_flag once;
     std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM); });
     cudaLaunchConfig_t cfg{};
@@ -701,10 +702,19 @@ static void launch_conv(b200_conv_plan* pl, void* stream) {
 template <int KIND>
 static bool select_launch(b200_conv_plan* pl) {
     switch (pl->bn) {
-        case 32: pl->launch = launch_conv<KIND, 32>; return true;
-        case 64: pl->launch = launch_conv<KIND, 64>; return true;
-        case 128: pl->launch = launch_conv<KIND, 128>; return true;
-        case 256: pl->launch = launch_conv<KIND, 256>; return true;
+        case 32: pl->launch = launch_conv<KIND, 32, false>; return true;
+        case 64: pl->launch = launch_conv<KIND, 64, false>; return true;
+        case 128: pl->launch = launch_conv<KIND, 128, false>; return true;
+        case 256: pl->launch = launch_conv<KIND, 256, false>; return true;
+    }
+    return false;
+}
+// split-K instantiations exist for the narrow tiles only (the heuristic never splits wide ones)
+template <int KIND>
+static bool select_launch_split(b200_conv_plan* pl) {
+    switch (pl->bn) {
+        case 32: pl->launch = launch_conv<KIND, 32, true>; return true;
+        case 64: pl->launch = launch_conv<KIND, 64, true>; return true;
     }
     return false;
 }
@@ -965,6 +975,14 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) {   // tuning experiments only
         const int fs = atoi(e);
         if ((fs == 1 || fs == 2 || fs == 4) && k_iters >= fs) split = fs;
+    }
+    if (split > 1) {
+        bool sok = false;
+        if (d->math == B200_MATH_I8) sok = select_launch_split<KIND_I8>(pl);
+        else if (d->math == B200_MATH_F16) sok = select_launch_split<KIND_F16>(pl);
+        else if (d->math == B200_MATH_TF32X3) sok = select_launch_split<KIND_TF32X3>(pl);
+        else sok = select_launch_split<KIND_TF32>(pl);
+        if (!sok) split = 1;   // wide tile: no split variant
     }
     kp.split = split;
     const int part_bytes = (split - 1) * BLOCK_M * bn * 4;
