@@ -173,15 +173,17 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
                                            uint32_t scale_sa, const PanelRow& res_row, const PanelRow& out_row) {
     float f[16], r[16];
     const bool has_res = p.res_panels > 0;
+    // residual / output element types that can occur: int8 nets carry s8 | u8 residuals and write
+    // s8 | u8 | f32 (the fc feeding softmax); float nets carry and write their own type (or f32).
     if (has_res) {
-        if (p.res_dtype == B200_FLOAT) {
+        if (KIND != KIND_I8 && p.res_dtype == B200_FLOAT) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint4 t = lds128(panel_addr(res_row, cl * 4 + q * 16));
                 r[4 * q] = __uint_as_float(t.x); r[4 * q + 1] = __uint_as_float(t.y);
                 r[4 * q + 2] = __uint_as_float(t.z); r[4 * q + 3] = __uint_as_float(t.w);
             }
-        } else if (p.res_dtype == B200_HALF) {
+        } else if (KIND == KIND_F16 && p.res_dtype == B200_HALF) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const uint4 t = lds128(panel_addr(res_row, cl * 2 + q * 16));
@@ -192,7 +194,7 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
                     r[8 * q + 2 * i] = x.x; r[8 * q + 2 * i + 1] = x.y;
                 }
             }
-        } else {
+        } else if (KIND == KIND_I8) {
             const uint4 t = lds128(panel_addr(res_row, cl));
             const uint32_t w[4] = {t.x, t.y, t.z, t.w};
             if (p.res_dtype == B200_INT8) {
@@ -244,7 +246,7 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
             sts128(panel_addr(out_row, cl * 4 + q * 16),
                    make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
                               __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
-    } else if (p.out_dtype == B200_HALF) {
+    } else if (KIND == KIND_F16 && p.out_dtype == B200_HALF) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             uint32_t w[4];
@@ -255,11 +257,11 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
             }
             sts128(panel_addr(out_row, cl * 2 + q * 16), make_uint4(w[0], w[1], w[2], w[3]));
         }
-    } else if (p.out_dtype == B200_INT8) {
+    } else if (KIND == KIND_I8 && p.out_dtype == B200_INT8) {
         sts128(panel_addr(out_row, cl),
                make_uint4(pack4_s8(f[0], f[1], f[2], f[3]), pack4_s8(f[4], f[5], f[6], f[7]),
                           pack4_s8(f[8], f[9], f[10], f[11]), pack4_s8(f[12], f[13], f[14], f[15])));
-    } else {
+    } else if (KIND == KIND_I8) {
         sts128(panel_addr(out_row, cl),
                make_uint4(pack4_u8(f[0], f[1], f[2], f[3]), pack4_u8(f[4], f[5], f[6], f[7]),
                           pack4_u8(f[8], f[9], f[10], f[11]), pack4_u8(f[12], f[13], f[14], f[15])));
@@ -369,6 +371,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int nsub = min(subs_per_stage, p.KS - ks);
                 mbar_arrive_expect_tx_sa(full_sa, nsub * tx_per_sub);
                 uint32_t a_dst = stage_sa, b_dst = stage_sa + B_OFF, bl_dst = stage_sa + B_LO_OFF;
+#pragma unroll 1
                 for (int j = 0; j < nsub; ++j) {
                     // the padding k-step (ks == KS_real) re-reads tap (0,0); its weights are zero
                     const bool pad_step = may_pad && ks >= p.KS_real;
@@ -541,19 +544,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         };
 #pragma unroll 1
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
             if (n0 + c0 >= p.K) break;  // warp-uniform; TMA clips the unwritten columns anyway
-            uint32_t v0[16], v1[16];
-            const bool two = (c0 + 16) < cend;   // compile-time false only for 16-column slices
+            uint32_t v0[16];
             tmem_ld_32x32b_x16(t_row + c0, v0);
-            if (two) tmem_ld_32x32b_x16(t_row + c0 + 16, v1);
             tmem_ld_wait();
-            if (SPLITK) {
-                add_partials(v0, c0);
-                if (two) add_partials(v1, c0 + 16);
-            }
+            if (SPLITK) add_partials(v0, c0);
             epilogue16<MK>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
-            if (two) epilogue16<MK>(p, v1, c0 + 16, bias_sa, scale_sa, res_row, out_row);
         }
         tc_fence_before();
         fence_proxy_async_smem();                                          // staged tile -> visible to the TMA engine
