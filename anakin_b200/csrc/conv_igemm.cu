@@ -334,11 +334,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // PDL: let the next kernel start its own prologue now; everything that reads the previous
     // kernel's outputs (activations, residual) happens after the wait below.
     pdl_launch_dependents();
-    pdl_wait_prior_grid();
 
     if (warp_idx == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
+            const uint32_t b_sub_bytes = BN * p.chunk;
+            const uint32_t tx_per_sub = BLOCK_M * p.chunk + (X3 ? 2 : 1) * b_sub_bytes;
+            // Weights do not depend on the previous kernel: the first trip round the ring gets its B tiles
+            // (and the whole stage's expect_tx) before the grid-dependency wait, so their HBM / L2 latency
+            // overlaps the previous kernel's tail. Only this thread reads the prior grid's output.
+            const int npre = min(p.stages, it_end - it_begin);
+            {
+                int ks = it_begin * subs_per_stage;
+                uint32_t full_sa = smem_u32(full_bar), b_dst0 = smem_u32(smem) + B_OFF;
+#pragma unroll 1
+                for (int i = 0; i < npre; ++i) {
+                    const int nsub = min(subs_per_stage, p.KS - ks);
+                    mbar_arrive_expect_tx_sa(full_sa, nsub * tx_per_sub);
+                    uint32_t b_dst = b_dst0;
+#pragma unroll 1
+                    for (int j = 0; j < nsub; ++j) {
+                        tma_load_2d_sa(&map_b, full_sa, b_dst, ks * p.chunk_el, n0);
+                        if (X3) tma_load_2d_sa(&map_b, full_sa, b_dst + (B_LO_OFF - B_OFF), ks * p.chunk_el, p.K + n0);
+                        b_dst += b_sub_bytes;
+                        ++ks;
+                    }
+                    full_sa += 8; b_dst0 += SB;
+                }
+            }
+            pdl_wait_prior_grid();
             if (p.res_panels > 0 && rank == 0) {
                 mbar_arrive_expect_tx(res_full_bar, p.res_panels * BLOCK_M * p.res_pw);
                 const int cols_per_panel = p.res_pw / p.res_es;
@@ -353,8 +377,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int base_w = q0 * p.stride_w - p.pad_w;
             const int base_h = p0 * p.stride_h - p.pad_h;
             const uint32_t a_sub_bytes = BLOCK_M * p.chunk;
-            const uint32_t b_sub_bytes = BN * p.chunk;
-            const uint32_t tx_per_sub = a_sub_bytes + (X3 ? 2 : 1) * b_sub_bytes;
             // lean single-thread loop: 32-bit shared addresses and running coordinates only
             const uint32_t ring_sa = smem_u32(smem), full_sa0 = smem_u32(full_bar), empty_sa0 = smem_u32(empty_bar);
             int ks = it_begin * subs_per_stage;
@@ -366,10 +388,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0, stage_sa = ring_sa, full_sa = full_sa0, empty_sa = empty_sa0;
             const bool may_pad = p.KS != p.KS_real;
+            int pre_left = npre;
             for (int it = it_begin; it < it_end; ++it) {
-                mbar_wait_sa(empty_sa, phase ^ 1);
+                const bool pre = pre_left > 0;   // first trip: slot free, B + expect_tx already issued
+                --pre_left;
                 const int nsub = min(subs_per_stage, p.KS - ks);
-                mbar_arrive_expect_tx_sa(full_sa, nsub * tx_per_sub);
+                if (!pre) {
+                    mbar_wait_sa(empty_sa, phase ^ 1);
+                    mbar_arrive_expect_tx_sa(full_sa, nsub * tx_per_sub);
+                }
                 uint32_t a_dst = stage_sa, b_dst = stage_sa + B_OFF, bl_dst = stage_sa + B_LO_OFF;
 #pragma unroll 1
                 for (int j = 0; j < nsub; ++j) {
@@ -378,9 +405,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tma_load_im2col_4d_sa(&map_a, full_sa, a_dst, pad_step ? 0 : c_coord, base_w, base_h, n_img,
                                           static_cast<uint16_t>(pad_step ? 0 : off_w),
                                           static_cast<uint16_t>(pad_step ? 0 : off_h));
-                    tma_load_2d_sa(&map_b, full_sa, b_dst, k_coord, n0);
-                    if (X3)  // the W-low image follows the W-high image (row offset K)
-                        tma_load_2d_sa(&map_b, full_sa, bl_dst, k_coord, p.K + n0);
+                    if (!pre) {
+                        tma_load_2d_sa(&map_b, full_sa, b_dst, k_coord, n0);
+                        if (X3)  // the W-low image follows the W-high image (row offset K)
+                            tma_load_2d_sa(&map_b, full_sa, bl_dst, k_coord, p.K + n0);
+                    }
                     a_dst += a_sub_bytes; b_dst += b_sub_bytes; bl_dst += b_sub_bytes;
                     ++ks;
                     k_coord += p.chunk_el;
@@ -987,7 +1016,8 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     kp.part_off = staging_al;
     pl->grid.z = split;
     const int k_iters_local = (k_iters + split - 1) / split;
-    const int budget = (ctas * split > sms) ? (MAX_SMEM / 2 - 2048) : MAX_SMEM;
+    static const int smem_half = [] { const char* e = getenv("B200_SABER_SMEM_HALF"); return e ? atoi(e) : 0; }();
+    const int budget = (ctas * split > sms || smem_half) ? (MAX_SMEM / 2 - 2048) : MAX_SMEM;
     int stages = (budget - fixed) / sb;
     if (stages > k_iters_local) stages = k_iters_local;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
