@@ -129,54 +129,115 @@ __device__ __forceinline__ void lds_f32x16(uint32_t saddr, float (&f)[16]) {
     }
 }
 
-// round-to-nearest-even + saturation == vcvtps2dq(RN) + vpmovsdb / vpmovusdb; four lanes -> one word
-__device__ __forceinline__ uint32_t pack4_s8(float a, float b, float c, float d) {
-    int32_t ia, ib, ic, id;
-    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ia) : "f"(a));
-    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ib) : "f"(b));
-    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ic) : "f"(c));
-    asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(id) : "f"(d));
-    uint32_t lo, hi;
-    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(lo) : "r"(ia), "r"(ib));   // b0 = ia.b0, b1 = ib.b0
-    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(hi) : "r"(ic), "r"(id));
-    uint32_t w;
-    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(w) : "r"(lo), "r"(hi));    // lo.b0 lo.b1 hi.b0 hi.b1
+// ---- int8 epilogue arithmetic kept off the conversion pipe (I2F.U8 / F2I issue at a quarter of the fp32 rate and
+// made the epilogue of wide tiles conversion-bound, tools/timeline.py) and on packed fp32x2 where the op exists.
+struct F2 { float x, y; };
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+    F2 d;
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+    F2 d;
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+    F2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 ra, ra, rb, rc;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+// byte `lane` of w -> float, exactly: splice the byte under the exponent of 2^23 and subtract 2^23
+// (+128 for int8 residuals, whose words were xor-ed with 0x80808080 first)
+__device__ __forceinline__ float byte_as_biased_float(uint32_t w, int lane) {
+    uint32_t t;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(w), "r"(0x4B000000u), "r"(0x7650u + lane));
+    return __uint_as_float(t);
+}
+// Quantise four lanes: clamp to the integer range [lo, hi], add 1.5 * 2^23 -- the fp32 add rounds to
+// nearest-even exactly as cvt.rni / vcvtps2dq do -- and gather the low bytes. round(clamp(x)) == clamp(round(x))
+// for integer bounds, so this equals cvt.rni.sat.{s8,u8}.f32 on every finite input.
+__device__ __forceinline__ uint32_t pack4_q8(F2 a, F2 b, float lo, float hi) {
+    const F2 magic = {12582912.f, 12582912.f};
+    a.x = fminf(fmaxf(a.x, lo), hi); a.y = fminf(fmaxf(a.y, lo), hi);
+    b.x = fminf(fmaxf(b.x, lo), hi); b.y = fminf(fmaxf(b.y, lo), hi);
+    a = add2(a, magic);
+    b = add2(b, magic);
+    uint32_t l, h, w;
+    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(l) : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)));
+    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(h) : "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(w) : "r"(l), "r"(h));
     return w;
-}
-__device__ __forceinline__ uint32_t pack4_u8(float a, float b, float c, float d) {
-    uint32_t ia, ib, ic, id;
-    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(ia) : "f"(a));
-    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(ib) : "f"(b));
-    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(ic) : "f"(c));
-    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(id) : "f"(d));
-    uint32_t lo, hi, w;
-    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(lo) : "r"(ia), "r"(ib));
-    asm("prmt.b32 %0, %1, %2, 0x0040;" : "=r"(hi) : "r"(ic), "r"(id));
-    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(w) : "r"(lo), "r"(hi));
-    return w;
-}
-// byte lane of a word -> float (exact)
-__device__ __forceinline__ float u8_lane(uint32_t w, int lane) {
-    uint32_t b;
-    asm("bfe.u32 %0, %1, %2, 8;" : "=r"(b) : "r"(w), "r"(8 * lane));
-    return __uint2float_rn(b);
-}
-__device__ __forceinline__ float s8_lane(uint32_t w, int lane) {
-    int32_t b;
-    asm("bfe.s32 %0, %1, %2, 8;" : "=r"(b) : "r"(w), "r"(8 * lane));
-    return __int2float_rn(b);
 }
 
 // One thread, one output row, 16 consecutive channels starting at tile-local column cl.
+// int8 nets: x86 Saber epilogue (acc + bias) * scale, [relu], [+ res * sum_scale], [relu], rne + saturate; the
+// residual is s8 | u8 and the output s8 | u8 | f32 (the fc feeding softmax).
+__device__ __forceinline__ void epilogue16_i8(const ConvKParams& p, const uint32_t (&v)[16], int cl, uint32_t bias_sa,
+                                              uint32_t scale_sa, const PanelRow& res_row, const PanelRow& out_row) {
+    F2 f[8];
+    {
+        float bias[16], scale[16];
+        lds_f32x16(bias_sa + cl * 4, bias);
+        lds_f32x16(scale_sa + cl * 4, scale);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const F2 a = {__int2float_rn(static_cast<int32_t>(v[2 * i])), __int2float_rn(static_cast<int32_t>(v[2 * i + 1]))};
+            f[i] = mul2(add2(a, F2{bias[2 * i], bias[2 * i + 1]}), F2{scale[2 * i], scale[2 * i + 1]});
+        }
+    }
+    if (p.res_panels > 0) {
+        const uint4 t = lds128(panel_addr(res_row, cl));
+        const bool rs = p.res_dtype == B200_INT8;
+        const uint32_t flip = rs ? 0x80808080u : 0u;
+        const float off = rs ? -8388736.f : -8388608.f;     // -(2^23 [+ 128])
+        const uint32_t w[4] = {t.x ^ flip, t.y ^ flip, t.z ^ flip, t.w ^ flip};
+        const bool unit = p.sum_scale == 1.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const F2 r = add2(F2{byte_as_biased_float(w[i >> 1], (2 * i) & 3), byte_as_biased_float(w[i >> 1], (2 * i + 1) & 3)},
+                              F2{off, off});
+            f[i] = unit ? add2(f[i], r) : fma2(r, F2{p.sum_scale, p.sum_scale}, f[i]);
+        }
+    }
+    if (p.out_dtype == B200_FLOAT) {
+        if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { f[i].x = fmaxf(f[i].x, 0.f); f[i].y = fmaxf(f[i].y, 0.f); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            sts128(panel_addr(out_row, cl * 4 + q * 16),
+                   make_uint4(__float_as_uint(f[2 * q].x), __float_as_uint(f[2 * q].y),
+                              __float_as_uint(f[2 * q + 1].x), __float_as_uint(f[2 * q + 1].y)));
+    } else {
+        // relu (it is the last step whenever it is set: relu-before-sum only exists without a sum) folds into
+        // the lower clamp bound; u8 saturates at 0 anyway
+        const bool u = p.out_dtype == B200_UINT8;
+        const float lo = (u || p.relu) ? 0.f : -128.f, hi = u ? 255.f : 127.f;
+        sts128(panel_addr(out_row, cl), make_uint4(pack4_q8(f[0], f[1], lo, hi), pack4_q8(f[2], f[3], lo, hi),
+                                                   pack4_q8(f[4], f[5], lo, hi), pack4_q8(f[6], f[7], lo, hi)));
+    }
+}
+
+// float nets carry and write their own type (or f32): acc (+ beta * res) + bias, relu(neg_slope)
 template <int KIND>
 __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t (&v)[16], int cl, uint32_t bias_sa,
                                            uint32_t scale_sa, const PanelRow& res_row, const PanelRow& out_row) {
+    if constexpr (KIND == KIND_I8) {
+        epilogue16_i8(p, v, cl, bias_sa, scale_sa, res_row, out_row);
+        return;
+    }
     float f[16], r[16];
     const bool has_res = p.res_panels > 0;
-    // residual / output element types that can occur: int8 nets carry s8 | u8 residuals and write
-    // s8 | u8 | f32 (the fc feeding softmax); float nets carry and write their own type (or f32).
     if (has_res) {
-        if (KIND != KIND_I8 && p.res_dtype == B200_FLOAT) {
+        if (p.res_dtype == B200_FLOAT) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint4 t = lds128(panel_addr(res_row, cl * 4 + q * 16));
@@ -194,50 +255,17 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
                     r[8 * q + 2 * i] = x.x; r[8 * q + 2 * i + 1] = x.y;
                 }
             }
-        } else if (KIND == KIND_I8) {
-            const uint4 t = lds128(panel_addr(res_row, cl));
-            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-            if (p.res_dtype == B200_INT8) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = s8_lane(w[i >> 2], i & 3);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = u8_lane(w[i >> 2], i & 3);
-            }
         }
     }
     float bias[16];
     lds_f32x16(bias_sa + cl * 4, bias);
-    if constexpr (KIND == KIND_I8) {
-        // x86 Saber int8 epilogue: (acc + bias) * scale, [relu], [+ res*sum_scale], [relu], rne+sat
-        float scale[16];
-        lds_f32x16(scale_sa + cl * 4, scale);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            f[i] = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int32_t>(v[i])), bias[i]), scale[i]);
-        if (has_res) {
-            if (p.sum_scale == 1.f) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __fadd_rn(f[i], r[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __fmaf_rn(r[i], p.sum_scale, f[i]);
-            }
-        }
-        if (p.relu) {   // relu-before-sum only exists when there is no sum, so one clamp covers both
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-    } else {
-        // float epilogue: acc (+ beta*res) + bias, relu(neg_slope)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(v[i]);
-            if (has_res) x = __fmaf_rn(p.sum_scale, r[i], x);
-            x = __fadd_rn(x, bias[i]);
-            if (p.relu) x = x > 0.f ? x : __fmul_rn(x, p.neg_slope);
-            f[i] = x;
-        }
+    for (int i = 0; i < 16; ++i) {
+        float x = __uint_as_float(v[i]);
+        if (has_res) x = __fmaf_rn(p.sum_scale, r[i], x);
+        x = __fadd_rn(x, bias[i]);
+        if (p.relu) x = x > 0.f ? x : __fmul_rn(x, p.neg_slope);
+        f[i] = x;
     }
     // ---- stage into the swizzled output tile
     if (p.out_dtype == B200_FLOAT) {
@@ -257,16 +285,30 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& p, const uint32_t 
             }
             sts128(panel_addr(out_row, cl * 2 + q * 16), make_uint4(w[0], w[1], w[2], w[3]));
         }
-    } else if (KIND == KIND_I8 && p.out_dtype == B200_INT8) {
-        sts128(panel_addr(out_row, cl),
-               make_uint4(pack4_s8(f[0], f[1], f[2], f[3]), pack4_s8(f[4], f[5], f[6], f[7]),
-                          pack4_s8(f[8], f[9], f[10], f[11]), pack4_s8(f[12], f[13], f[14], f[15])));
-    } else if (KIND == KIND_I8) {
-        sts128(panel_addr(out_row, cl),
-               make_uint4(pack4_u8(f[0], f[1], f[2], f[3]), pack4_u8(f[4], f[5], f[6], f[7]),
-                          pack4_u8(f[8], f[9], f[10], f[11]), pack4_u8(f[12], f[13], f[14], f[15])));
     }
 }
+
+// ----------------------------------------------------------------- phase timeline (debug builds only)
+// -DB200_TIMELINE (tools/timeline.py builds it into anakin_b200/lib_tl) records per-CTA SM-clock stamps of
+// the pipeline phases; the shipped library compiles all of it out.
+#ifdef B200_TIMELINE
+struct TlRec {
+    unsigned long long gt0, gt1;
+    long long clk[8];
+    uint32_t bx, by, bz, smid, K, KS, bn, stages;
+};
+constexpr unsigned TL_CAP = 1u << 15;
+__device__ TlRec g_tl[TL_CAP];
+__device__ unsigned g_tl_n;
+__device__ __forceinline__ unsigned long long tl_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL(slot) do { g_tl[tl_idx].clk[slot] = clock64(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
 
 // ----------------------------------------------------------------- the kernel
 template <int KIND, int BN, bool SPLITK>
@@ -299,6 +341,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+#ifdef B200_TIMELINE
+    uint32_t& tl_idx = tmem_ptr_smem[1];   // spare word of the tail region
+    if (threadIdx.x == 0) {
+        tl_idx = atomicAdd(&g_tl_n, 1u) & (TL_CAP - 1);
+        TlRec& r = g_tl[tl_idx];
+        r.gt0 = tl_globaltimer();
+        r.clk[0] = clock64();
+        r.bx = blockIdx.x; r.by = blockIdx.y; r.bz = blockIdx.z;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(r.smid));
+        r.K = p.K; r.KS = p.KS; r.bn = BN; r.stages = p.stages;
+    }
+#endif
     const int subs_per_stage = STAGE_K_BYTES / p.chunk;
     const int num_stage_iters = (p.KS + subs_per_stage - 1) / subs_per_stage;
     const int m0 = blockIdx.x * BLOCK_M;
@@ -330,6 +384,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) TL(1);
 
     // PDL: let the next kernel start its own prologue now; everything that reads the previous
     // kernel's outputs (activations, residual) happens after the wait below.
@@ -363,6 +418,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
             pdl_wait_prior_grid();
+            TL(2);
             if (p.res_panels > 0 && rank == 0) {
                 mbar_arrive_expect_tx(res_full_bar, p.res_panels * BLOCK_M * p.res_pw);
                 const int cols_per_panel = p.res_pw / p.res_es;
@@ -444,6 +500,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int it = it_begin; it < it_end; ++it) {
                 mbar_wait_sa(full_sa, phase);
                 tc_fence_after();
+#ifdef B200_TIMELINE
+                if (it == it_begin) TL(3);
+#endif
                 const int nsub = min(subs_per_stage, p.KS - ks);
                 uint32_t a16 = stage16, b16 = stage16 + (B_OFF >> 4);
                 for (int j = 0; j < nsub; j += sub_step) {
@@ -467,6 +526,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++stage == p.stages) { stage = 0; phase ^= 1; stage16 = ring16; full_sa = full_sa0; empty_sa = empty_sa0; }
             }
             tc_commit(tmem_full_bar);
+            TL(4);
         }
         __syncwarp();
     } else {
@@ -507,6 +567,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         mbar_wait(tmem_full_bar, 0);  // all of this CTA's MMAs retired: its operand ring is free
         tc_fence_after();
+        if (threadIdx.x == 64) TL(5);
     }
 
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);   // warps sharing a lane quarter split the columns
@@ -585,6 +646,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         fence_proxy_async_smem();                                          // staged tile -> visible to the TMA engine
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");    // the epilogue warps only
         if (warp_idx == 2 && lane == 0) {
+            TL(6);
             const int cols_per_panel = p.out_pw / p.out_es;
             for (int j = 0; j < p.out_panels; ++j) {
                 if (n0 + j * cols_per_panel >= p.K) break;
@@ -593,6 +655,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_store_commit();
             tma_store_wait_read();  // smem may be released once the engine has read it; the writes
                                     // complete before the grid is reported complete
+#ifdef B200_TIMELINE
+            TL(7);
+            g_tl[tl_idx].gt1 = tl_globaltimer();
+#endif
         }
     }
 
@@ -741,6 +807,9 @@ static bool select_launch_split(b200_conv_plan* pl) {
     switch (pl->bn) {
         case 32: pl->launch = launch_conv<KIND, 32, true>; return true;
         case 64: pl->launch = launch_conv<KIND, 64, true>; return true;
+        case 128:
+            if (KIND == KIND_I8) { pl->launch = launch_conv<KIND_I8, 128, true>; return true; }
+            break;
     }
     return false;
 }
@@ -1074,6 +1143,8 @@ int b200_conv_plan_info(const b200_conv_plan_t* pl, int32_t* block_n, int32_t* g
     return B200_SUCCESS;
 }
 
+int b200_conv_plan_split(const b200_conv_plan_t* pl) { return pl ? static_cast<int>(pl->grid.z) : 0; }
+
 int b200_fc_desc(b200_conv_desc_t* d, int32_t math, int32_t in_dtype, int32_t out_dtype, int32_t m, int32_t k_in,
                  int32_t n_out) {
     if (!d) return B200_INVALID_VALUE;
@@ -1086,3 +1157,18 @@ int b200_fc_desc(b200_conv_desc_t* d, int32_t math, int32_t in_dtype, int32_t ou
 }
 
 }  // extern "C"
+
+#ifdef B200_TIMELINE
+// debug only: copy out and reset the phase timeline (record layout = TlRec, 112 bytes)
+extern "C" B200_API int b200_debug_timeline(void* out, int max_recs) {
+    unsigned n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, b200::g_tl_n, sizeof(n));
+    if (n > b200::TL_CAP) n = b200::TL_CAP;
+    if (static_cast<int>(n) > max_recs) n = max_recs;
+    if (out && n) cudaMemcpyFromSymbol(out, b200::g_tl, n * sizeof(b200::TlRec));
+    const unsigned zero = 0;
+    cudaMemcpyToSymbol(b200::g_tl_n, &zero, sizeof(zero));
+    return static_cast<int>(n);
+}
+#endif

@@ -162,6 +162,8 @@ B200_API void b200_conv_plan_destroy(b200_conv_plan_t* plan);
 /* Introspection for tests / roofline: tile shape and grid the plan chose. */
 B200_API int b200_conv_plan_info(const b200_conv_plan_t* plan, int32_t* block_n, int32_t* grid_x,
                         int32_t* grid_y, int32_t* k_steps, int32_t* smem_bytes);
+/* split-K factor of the plan (= cluster size along z; 1 when the k loop is not split), 0 for a null plan. */
+B200_API int b200_conv_plan_split(const b200_conv_plan_t* plan);
 
 /* ------------------------------------------------------------------------
  * Depthwise convolution (MobileNet). Replaces SaberDepthWiseConv

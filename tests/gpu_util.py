@@ -72,7 +72,9 @@ class ConvRunner:
     def info(self):
         v = [C.c_int32() for _ in range(5)]
         self.lib.b200_conv_plan_info(self.plan, *[C.byref(x) for x in v])
-        return dict(zip(("block_n", "grid_x", "grid_y", "k_steps", "smem"), [x.value for x in v]))
+        d = dict(zip(("block_n", "grid_x", "grid_y", "k_steps", "smem"), [x.value for x in v]))
+        d["split"] = self.lib.b200_conv_plan_split(self.plan)
+        return d
 
     def run(self, x_dev, res_dev=None, out_dev=None):
         d = self.d
