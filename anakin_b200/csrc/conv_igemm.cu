@@ -72,7 +72,6 @@ struct ConvKParams {
     int32_t out_panels;  // BN*out_es / out_pw
     int32_t res_es, res_pw, res_panels;  // same for the residual tile (0 panels = no residual)
     int32_t split;       // split-K factor = cluster size along z (1, 2 or 4)
-    int32_t part_off;    // byte offset (from the smem base) of the partial-accumulator buffers in rank 0
     const float* bias;
     const float* scale;
 };
@@ -86,7 +85,7 @@ struct ConvKParams {
 __host__ __device__ constexpr int stage_bytes(int bn, bool x3 = false) {
     return (x3 ? 2 : 1) * (A_STAGE_BYTES + bn * STAGE_K_BYTES);
 }
-__host__ __device__ constexpr int tail_bytes(int bn) { return 2 * bn * 4 + (3 * MAX_STAGES + 2) * 8 + 16; }
+__host__ __device__ constexpr int tail_bytes(int bn) { return 2 * bn * 4 + (3 * MAX_STAGES + 3) * 8 + 16; }
 
 __device__ __forceinline__ uint32_t layout_type_for_chunk(int chunk) {
     return chunk == 128 ? 2u : (chunk == 64 ? 4u : (chunk == 32 ? 6u : 0u));
@@ -329,7 +328,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* res_tile = smem + p.stages * SB;
+    constexpr uint32_t PART_BYTES = BLOCK_M * BN * 4;     // one CTA's raw 32-bit accumulator tile
+    // [ring][split-K: (split-1) partial accumulator tiles, written by the other ranks][residual][tables][barriers]
+    uint8_t* part_tile = smem + p.stages * SB;
+    uint8_t* res_tile = part_tile + (SPLITK ? (p.split - 1) * PART_BYTES : 0u);
     float* bias_s = reinterpret_cast<float*>(res_tile + p.res_panels * BLOCK_M * p.res_pw);
     float* scale_s = bias_s + BN;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(scale_s + BN);
@@ -337,7 +339,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* conv_bar = empty_bar + MAX_STAGES;   // X3: "A split done" per stage
     uint64_t* tmem_full_bar = conv_bar + MAX_STAGES;
     uint64_t* res_full_bar = tmem_full_bar + 1;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full_bar + 1);
+    uint64_t* part_bar = res_full_bar + 1;         // split-K rank 0: the other ranks' partial sums have landed
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(part_bar + 1);
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -377,12 +380,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         mbar_init(tmem_full_bar, 1);
         mbar_init(res_full_bar, 1);
+        if (SPLITK) {
+            mbar_init(part_bar, 1);
+            if (rank == 0) {
+                // every other rank sends 128 rows x 64 bytes per 16-column group that holds real channels
+                const int groups = (min(BN, p.K - n0) + 15) >> 4;
+                mbar_arrive_expect_tx(part_bar, (split - 1) * groups * BLOCK_M * 64);
+            }
+        }
         fence_mbar_init();
     }
     if (warp_idx == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // rank 0's barrier must exist before a peer can complete bytes on it; this runs before the
+    // grid-dependency wait, i.e. under the previous kernel's tail
+    if (SPLITK) cluster_sync_all();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (threadIdx.x == 0) TL(1);
 
@@ -571,35 +585,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);   // warps sharing a lane quarter split the columns
-    constexpr uint32_t PART_BYTES = BLOCK_M * BN * 4;     // one CTA's raw 32-bit accumulator tile
-    if (SPLITK) {
-        tc_fence_before();
-        __syncwarp();         // the cluster barrier is warp-aligned: reconverge the single-lane role warps
-        cluster_sync_all();   // every CTA of the cluster has finished its MMAs -> rank 0's ring may be written
-        if (rank > 0 && warp_idx >= 2) {
-            // ship this CTA's partial accumulators into rank 0's shared memory:
-            // layout [16-column group][row][16 x 32 bit], 64 contiguous bytes per thread
-            const int quarter = warp_idx & 3;
-            const int row = quarter * 32 + lane;
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-            const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
-            const uint32_t dst0 = map_to_cta(smem_u32(smem) + p.part_off + (rank - 1) * PART_BYTES, 0);
-            tc_fence_after();
+    if (SPLITK && rank > 0 && warp_idx >= 2) {
+        // ship this CTA's partial accumulators into rank 0's shared memory with asynchronous stores that
+        // complete on rank 0's mbarrier: layout [16-column group][row][16 x 32 bit], 64 contiguous bytes per thread
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
+        const uint32_t dst0 = map_to_cta(smem_u32(part_tile) + static_cast<uint32_t>(rank - 1) * PART_BYTES, 0);
+        const uint32_t bar0 = map_to_cta(smem_u32(part_bar), 0);
 #pragma unroll 1
-            for (int c0 = cbeg; c0 < cend; c0 += 16) {
-                if (n0 + c0 >= p.K) break;
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(t_row + c0, v);
-                tmem_ld_wait();
-                const uint32_t d = dst0 + (static_cast<uint32_t>((c0 >> 4) * BLOCK_M + row) << 6);
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            if (n0 + c0 >= p.K) break;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_row + c0, v);
+            tmem_ld_wait();
+            const uint32_t d = dst0 + (static_cast<uint32_t>((c0 >> 4) * BLOCK_M + row) << 6);
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                    st_cluster_v4(d + q4 * 16, v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-            }
-            tc_fence_before();
+            for (int q4 = 0; q4 < 4; ++q4)
+                st_async_v4(d + q4 * 16, bar0, v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
         }
-        __syncwarp();
-        cluster_sync_all();   // partials have landed in rank 0
+        tc_fence_before();
     }
 
     if (warp_idx >= 2 && rank == 0) {
@@ -611,7 +617,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const PanelRow out_row = make_panel_row(smem_u32(smem), lg2(p.out_pw), row);
         const PanelRow res_row = make_panel_row(smem_u32(res_tile), lg2(p.res_pw ? p.res_pw : 128), row);
         const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
-        const uint32_t part_sa = smem_u32(smem) + p.part_off;
+        const uint32_t part_sa = smem_u32(part_tile);
+        if (SPLITK) mbar_wait(part_bar, 0);
         uint8_t* out_tile = smem;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
@@ -667,6 +674,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_fence_after();
         tmem_dealloc<TMEM_COLS>(tmem_base);
     }
+    // no CTA of the cluster exits while its asynchronous stores may still be in flight towards rank 0
+    if (SPLITK) cluster_sync_all();
 }
 
 // ----------------------------------------------------------------- host side
@@ -1080,23 +1089,22 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
         if (!sok) split = 1;   // wide tile: no split variant
     }
     kp.split = split;
-    const int part_bytes = (split - 1) * BLOCK_M * bn * 4;
-    const int staging_al = (staging + 1023) & ~1023;
-    kp.part_off = staging_al;
+    const int part_bytes = (split - 1) * BLOCK_M * bn * 4;   // rank 0 receives the other ranks' partial tiles
     pl->grid.z = split;
     const int k_iters_local = (k_iters + split - 1) / split;
     static const int smem_half = [] { const char* e = getenv("B200_SABER_SMEM_HALF"); return e ? atoi(e) : 0; }();
     const int budget = (ctas * split > sms || smem_half) ? (MAX_SMEM / 2 - 2048) : MAX_SMEM;
-    int stages = (budget - fixed) / sb;
+    const int fixed_all = fixed + part_bytes;
+    int stages = (budget - fixed_all) / sb;
     if (stages > k_iters_local) stages = k_iters_local;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    const int min_stages = (staging_al + part_bytes + sb - 1) / sb;
+    const int min_stages = (staging + sb - 1) / sb;   // the ring doubles as the output staging tile
     if (stages < min_stages) stages = min_stages;
     if (stages < 1) stages = 1;
-    if (stages < 2 && k_iters >= 2 && 2 * sb + fixed <= MAX_SMEM) stages = 2;  // never serialise load / MMA
-    if (stages * sb + fixed > MAX_SMEM) { delete pl; return B200_OUT_OF_MEM; }
+    if (stages < 2 && k_iters >= 2 && 2 * sb + fixed_all <= MAX_SMEM) stages = 2;  // never serialise load / MMA
+    if (stages * sb + fixed_all > MAX_SMEM) { delete pl; return B200_OUT_OF_MEM; }
     kp.stages = stages;
-    pl->smem_bytes = stages * sb + fixed;
+    pl->smem_bytes = stages * sb + fixed_all;
     *plan_out = pl;
     return B200_SUCCESS;
 }

@@ -45,6 +45,21 @@ static void launch_pdl(Kern kern, unsigned grid, unsigned block, cudaStream_t st
     cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+template <typename Kern, typename... Args>
+static void launch_pdl_smem(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static int check_launch(const char* what) {
     count_launch();
     cudaError_t e = cudaPeekAtLastError();
@@ -675,49 +690,65 @@ __global__ void nchw_to_nhwc_smallc_kernel(const float* __restrict__ in, void* _
 // i.e. for every (padded) input row and every OUTPUT column the S horizontal taps x 4 channels the
 // filter row touches, already quantised / converted. The R x S conv then runs on the tensor-core
 // kernel as an R x 1 conv over X2 with c = taps*4, stride_w = 1, no padding.
+// One block per (image, padded input row): the row's pixels are read (coalesced), quantised / converted ONCE
+// into a shared-memory line of 4-channel pixels, then the overlapping tap windows are emitted as 16-byte
+// stores that are contiguous across the block.
 template <int OUT>  // 0 f32, 1 f16, 2 s8, 3 u8
 __global__ void stem_pack_kernel(const float* __restrict__ in, void* __restrict__ out, int n, int c, int h,
                                  int w, int pad_h, int pad_w, int s, int stride_w, int taps, int wo,
                                  float inv_scale) {
     pdl_enter();
+    constexpr int PX = OUT == 0 ? 16 : (OUT == 1 ? 8 : 4);   // bytes per 4-channel pixel
+    constexpr int TP = 16 / PX;                              // taps per 16-byte store
+    extern __shared__ __align__(16) uint8_t line[];          // (w + 2*pad_w + taps) pixels
     const int hp = h + 2 * pad_h;
-    const long long total = 1ll * n * hp * wo;
-    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
-         idx += 1ll * gridDim.x * blockDim.x) {
-        const int q = static_cast<int>(idx % wo);
-        long long t = idx / wo;
-        const int hr = static_cast<int>(t % hp);
-        const int b = static_cast<int>(t / hp);
-        const int y = hr - pad_h;
-        const bool row_ok = y >= 0 && y < h;
-        uint32_t words[8];
-        for (int tap = 0; tap < taps; ++tap) {
-            const int x = q * stride_w - pad_w + tap;
-            const bool ok = row_ok && tap < s && x >= 0 && x < w;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ok)
-                for (int ch = 0; ch < c; ++ch) v[ch] = __ldg(in + ((1ll * b * c + ch) * h + y) * w + x);
-            const long long o = idx * taps + tap;  // index of this tap's 4-channel group
-            if (OUT == 0) {
-                reinterpret_cast<float4*>(out)[o] = make_float4(v[0], v[1], v[2], v[3]);
-            } else if (OUT == 1) {
-                __half2 a = __floats2half2_rn(v[0], v[1]), bq = __floats2half2_rn(v[2], v[3]);
-                reinterpret_cast<uint2*>(out)[o] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bq));
-            } else {
-                uint32_t wd = 0;
-                for (int ch = 0; ch < 4; ++ch) {
-                    float f = __fmul_rn(v[ch], inv_scale);
-                    int code;
-                    if (OUT == 2) { f = fminf(fmaxf(roundf(f), -128.f), 127.f); code = static_cast<int>(f); }
-                    else { f = fminf(fmaxf(f, 0.f), 255.f); code = static_cast<int>(f); }
-                    wd |= (static_cast<uint32_t>(code) & 0xffu) << (8 * ch);
-                }
-                words[tap & 7] = wd;
-                if ((tap & 3) == 3)   // four taps = one 16-byte store
-                    reinterpret_cast<uint4*>(out)[o >> 2] =
-                        make_uint4(words[(tap & 7) - 3], words[(tap & 7) - 2], words[(tap & 7) - 1], words[tap & 7]);
+    const int row = blockIdx.x;
+    const int b = row / hp;
+    const int y = row - b * hp - pad_h;
+    const bool row_ok = y >= 0 && y < h;
+    const int wp = w + 2 * pad_w + taps;
+    for (int xp = threadIdx.x; xp < wp; xp += blockDim.x) {
+        const int x = xp - pad_w;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row_ok && x >= 0 && x < w)
+            for (int ch = 0; ch < c; ++ch) v[ch] = __ldg(in + ((1ll * b * c + ch) * h + y) * w + x);
+        if (OUT == 0) {
+            reinterpret_cast<float4*>(line)[xp] = make_float4(v[0], v[1], v[2], v[3]);
+        } else if (OUT == 1) {
+            __half2 a = __floats2half2_rn(v[0], v[1]), bq = __floats2half2_rn(v[2], v[3]);
+            reinterpret_cast<uint2*>(line)[xp] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&bq));
+        } else {
+            uint32_t wd = 0;
+            for (int ch = 0; ch < 4; ++ch) {
+                float f = __fmul_rn(v[ch], inv_scale);
+                int code;
+                if (OUT == 2) { f = fminf(fmaxf(roundf(f), -128.f), 127.f); code = static_cast<int>(f); }
+                else { f = fminf(fmaxf(f, 0.f), 255.f); code = static_cast<int>(f); }
+                wd |= (static_cast<uint32_t>(code) & 0xffu) << (8 * ch);
             }
+            reinterpret_cast<uint32_t*>(line)[xp] = wd;
         }
+    }
+    __syncthreads();
+    const int groups = taps / TP;   // 16-byte stores per output column
+    uint4* dst = reinterpret_cast<uint4*>(out) + 1ll * row * wo * groups;
+    for (int i = threadIdx.x; i < wo * groups; i += blockDim.x) {
+        const int q = i / groups, g = i - q * groups;
+        const int tap0 = g * TP;
+        const int xp0 = q * stride_w + tap0;   // x = q*stride_w - pad_w + tap  ->  xp = x + pad_w
+        uint4 val;
+        if (OUT == 0) {
+            val = tap0 < s ? reinterpret_cast<const uint4*>(line)[xp0] : make_uint4(0, 0, 0, 0);
+        } else if (OUT == 1) {
+            const uint2 p0 = tap0 < s ? reinterpret_cast<const uint2*>(line)[xp0] : make_uint2(0, 0);
+            const uint2 p1 = tap0 + 1 < s ? reinterpret_cast<const uint2*>(line)[xp0 + 1] : make_uint2(0, 0);
+            val = make_uint4(p0.x, p0.y, p1.x, p1.y);
+        } else {
+            const uint32_t* l = reinterpret_cast<const uint32_t*>(line);
+            val = make_uint4(tap0 < s ? l[xp0] : 0u, tap0 + 1 < s ? l[xp0 + 1] : 0u, tap0 + 2 < s ? l[xp0 + 2] : 0u,
+                             tap0 + 3 < s ? l[xp0 + 3] : 0u);
+        }
+        dst[i] = val;
     }
 }
 
@@ -1021,13 +1052,15 @@ int b200_stem_pack(const float* in, void* out, int32_t out_dtype, int32_t n, int
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
     const int wo = (w + 2 * pad_w - s) / stride_w + 1;
     if (wo <= 0) return B200_INVALID_VALUE;
-    const long long total = 1ll * n * (h + 2 * pad_h) * wo;
-    const unsigned g = grid_for(total, 256);
+    const unsigned g = static_cast<unsigned>(n * (h + 2 * pad_h));
+    const int px = out_dtype == B200_FLOAT ? 16 : (out_dtype == B200_HALF ? 8 : 4);
+    const size_t smem = static_cast<size_t>(w + 2 * pad_w + taps) * px;
+    if (smem > 48 * 1024) return B200_UNIMPL_ERROR;
     switch (out_dtype) {
-        case B200_FLOAT: launch_pdl(stem_pack_kernel<0>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
-        case B200_HALF: launch_pdl(stem_pack_kernel<1>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
-        case B200_INT8: launch_pdl(stem_pack_kernel<2>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
-        case B200_UINT8: launch_pdl(stem_pack_kernel<3>, g, 256, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        case B200_FLOAT: launch_pdl_smem(stem_pack_kernel<0>, g, 128, smem, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        case B200_HALF: launch_pdl_smem(stem_pack_kernel<1>, g, 128, smem, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        case B200_INT8: launch_pdl_smem(stem_pack_kernel<2>, g, 128, smem, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
+        case B200_UINT8: launch_pdl_smem(stem_pack_kernel<3>, g, 128, smem, S(stream), in, out, n, c, h, w, pad_h, pad_w, s, stride_w, taps, wo, inv_scale); break;
         default: return B200_UNIMPL_ERROR;
     }
     return check_launch("stem_pack");

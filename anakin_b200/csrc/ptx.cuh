@@ -282,6 +282,19 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint32_t a, uint32
     asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 16-byte store into another CTA's shared memory that completes `bytes` on that CTA's mbarrier
+// (both addresses shared::cluster): the receiver just waits on the barrier, no cluster-wide sync
+__device__ __forceinline__ void st_async_v4(uint32_t caddr, uint32_t cbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cbar) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- PDL
 __device__ __forceinline__ void pdl_wait_prior_grid() {
     asm volatile("griddepcontrol.wait;" ::: "memory");

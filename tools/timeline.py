@@ -117,6 +117,15 @@ def run(batch, model, precision, flush):
         print("%-4d %-16s %5d | %8.2f %8.2f %8.2f %7.2f %7.2f | %21s %7.2f %7.2f %6.2f %6.2f %6.2f %6.2f %6.2f" %
               (i, "%d/%d/%d" % L["key"], len(rr), entry, release, end, handoff, crit, "", *ph))
         prev_end = end
+        if rr["bz"].max() > 0:
+            # split-K launch: absolute phase times per rank, relative to the launch's first dependency release
+            base = (rr["gt0"].astype(np.float64) - t_first) / 1e3
+            for z in range(int(rr["bz"].max()) + 1):
+                m = rr["bz"] == z
+                absu = lambda k: float(np.median(base[m] + (clk[m][:, k] - clk[m][:, 0]) * f)) - release
+                print("       rank %d: entry %+6.2f prolog %+6.2f release %+6.2f first-stage %+6.2f last-mma %+6.2f acc-done %+6.2f%s" %
+                      (z, float(np.median(base[m])) - release, absu(1), absu(2), absu(3), absu(4), absu(5),
+                       (" staged %+6.2f stored %+6.2f" % (absu(6), absu(7))) if z == 0 else ""))
     print("sum handoff (prev end -> dependency released) %.1f us; sum crit (release -> last exit) %.1f us" % (tot_handoff, tot_crit))
     print("SM clock estimate %.3f GHz" % (clk_ghz or 0))
 
