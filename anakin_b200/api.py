@@ -52,6 +52,9 @@ SYMBOLS = {
     "anakin_net_destroy": (None, [_vp]),
     "anakin_worker_create": (_i, [_cp, _i, _i, C.POINTER(_i), _i, _i, C.POINTER(_vp)]),
     "anakin_worker_sync_prediction": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "anakin_worker_wait_ready": (_i, [_vp]),
+    "anakin_worker_async_prediction": (_i, [_vp, _vp, _sz, _vp, _sz]),
+    "anakin_worker_async_get_result": (_i, [_vp]),
     "anakin_worker_destroy": (None, [_vp]),
 }
 
@@ -252,6 +255,17 @@ class Worker:
         _check(self._lib.anakin_worker_sync_prediction(self._h, a.ctypes.data_as(_vp), a.size,
                                                        out.ctypes.data_as(_vp), out.size), "sync_prediction")
         return out
+
+    def wait_ready(self):
+        _check(self._lib.anakin_worker_wait_ready(self._h), "Worker init")
+
+    def async_prediction_ptr(self, in_ptr, in_count, out_ptr, out_count):
+        """Queue one request on caller-owned (pinned) fp32 host buffers; pair with async_get_result()."""
+        _check(self._lib.anakin_worker_async_prediction(self._h, _vp(in_ptr), in_count, _vp(out_ptr), out_count),
+               "async_prediction")
+
+    def async_get_result(self):
+        _check(self._lib.anakin_worker_async_get_result(self._h), "async_get_result")
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -68,8 +68,9 @@ struct ConvKParams {
     int32_t out_dtype, res_dtype;
     int32_t stages;      // depth of the operand ring
     int32_t out_es;      // bytes per output element
-    int32_t out_pw;      // output panel width in bytes (32|64|128) = TMA-store box inner extent
-    int32_t out_panels;  // BN*out_es / out_pw
+    int32_t epi_bn;      // channels of the tile this CTA finishes and stores (BN, or BN/split with split-K)
+    int32_t out_pw;      // output panel width in bytes (16|32|64|128) = TMA-store box inner extent
+    int32_t out_panels;  // epi_bn*out_es / out_pw
     int32_t res_es, res_pw, res_panels;  // same for the residual tile (0 panels = no residual)
     int32_t split;       // split-K factor = cluster size along z (1, 2 or 4)
     const float* bias;
@@ -328,10 +329,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    constexpr uint32_t PART_BYTES = BLOCK_M * BN * 4;     // one CTA's raw 32-bit accumulator tile
-    // [ring][split-K: (split-1) partial accumulator tiles, written by the other ranks][residual][tables][barriers]
+    // split-K: the `split` CTAs of a cluster (along z) each take a contiguous range of the k loop, then
+    // reduce-scatter: rank r receives everyone's partial sums for channel slice r (epi_bn = BN/split
+    // channels) through distributed shared memory, finishes and stores that slice.
+    // (compiled out of the SPLITK = false instantiations, which most layers use)
+    const int split = SPLITK ? p.split : 1;
+    const int rank = SPLITK ? static_cast<int>(cluster_ctarank()) : 0;
+    const int epi_bn = SPLITK ? p.epi_bn : BN;
+    const uint32_t slice_bytes = BLOCK_M * epi_bn * 4;    // one rank's raw 32-bit partial sums of a slice
+    // [ring][split-K: (split-1) partial slices, written by the other ranks][residual][tables][barriers]
     uint8_t* part_tile = smem + p.stages * SB;
-    uint8_t* res_tile = part_tile + (SPLITK ? (p.split - 1) * PART_BYTES : 0u);
+    uint8_t* res_tile = part_tile + (SPLITK ? (split - 1) * slice_bytes : 0u);
     float* bias_s = reinterpret_cast<float*>(res_tile + p.res_panels * BLOCK_M * p.res_pw);
     float* scale_s = bias_s + BN;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(scale_s + BN);
@@ -360,11 +368,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int num_stage_iters = (p.KS + subs_per_stage - 1) / subs_per_stage;
     const int m0 = blockIdx.x * BLOCK_M;
     const int n0 = blockIdx.y * BN;
-    // split-K: the `split` CTAs of a cluster (along z) each take a contiguous range of the k loop and
-    // rank 0 folds the partial accumulators it receives through distributed shared memory.
-    // (compiled out of the SPLITK = false instantiations, which most layers use)
-    const int split = SPLITK ? p.split : 1;
-    const int rank = SPLITK ? static_cast<int>(cluster_ctarank()) : 0;
+    const int n0_epi = n0 + rank * epi_bn;     // first channel of the slice this CTA finishes
+    // 16-channel groups of that slice which hold real channels (0: nothing to finish or store)
+    const int own_groups = max(0, min(epi_bn, p.K - n0_epi) + 15) >> 4;
     const int it_begin = SPLITK ? num_stage_iters * rank / split : 0;
     const int it_end = SPLITK ? num_stage_iters * (rank + 1) / split : num_stage_iters;
 
@@ -382,11 +388,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_init(res_full_bar, 1);
         if (SPLITK) {
             mbar_init(part_bar, 1);
-            if (rank == 0) {
-                // every other rank sends 128 rows x 64 bytes per 16-column group that holds real channels
-                const int groups = (min(BN, p.K - n0) + 15) >> 4;
-                mbar_arrive_expect_tx(part_bar, (split - 1) * groups * BLOCK_M * 64);
-            }
+            // every other rank sends 128 rows x 64 bytes per 16-channel group of this CTA's slice
+            mbar_arrive_expect_tx(part_bar, (split - 1) * own_groups * BLOCK_M * 64);
         }
         fence_mbar_init();
     }
@@ -433,12 +436,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             pdl_wait_prior_grid();
             TL(2);
-            if (p.res_panels > 0 && rank == 0) {
+            if (p.res_panels > 0 && own_groups > 0) {
                 mbar_arrive_expect_tx(res_full_bar, p.res_panels * BLOCK_M * p.res_pw);
                 const int cols_per_panel = p.res_pw / p.res_es;
                 for (int j = 0; j < p.res_panels; ++j)
                     tma_load_2d(&map_res, res_full_bar, res_tile + j * BLOCK_M * p.res_pw,
-                                n0 + j * cols_per_panel, m0);
+                                n0_epi + j * cols_per_panel, m0);
             }
             const int n_img = m0 / p.HoWo;
             const int rem = m0 - n_img * p.HoWo;
@@ -546,10 +549,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else {
         // ===================== epilogue warps =====================
         // bias / scale tables (weights-side constants): filled while the main loop runs
-        for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
-            const bool ok = (n0 + i) < p.K;
-            bias_s[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n0 + i) : 0.f;
-            scale_s[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0 + i) : 1.f;
+        for (int i = threadIdx.x - 64; i < epi_bn; i += EPI_THREADS) {
+            const bool ok = (n0_epi + i) < p.K;
+            bias_s[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n0_epi + i) : 0.f;
+            scale_s[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0_epi + i) : 1.f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         if (X3) {
@@ -585,47 +588,53 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);   // warps sharing a lane quarter split the columns
-    if (SPLITK && rank > 0 && warp_idx >= 2) {
-        // ship this CTA's partial accumulators into rank 0's shared memory with asynchronous stores that
-        // complete on rank 0's mbarrier: layout [16-column group][row][16 x 32 bit], 64 contiguous bytes per thread
+    if (SPLITK && warp_idx >= 2) {
+        // scatter: every 16-channel group of this CTA's accumulators goes to the rank that owns its slice, as
+        // asynchronous stores completing on that rank's mbarrier. Layout at the receiver:
+        // [sender slot][16-channel group][row][16 x 32 bit], 64 contiguous bytes per thread.
         const int quarter = warp_idx & 3;
         const int row = quarter * 32 + lane;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
-        const uint32_t dst0 = map_to_cta(smem_u32(part_tile) + static_cast<uint32_t>(rank - 1) * PART_BYTES, 0);
-        const uint32_t bar0 = map_to_cta(smem_u32(part_bar), 0);
+        const uint32_t part_sa = smem_u32(part_tile), bar_sa = smem_u32(part_bar);
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
             if (n0 + c0 >= p.K) break;
+            const int owner = c0 / epi_bn;
+            if (owner == rank) continue;
+            const int slot = rank - (rank > owner ? 1 : 0);
+            const int grp = (c0 - owner * epi_bn) >> 4;
             uint32_t v[16];
             tmem_ld_32x32b_x16(t_row + c0, v);
             tmem_ld_wait();
-            const uint32_t d = dst0 + (static_cast<uint32_t>((c0 >> 4) * BLOCK_M + row) << 6);
+            const uint32_t d = map_to_cta(part_sa + slot * slice_bytes + (static_cast<uint32_t>(grp * BLOCK_M + row) << 6), owner);
+            const uint32_t bar = map_to_cta(bar_sa, owner);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
-                st_async_v4(d + q4 * 16, bar0, v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                st_async_v4(d + q4 * 16, bar, v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
         }
-        tc_fence_before();
     }
 
-    if (warp_idx >= 2 && rank == 0) {
+    if (warp_idx >= 2 && own_groups > 0) {
         const int quarter = warp_idx & 3;
         const int row = quarter * 32 + lane;
         if (p.res_panels > 0) mbar_wait(res_full_bar, 0);
         tc_fence_after();
-        auto lg2 = [](int pw) { return pw == 128 ? 7 : (pw == 64 ? 6 : 5); };
+        auto lg2 = [](int pw) { return pw == 128 ? 7 : (pw == 64 ? 6 : (pw == 32 ? 5 : 4)); };
         const PanelRow out_row = make_panel_row(smem_u32(smem), lg2(p.out_pw), row);
         const PanelRow res_row = make_panel_row(smem_u32(res_tile), lg2(p.res_pw ? p.res_pw : 128), row);
         const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
         const uint32_t part_sa = smem_u32(part_tile);
         if (SPLITK) mbar_wait(part_bar, 0);
         uint8_t* out_tile = smem;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
-        // fold the other ranks' partial sums into 16 accumulator columns (rank order: deterministic)
+        // TMEM columns of this CTA's slice; the two warps of a lane quarter share its 16-channel groups
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (SPLITK ? rank * epi_bn : 0);
+        const int cw = SPLITK ? max(16, epi_bn >> 1) : COLS_PER_WARP;
+        const int cbeg = ((warp_idx - 2) >> 2) * cw, cend = min(epi_bn, cbeg + cw);
+        // fold the other ranks' partial sums into 16 accumulator columns (slot order: deterministic)
         auto add_partials = [&](uint32_t (&v)[16], int c0) {
-            for (int r2 = 1; r2 < split; ++r2) {
-                const uint32_t src = part_sa + (r2 - 1) * PART_BYTES + (static_cast<uint32_t>((c0 >> 4) * BLOCK_M + row) << 6);
+            for (int sl = 0; sl < split - 1; ++sl) {
+                const uint32_t src = part_sa + sl * slice_bytes + (static_cast<uint32_t>((c0 >> 4) * BLOCK_M + row) << 6);
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const uint4 t = lds128(src + q4 * 16);
@@ -642,7 +651,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         };
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            if (n0 + c0 >= p.K) break;  // warp-uniform; TMA clips the unwritten columns anyway
+            if (n0_epi + c0 >= p.K) break;  // warp-uniform; TMA clips the unwritten columns anyway
             uint32_t v0[16];
             tmem_ld_32x32b_x16(t_row + c0, v0);
             tmem_ld_wait();
@@ -656,8 +665,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             TL(6);
             const int cols_per_panel = p.out_pw / p.out_es;
             for (int j = 0; j < p.out_panels; ++j) {
-                if (n0 + j * cols_per_panel >= p.K) break;
-                tma_store_2d(&map_out, out_tile + j * BLOCK_M * p.out_pw, n0 + j * cols_per_panel, m0);
+                if (n0_epi + j * cols_per_panel >= p.K) break;
+                tma_store_2d(&map_out, out_tile + j * BLOCK_M * p.out_pw, n0_epi + j * cols_per_panel, m0);
             }
             tma_store_commit();
             tma_store_wait_read();  // smem may be released once the engine has read it; the writes
@@ -816,9 +825,7 @@ static bool select_launch_split(b200_conv_plan* pl) {
     switch (pl->bn) {
         case 32: pl->launch = launch_conv<KIND, 32, true>; return true;
         case 64: pl->launch = launch_conv<KIND, 64, true>; return true;
-        case 128:
-            if (KIND == KIND_I8) { pl->launch = launch_conv<KIND_I8, 128, true>; return true; }
-            break;
+        case 128: pl->launch = launch_conv<KIND, 128, true>; return true;
     }
     return false;
 }
@@ -1050,19 +1057,12 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     kp.out_dtype = d->out_dtype; kp.res_dtype = d->res_dtype;
     kp.bias = bias_dev; kp.scale = scale_dev;
     kp.out_es = out_es;
-    kp.out_pw = bn * out_es >= 128 ? 128 : bn * out_es;
-    kp.out_panels = bn * out_es / kp.out_pw;
     kp.res_es = res_es;
-    kp.res_pw = res_es ? (bn * res_es >= 128 ? 128 : bn * res_es) : 0;
-    kp.res_panels = res_es ? bn * res_es / kp.res_pw : 0;
 
     // ---- pipeline depth: as deep as the k loop needs, within the shared-memory budget. A grid that
     // exceeds one wave keeps two CTAs per SM resident (epilogue of one overlaps the main loop of the
     // other); a sub-wave grid takes the whole SM for latency hiding on its long k loop.
     const int sb = stage_bytes(bn, d->math == B200_MATH_TF32X3);
-    const int res_bytes = BLOCK_M * bn * res_es;
-    const int fixed = res_bytes + tail_bytes(bn) + 1024;
-    const int staging = BLOCK_M * bn * out_es;
     const int subs = STAGE_K_BYTES / g.chunk;
     const int k_iters = (g.KS + subs - 1) / subs;
     // split-K for sub-wave grids with a long k loop (deep 3x3 / wide 1x1 layers on small feature maps):
@@ -1078,8 +1078,9 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     }
     if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) {   // tuning experiments only
         const int fs = atoi(e);
-        if ((fs == 1 || fs == 2 || fs == 4) && k_iters >= fs) split = fs;
+        if ((fs == 1 || fs == 2 || fs == 4 || fs == 8) && k_iters >= fs) split = fs;
     }
+    while (split > 1 && (bn / split) % 16) split >>= 1;      // a slice is whole 16-channel groups
     if (split > 1) {
         bool sok = false;
         if (d->math == B200_MATH_I8) sok = select_launch_split<KIND_I8>(pl);
@@ -1089,7 +1090,17 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
         if (!sok) split = 1;   // wide tile: no split variant
     }
     kp.split = split;
-    const int part_bytes = (split - 1) * BLOCK_M * bn * 4;   // rank 0 receives the other ranks' partial tiles
+    // each rank of a split cluster finishes and stores a slice of epi_bn channels (reduce-scatter)
+    const int epi_bn = bn / split;
+    kp.epi_bn = epi_bn;
+    kp.out_pw = epi_bn * out_es >= 128 ? 128 : epi_bn * out_es;
+    kp.out_panels = epi_bn * out_es / kp.out_pw;
+    kp.res_pw = res_es ? (epi_bn * res_es >= 128 ? 128 : epi_bn * res_es) : 0;
+    kp.res_panels = res_es ? epi_bn * res_es / kp.res_pw : 0;
+    const int res_bytes = BLOCK_M * epi_bn * res_es;
+    const int fixed = res_bytes + tail_bytes(bn) + 1024;
+    const int staging = BLOCK_M * epi_bn * out_es;
+    const int part_bytes = (split - 1) * BLOCK_M * epi_bn * 4;   // the other ranks' partial sums of this slice
     pl->grid.z = split;
     const int k_iters_local = (k_iters + split - 1) / split;
     static const int smem_half = [] { const char* e = getenv("B200_SABER_SMEM_HALF"); return e ? atoi(e) : 0; }();

@@ -222,6 +222,29 @@ int anakin_worker_sync_prediction(anakin_worker_t* w, const float* in, size_t in
     return 0;
 }
 
+int anakin_worker_wait_ready(anakin_worker_t* w) {
+    if (!w) return fail("null argument");
+    const std::string err = w->w->wait_ready();
+    return err.empty() ? 0 : fail(err);
+}
+
+int anakin_worker_async_prediction(anakin_worker_t* w, const float* in, size_t in_count, float* out, size_t out_count) {
+    if (!w || !in || !out) return fail("null argument");
+    w->w->async_prediction_view(in, in_count, out, out_count);
+    return 0;
+}
+
+int anakin_worker_async_get_result(anakin_worker_t* w) {
+    if (!w) return fail("null argument");
+    if (w->w->empty()) return fail("no request in flight");
+    try {
+        w->w->async_get_result();
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
+    return 0;
+}
+
 void anakin_worker_destroy(anakin_worker_t* w) { delete w; }
 
 }  // extern "C"

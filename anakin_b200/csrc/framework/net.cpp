@@ -275,7 +275,15 @@ void WorkerCore::launch() {
 void WorkerCore::thread_main(int tid) {
     const int device = _devices.empty() ? -1 : _devices[tid % _devices.size()];
     NetCore net;
+    struct ReadyMark {   // counted on every exit path of the init block
+        WorkerCore* w;
+        ~ReadyMark() {
+            { std::lock_guard<std::mutex> lk(w->_mu); ++w->_ready; }
+            w->_ready_cv.notify_all();
+        }
+    };
     {
+        ReadyMark mark{this};
         // first thread loads + optimises the graph, every thread builds its own Net (worker.cpp:13-39)
         std::lock_guard<std::mutex> lk(_graph_mu);
         if (!_graph) {
@@ -304,6 +312,18 @@ void WorkerCore::thread_main(int tid) {
         }
         std::vector<std::vector<float>> outs;
         try {
+            if (task->in_view) {
+                NetCore::DTensor* d = net.get_in(_inputs[0]);
+                const size_t ib = std::min(d->storage_bytes(), task->in_count * sizeof(float));
+                CUDA_CHECK(cudaMemcpyAsync(d->mutable_data(), task->in_view, ib, cudaMemcpyHostToDevice, net.stream()));
+                net.prediction();
+                NetCore::DTensor* o = net.get_out(_outputs[0]);
+                const size_t ob = std::min(o->storage_bytes(), task->out_count * sizeof(float));
+                CUDA_CHECK(cudaMemcpyAsync(task->out_view, o->data(), ob, cudaMemcpyDeviceToHost, net.stream()));
+                net.sync();
+                task->done.set_value(std::move(outs));
+                continue;
+            }
             for (size_t i = 0; i < _inputs.size() && i < task->ins.size(); ++i) {
                 NetCore::DTensor* d = net.get_in(_inputs[i]);
                 const size_t bytes = std::min(d->storage_bytes(), task->ins[i].size() * sizeof(float));
@@ -334,6 +354,25 @@ std::future<std::vector<std::vector<float>>> WorkerCore::sync_prediction(const s
     }
     _cv.notify_one();
     return fut;
+}
+
+void WorkerCore::async_prediction_view(const float* in, size_t in_count, float* out, size_t out_count) {
+    auto task = std::make_shared<Task>();
+    task->in_view = in; task->in_count = in_count;
+    task->out_view = out; task->out_count = out_count;
+    auto fut = task->done.get_future();
+    {
+        std::lock_guard<std::mutex> lk(_mu);
+        _tasks.push_back(task);
+        _async_que.push_back(std::move(fut));
+    }
+    _cv.notify_one();
+}
+
+std::string WorkerCore::wait_ready() {
+    std::unique_lock<std::mutex> lk(_mu);
+    _ready_cv.wait(lk, [this] { return _ready >= _thread_num; });
+    return _init_errors.empty() ? std::string() : _init_errors.front();
 }
 
 void WorkerCore::async_prediction(const std::vector<std::vector<float>>& host_ins) {

@@ -113,12 +113,22 @@ public:
     std::future<std::vector<std::vector<float>>> sync_prediction(const std::vector<std::vector<float>>& host_ins);
     void async_prediction(const std::vector<std::vector<float>>& host_ins);
     std::vector<std::vector<float>> async_get_result();
+    // Zero-copy flavour for serving loops: `in` (fp32 NCHW of the first registered input) and `out` (first
+    // registered output) are caller-owned -- ideally pinned -- host buffers that stay valid until the matching
+    // async_get_result() returns; the worker thread copies H2D, runs prediction() and copies D2H on its own
+    // stream, so with >= 2 threads one request's transfers overlap another's kernels.
+    void async_prediction_view(const float* in, size_t in_count, float* out, size_t out_count);
+    // blocks until every thread has built its Net (or failed); returns the first init error, if any
+    std::string wait_ready();
     bool empty();
     int thread_num() const { return _thread_num; }
 
 private:
     struct Task {
         std::vector<std::vector<float>> ins;
+        const float* in_view = nullptr;
+        float* out_view = nullptr;
+        size_t in_count = 0, out_count = 0;
         std::promise<std::vector<std::vector<float>>> done;
     };
     void thread_main(int tid);
@@ -134,6 +144,8 @@ private:
     std::mutex _mu, _graph_mu;
     std::condition_variable _cv;
     bool _stop = false;
+    int _ready = 0;
+    std::condition_variable _ready_cv;
     std::shared_ptr<graph::GraphCore> _graph;  // loaded + optimised once, shared by all threads
     std::vector<std::string> _init_errors;
 };

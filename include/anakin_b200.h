@@ -89,6 +89,13 @@ ANAKIN_API int anakin_worker_create(const char* model_path, int precision, int t
 /* sync_prediction: one fp32 NCHW input, one fp32 output (first registered in / out). */
 ANAKIN_API int anakin_worker_sync_prediction(anakin_worker_t* w, const float* in, size_t in_count, float* out,
                                              size_t out_count);
+/* Worker::async_prediction / async_get_result (framework/core/worker.h:77-92), zero-copy: `in` / `out` are
+ * caller-owned (ideally pinned) host buffers that stay valid until the matching get_result returns. Results
+ * come back in submission order. With threads >= 2 one request's H2D / D2H copies overlap another's kernels. */
+ANAKIN_API int anakin_worker_wait_ready(anakin_worker_t* w);
+ANAKIN_API int anakin_worker_async_prediction(anakin_worker_t* w, const float* in, size_t in_count, float* out,
+                                              size_t out_count);
+ANAKIN_API int anakin_worker_async_get_result(anakin_worker_t* w);
 ANAKIN_API void anakin_worker_destroy(anakin_worker_t* w);
 
 #ifdef __cplusplus

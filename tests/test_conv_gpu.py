@@ -82,6 +82,54 @@ def test_conv_int8_bit_exact(case, variant, oracle):
         assert bad.shape[0] == 0, "first mismatches %s (info %s)" % (bad[:5], run.info())
 
 
+# split-K (cluster of `split` CTAs along the k loop, reduce-scatter of the partial sums through distributed
+# shared memory) under forced tile widths: every slice / ragged-channel combination must stay bit-exact.
+SPLIT_CASES = [
+    # (case, BN, split)
+    ((2, 7, 7, 512, 512, 3, 1, 1, 1), 32, 2),
+    ((2, 7, 7, 512, 512, 3, 1, 1, 1), 64, 4),
+    ((2, 7, 7, 512, 512, 3, 1, 1, 1), 128, 8),
+    ((1, 14, 14, 256, 200, 3, 1, 1, 1), 128, 4),   # second n tile: slices with 32, 32, 8 and 0 real channels
+    ((1, 14, 14, 256, 200, 3, 1, 1, 1), 64, 2),
+    ((3, 7, 7, 2048, 72, 1, 1, 0, 1), 128, 8),     # 16-channel slices, most of them empty
+    ((1, 9, 9, 1024, 1000, 1, 1, 0, 1), 128, 2),
+]
+
+
+@pytest.mark.parametrize("case,bn,split", SPLIT_CASES)
+@pytest.mark.parametrize("variant", ["s8_relu_u8", "u8_res_s8", "s8_f32"])
+def test_conv_int8_split_k_bit_exact(case, bn, split, variant, oracle, monkeypatch):
+    monkeypatch.setenv("B200_SABER_FORCE_BN", str(bn))
+    monkeypatch.setenv("B200_SABER_FORCE_SPLIT", str(split))
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev, pad_channels
+    rng = np.random.default_rng(hash((case, bn, split, variant)) % (2 ** 31))
+    n, h, w, c, k, r, stride, pad, dil = case
+    in_unsigned = variant == "u8_res_s8"
+    x, wq, bias, scale = _mk_i8(rng, case, in_unsigned)
+    out_dtype = {"s8_relu_u8": A.UINT8, "u8_res_s8": A.INT8, "s8_f32": A.FLOAT}[variant]
+    kw = dict(stride=(stride, stride), pad=(pad, pad), dil=(dil, dil), relu=variant != "s8_f32")
+    res, sum_scale = None, 1.0
+    oh = oracle.conv_out_size(h, pad, dil, r, stride)
+    if variant == "u8_res_s8":
+        res = rng.integers(0, 256, (n, oh, oh, k)).astype(np.uint8)
+        sum_scale = 0.37
+    want = oracle.conv_s8_nhwc_x86(x, wq, bias, scale, residual=res, sum_scale=sum_scale, out_dtype=out_dtype, **kw)
+    ldc = (k + 15) // 16 * 16 if out_dtype != A.FLOAT else (k + 3) // 4 * 4
+    run = ConvRunner(A.MATH_I8, x.shape, A.UINT8 if in_unsigned else A.INT8, wq, bias, scale,
+                     out_dtype, res_dtype=(A.UINT8 if res is not None else -1), sum_scale=sum_scale, ldc=ldc, **kw)
+    info = run.info()
+    if out_dtype == A.FLOAT and bn > 128:
+        pytest.skip("4-byte outputs cap the tile at 128 channels")
+    assert info["block_n"] == bn and info["split"] == split, info
+    got = run.run(dev(x), dev(pad_channels(res, ldc)) if res is not None else None)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert (got[..., k:] == 0).all(), "padding channels must stay untouched"
+    np.testing.assert_array_equal(got[..., :k], want)
+
+
 F_CASES = [
     (1, 12, 12, 16, 32, 3, 1, 1, 1),
     (3, 21, 21, 8, 8, 3, 2, 1, 1),
@@ -97,10 +145,19 @@ def _tf32_trunc(a):
     return (np.ascontiguousarray(a, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
+@pytest.mark.parametrize("math", ["f16", "tf32x3"])
+@pytest.mark.parametrize("bn,split", [(32, 2), (64, 4), (128, 4)])
+def test_conv_float_split_k(math, bn, split, oracle, monkeypatch):
+    """float kinds through the split-K cluster path (fp32 partial sums, fixed summation order)."""
+    monkeypatch.setenv("B200_SABER_FORCE_BN", str(bn))
+    monkeypatch.setenv("B200_SABER_FORCE_SPLIT", str(split))
+    test_conv_float((2, 14, 14, 128, 200, 3, 1, 1, 1), math, True, oracle, expect=(bn, split))
+
+
 @pytest.mark.parametrize("case", F_CASES)
 @pytest.mark.parametrize("math", ["f16", "tf32", "tf32x3"])
 @pytest.mark.parametrize("with_res", [False, True])
-def test_conv_float(case, math, with_res, oracle):
+def test_conv_float(case, math, with_res, oracle, expect=None):
     import torch
     from anakin_b200 import saber_abi as A
     from gpu_util import ConvRunner, dev, pad_channels
@@ -138,6 +195,8 @@ def test_conv_float(case, math, with_res, oracle):
     xin = pad_channels(xs, c)
     run = ConvRunner(mk, xin.shape, dt, ws, bias, None, A.FLOAT, res_dtype=(dt if with_res else -1),
                      sum_scale=1.0, **kw)
+    if expect is not None:
+        assert (run.info()["block_n"], run.info()["split"]) == expect, run.info()
     got = run.run(dev(xin), dev(res_in) if with_res else None)
     torch.cuda.synchronize()
     got = got.cpu().numpy()

@@ -11,7 +11,8 @@ for spec in "$@"; do
 import sys, json
 try:
     d = json.loads(sys.stdin.read())
-    print('%-28s b%-3d %8.0f img/s  %7.1f us  e2e %7.1f us' % ('$label', $b, d['value'], d['ms_per_step']*1e3, d['e2e']['ms_per_step']*1e3))
+    e = d['e2e']; ser = e.get('serial', e)
+    print('%-28s b%-3d %8.0f img/s  %7.1f us | e2e %8.0f img/s %7.1f us (serial %7.1f us)' % ('$label', $b, d['value'], d['ms_per_step']*1e3, e['value'], e['ms_per_step']*1e3, ser['ms_per_step']*1e3))
 except Exception as e:
     print('$label', $b, 'FAILED', e)
 "

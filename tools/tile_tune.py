@@ -92,7 +92,7 @@ def one(batch):
 def main(batch):
     table = {}   # layer -> {cfg: us}
     counts = {}
-    cfgs = [("auto", "")] + [(bn, sp) for bn in ("32", "64", "128", "256") for sp in ("1", "2", "4")]
+    cfgs = [("auto", "")] + [(bn, sp) for bn, sps in (("32", "12"), ("64", "124"), ("128", "1248"), ("256", "1")) for sp in sps]
     for bn, split in cfgs:
         env = dict(os.environ)
         if bn != "auto":
