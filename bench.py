@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
-    ap.add_argument("--worker-threads", type=int, default=4,
+    ap.add_argument("--worker-threads", type=int, default=6,
                     help="threads (= Nets = streams) of the Worker the pipelined e2e leg serves requests with; 0 skips it")
     return ap.parse_args()
 
@@ -350,6 +350,12 @@ def main():
                "top1_first": worker_top1, "serial": serial}
     else:
         e2e = dict(serial, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h)
+    # DRAM bytes per conv launch from the committed `ncu --set full` capture of this same workload (profiles/)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if model == "resnet50" and prec == "int8" and batch == 8 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
     line = {
         "metric": "%s %s images/sec" % (MODEL_NAMES.get(model, model), prec.upper()),
         "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
@@ -367,7 +373,8 @@ def main():
         "e2e": e2e,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % conv_launches,
                      "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s" if prec == "int8" else "TFLOP/s",
-                     "frac": achieved_tops / peak_tops if peak_tops else None, "traffic": None,
+                     "frac": achieved_tops / peak_tops if peak_tops else None, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch, mean over the step's conv launches (cold-cache ncu capture)",
                      "peak_source": "%s bf16 dense x%.1f" % (P["src"], mult),
                      "kernel_ms_per_step": conv_ms, "all_ops_ms_per_step_eager": all_ms,
                      "kernel_share_of_step": conv_ms / all_ms if all_ms else None},
