@@ -278,7 +278,6 @@ def main():
     worker_ms = None
     T = args.worker_threads
     if T > 0:
-        import time
         tmpdir = os.path.join(ROOT, ".bench_tmp")
         os.makedirs(tmpdir, exist_ok=True)
         mpath = os.path.join(tmpdir, "model_rank%d.anakin.bin" % rank)

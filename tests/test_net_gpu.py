@@ -241,3 +241,45 @@ def test_worker_sync_prediction_two_threads():
             out = w.sync_prediction(x, 4 * 12).reshape(4, 12)[:, :10]
             np.testing.assert_allclose(out, gold["prob_int8"], rtol=1e-4, atol=1e-6)
         del w
+
+
+def test_worker_async_prediction_pipelined_matches_single_net():
+    """Worker::async_prediction / async_get_result (worker.h:77-92) on pinned buffers, 3 threads, requests with
+    distinct inputs in flight: every result equals what one Net computes for that input, in submission order."""
+    import torch
+    from anakin_b200 import anakin_bin, api, modelzoo
+    batch, nreq = 4, 12
+    g = modelzoo.build("tiny_resnet", batch, "int8")
+    G = api.Graph.from_bytes(anakin_bin.dumps(g))
+    G.ResetBatchSize("input_0", batch)
+    G.Optimize()
+    net = api.Net(G, "int8")
+    xs = [modelzoo.synthetic_input(batch, 32, seed=100 + i) for i in range(nreq)]
+    want = []
+    for x in xs:
+        net.set_input("input_0", x)
+        net.prediction()
+        want.append(net.get_output().copy())
+    with tempfile.TemporaryDirectory() as d:
+        model = os.path.join(d, "tiny.anakin.bin")
+        modelzoo.save(g, model)
+        w = api.Worker(model, "int8", threads=3, devices=(0,), batch=batch)
+        w.wait_ready()
+        out_count = want[0].size // want[0].shape[1] * 12      # rows are stored with 12 (padded) floats
+        ins = [torch.from_numpy(x).pin_memory() for x in xs]
+        outs = [torch.zeros(out_count, dtype=torch.float32).pin_memory() for _ in range(nreq)]
+        inflight = 0
+        for i in range(nreq):
+            if inflight == 6:
+                w.async_get_result()
+                inflight -= 1
+            w.async_prediction_ptr(ins[i].data_ptr(), ins[i].numel(), outs[i].data_ptr(), outs[i].numel())
+            inflight += 1
+        while inflight:
+            w.async_get_result()
+            inflight -= 1
+        for i in range(nreq):
+            got = outs[i].numpy().reshape(batch, 12)[:, :want[i].shape[1]]
+            np.testing.assert_array_equal(got, want[i])
+        assert any((want[0] != want[i]).any() for i in range(1, nreq)), "inputs must differ for the order check"
+        del w
