@@ -434,15 +434,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     full_sa += 8; b_dst0 += SB;
                 }
             }
-            pdl_wait_prior_grid();
-            TL(2);
-            if (p.res_panels > 0 && own_groups > 0) {
-                mbar_arrive_expect_tx(res_full_bar, p.res_panels * BLOCK_M * p.res_pw);
-                const int cols_per_panel = p.res_pw / p.res_es;
-                for (int j = 0; j < p.res_panels; ++j)
-                    tma_load_2d(&map_res, res_full_bar, res_tile + j * BLOCK_M * p.res_pw,
-                                n0_epi + j * cols_per_panel, m0);
-            }
+            // (all coordinate arithmetic happens before the wait too: nothing but TMA issues follow it)
             const int n_img = m0 / p.HoWo;
             const int rem = m0 - n_img * p.HoWo;
             const int p0 = rem / p.Wo;
@@ -461,7 +453,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0, stage_sa = ring_sa, full_sa = full_sa0, empty_sa = empty_sa0;
             const bool may_pad = p.KS != p.KS_real;
+            const int res_cols_per_panel = p.res_panels > 0 ? p.res_pw / p.res_es : 0;
             int pre_left = npre;
+            pdl_wait_prior_grid();
+            TL(2);
             for (int it = it_begin; it < it_end; ++it) {
                 const bool pre = pre_left > 0;   // first trip: slot free, B + expect_tx already issued
                 --pre_left;
@@ -495,6 +490,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 stage_sa += SB; full_sa += 8; empty_sa += 8;
                 if (++stage == p.stages) { stage = 0; phase ^= 1; stage_sa = ring_sa; full_sa = full_sa0; empty_sa = empty_sa0; }
+                if (it == it_begin && p.res_panels > 0 && own_groups > 0) {
+                    // the residual tile is only needed by the epilogue: after the first operand stage is on its way
+                    mbar_arrive_expect_tx(res_full_bar, p.res_panels * BLOCK_M * p.res_pw);
+                    for (int j = 0; j < p.res_panels; ++j)
+                        tma_load_2d(&map_res, res_full_bar, res_tile + j * BLOCK_M * p.res_pw,
+                                    n0_epi + j * res_cols_per_panel, m0);
+                }
             }
         }
     } else if (warp_idx == 1) {

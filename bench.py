@@ -63,15 +63,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_ms=100):
         self.index = index
+        self.period_ms = period_ms
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -277,6 +278,11 @@ def main():
     # first submit to the last result (the requests complete on the host).
     worker_ms = None
     T = args.worker_threads
+    clocks = sampler.stop() if rank == 0 else None
+    # the Worker leg is host-threaded: poll nvidia-smi slowly there (each query takes driver locks)
+    sampler2 = ClockSampler(local_rank, period_ms=1000)
+    if rank == 0 and T > 0 and not os.environ.get("BENCH_NO_SAMPLER_E2E"):
+        sampler2.start()
     if T > 0:
         tmpdir = os.path.join(ROOT, ".bench_tmp")
         os.makedirs(tmpdir, exist_ok=True)
@@ -302,7 +308,7 @@ def main():
                 W.async_get_result()
                 inflight -= 1
 
-        serve(6 * T)     # every thread: eager run, graph capture, warm replays
+        serve(max(6 * T, 100))     # every thread: eager run, graph capture, warm replays; steady clocks
         barrier()
         t0 = time.perf_counter()
         serve(K)
@@ -310,7 +316,7 @@ def main():
         barrier()
         worker_top1 = [int(v) for v in xout[(K - 1) % depth].numpy().reshape(batch, -1)[:, :int(out_info["dims"][1])].argmax(1)[:4]]
         del W
-    clocks = sampler.stop() if rank == 0 else None
+    clocks_e2e = sampler2.stop() if (rank == 0 and sampler2.proc) else None
 
     # ---- per-op device times (eager, event pair per op) -> roofline of the dominant kernel
     prof = net.profile_ops(5, 20)
@@ -378,6 +384,7 @@ def main():
                      "kernel_ms_per_step": conv_ms, "all_ops_ms_per_step_eager": all_ms,
                      "kernel_share_of_step": conv_ms / all_ms if all_ms else None},
         "clocks": clocks,
+        "clocks_e2e": clocks_e2e,
         "top1_first": [int(v) for v in top1[:4]],
         "cuda_graph": net.cuda_graph_active(),
     }
