@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 # algorithmic work per image (BASELINE.md section 2 / SURVEY.md section 8d)
 MODEL_NAMES = {"resnet50": "ResNet-50", "resnet101": "ResNet-101", "vgg16": "VGG16", "mobilenet_v1": "MobileNet-v1"}
 GOP_PER_IMAGE = {"resnet50": 7.716, "resnet101": 15.140, "vgg16": 30.94, "mobilenet_v1": 1.137, "tiny_resnet": 0.0}
+# conv + fc weight elements, read once per batch at the operand width
+WEIGHT_ELEMS = {"resnet50": 25.50e6, "resnet101": 44.5e6, "vgg16": 138.36e6, "mobilenet_v1": 4.2e6, "tiny_resnet": 0.0}
+DTYPE_BYTES = {0: 2, 1: 4, 3: 1, 5: 4, 7: 1}   # saber DataType -> element bytes (AK_HALF, AK_FLOAT, AK_INT8, AK_INT32, AK_UINT8)
 
 
 def parse_args():
@@ -342,6 +345,20 @@ def main():
     mult = 2.0 if prec == "int8" else (1.0 if prec == "fp16" else 0.5)
     peak_tops = P["bf16_tflops"] * mult
     achieved_tops = (gop_step / 1e3) / (conv_ms / 1e3) if conv_ms > 0 else 0.0
+    # HBM roof of the same launches: algorithmic bytes = per conv / fc op its input, residual and
+    # output activations at their stored dtype (logical N*C*H*W, no padding), + the weights once per batch
+    def act_bytes(node):
+        ti = net.tensor_info(node)
+        n_, c_, h_, w_ = ti["dims"]
+        return n_ * c_ * h_ * w_ * DTYPE_BYTES.get(ti["dtype"], 4)
+    alg_bytes = WEIGHT_ELEMS.get(model, 0.0) * (1 if prec == "int8" else (2 if prec == "fp16" else 4))
+    for name, op, ins, _ in G.describe():
+        if op.startswith("Conv") or op == "Dense":
+            alg_bytes += act_bytes(name) + sum(act_bytes(i) for i in ins)
+    achieved_gbs = (alg_bytes / 1e9) / (conv_ms / 1e3) if conv_ms > 0 else 0.0
+    t_tensor_us = gop_step / peak_tops * 1e3 if peak_tops else 0.0          # GOP / (TOP/s) = ms -> us
+    t_hbm_us = alg_bytes / (P["hbm_gbs"] * 1e9) * 1e6
+    hbm_bound = t_hbm_us > t_tensor_us
     # e2e: every step = H2D of that step's input from pinned memory + prediction() + D2H of its result.
     # "serial": one Net, one request at a time (the latency view). Headline: the Worker serving a queue of
     # requests with T Nets / streams, so copies and kernels of different requests overlap.
@@ -376,11 +393,22 @@ def main():
         "value_warm_l2": images / (warm_ms / 1e3),
         "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p99": float(np.percentile(per_step, 99)),
         "e2e": e2e,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % conv_launches,
-                     "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s" if prec == "int8" else "TFLOP/s",
-                     "frac": achieved_tops / peak_tops if peak_tops else None, "traffic": traffic,
+        "roofline": {"bound": "hbm" if hbm_bound else "tensor",
+                     "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % conv_launches,
+                     "achieved": achieved_gbs if hbm_bound else achieved_tops,
+                     "peak": P["hbm_gbs"] if hbm_bound else peak_tops,
+                     "unit": "GB/s" if hbm_bound else ("TOP/s" if prec == "int8" else "TFLOP/s"),
+                     "frac": (achieved_gbs / P["hbm_gbs"]) if hbm_bound else (achieved_tops / peak_tops if peak_tops else None),
+                     "traffic": traffic,
                      "traffic_unit": "DRAM bytes per launch, mean over the step's conv launches (cold-cache ncu capture)",
-                     "peak_source": "%s bf16 dense x%.1f" % (P["src"], mult),
+                     "algorithmic_bytes_per_launch": alg_bytes / conv_launches if conv_launches else None,
+                     "algorithmic_gop_per_step": gop_step,
+                     "lower_bound_us": {"tensor": t_tensor_us, "hbm": t_hbm_us},
+                     "tensor": {"achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s" if prec == "int8" else "TFLOP/s",
+                                "frac": achieved_tops / peak_tops if peak_tops else None,
+                                "peak_source": "%s bf16 dense x%.1f" % (P["src"], mult)},
+                     "hbm": {"achieved": achieved_gbs, "peak": P["hbm_gbs"], "unit": "GB/s",
+                             "frac": achieved_gbs / P["hbm_gbs"], "peak_source": "%s device copy" % P["src"]},
                      "kernel_ms_per_step": conv_ms, "all_ops_ms_per_step_eager": all_ms,
                      "kernel_share_of_step": conv_ms / all_ms if all_ms else None},
         "clocks": clocks,
