@@ -1111,8 +1111,15 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     // stream 354 -> 348 us, six Worker streams 24.4k -> 40.8k img/s. B200_SABER_SMEM_FULL=1 restores the deep
     // ring for sub-wave grids (slightly better for a single batch-1 stream).
     static const bool smem_full = [] { const char* e = getenv("B200_SABER_SMEM_FULL"); return e && e[0] == '1'; }();
-    const int budget = (ctas * split > sms || !smem_full) ? (MAX_SMEM / 2 - 2048) : MAX_SMEM;
     const int fixed_all = fixed + part_bytes;
+    const int half_budget = MAX_SMEM / 2 - 2048;
+    int budget = half_budget;
+    if (ctas * split <= sms) {
+        // a sub-wave grid may take the whole SM when half of it cannot hold a useful ring (wide int8 tiles with a
+        // long k loop, and every 3xTF32 tile, whose stages are twice as large): 2 stages would serialise TMA and MMA
+        const int stages_half = (half_budget - fixed_all) / sb;
+        if (smem_full || stages_half < (k_iters_local < 4 ? k_iters_local : 4)) budget = MAX_SMEM;
+    }
     int stages = (budget - fixed_all) / sb;
     if (stages > k_iters_local) stages = k_iters_local;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
