@@ -997,6 +997,12 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
         // not enough work for a full wave: maximise the CTA count, but keep N >= 64 when free
         bn = 32;
         if (kr32 >= 64 && tiles_m * ((d->k + 63) / 64) == tiles_m * ((d->k + 31) / 32)) bn = 64;
+        // fp32 operands: a k-iteration is 4 (tf32) or 12 (3xtf32) MMAs whose cost barely depends on N below 64
+        // (~80 clk at N=32, ~104 at N=64), and the long k loops of these layers are split over a cluster anyway:
+        // the wider tile halves the MMA count per output (ResNet-50 FP32 b1: 800 -> 630 us of op time)
+        if ((d->math == B200_MATH_TF32 || d->math == B200_MATH_TF32X3) && kr32 >= 64 &&
+            static_cast<int64_t>(g.KS) * g.chunk >= 2048)
+            bn = 64;
     }
     if (const char* e = getenv("B200_SABER_FORCE_BN")) {   // tuning experiments only
         const int fb = atoi(e);
