@@ -128,6 +128,33 @@ def test_resnet50_int8_golden_and_oracle(oracle):
     assert net.launched_ops() <= 60
 
 
+@pytest.mark.parametrize("batch", [8, 32])
+def test_resnet50_int8_full_batch_matches_golden_and_is_batch_invariant(batch):
+    """BASELINE.json's full sizes (batch 8 and 32: other tile widths, split-K factors and wave counts than the
+    batch-2 plans the oracle pins): images are independent, so image i of the big batch must give bit-for-bit the
+    logits it gives in a batch of 4 -- which are the committed golden logits for the first four."""
+    from anakin_b200 import modelzoo
+    gold = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
+    x = modelzoo.synthetic_input(batch)
+    _, G = _build("resnet50", batch, "int8")
+    net = _run(G, "int8", x)
+    logits, info = net.read_tensor("fc1000")
+    logits = _valid(logits, info).reshape(batch, -1)
+    np.testing.assert_array_equal(logits[:4], gold["logits_int8"])
+    assert (net.get_output().argmax(1)[:4] == gold["top1_int8"]).all()
+    _, G4 = _build("resnet50", 4, "int8")
+    net4 = _run(G4, "int8", x[4:8])
+    l4, i4 = net4.read_tensor("fc1000")
+    np.testing.assert_array_equal(logits[4:8], _valid(l4, i4).reshape(4, -1))
+    if batch > 8:   # a permuted batch permutes the result
+        perm = np.random.default_rng(0).permutation(batch)
+        netp = _run(G, "int8", x[perm])
+        lp, ip = netp.read_tensor("fc1000")
+        np.testing.assert_array_equal(_valid(lp, ip).reshape(batch, -1), logits[perm])
+    prob = net.get_output()
+    np.testing.assert_allclose(prob.sum(1), 1.0, rtol=1e-5)
+
+
 def test_resnet50_fp32_golden():
     from anakin_b200 import modelzoo
     gold = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
