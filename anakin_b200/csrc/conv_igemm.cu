@@ -311,8 +311,11 @@ __device__ __forceinline__ unsigned long long tl_globaltimer() {
 #endif
 
 // ----------------------------------------------------------------- the kernel
+#ifndef B200_CTAS_PER_SM
+#define B200_CTAS_PER_SM 2   // register budget: 65536 / (320 threads x CTAs)
+#endif
 template <int KIND, int BN, bool SPLITK>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, B200_CTAS_PER_SM)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                   const ConvKParams p, const uint32_t idesc) {
