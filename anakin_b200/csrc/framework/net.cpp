@@ -171,6 +171,9 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
 }
 
 void NetCore::run_eager() {
+    // experimental tile-level hand-over between conv layers (off unless the library was built with it and
+    // B200_SABER_DATAFLOW=1): zero this stream's completion counters at the top of the step
+    b200_dataflow_begin_step(_stream);
     for (auto& e : _exec) (*e.op)(_ctx, e.ins, e.outs);
 }
 
