@@ -626,10 +626,12 @@ ORACLE_API void oracle_activation_f32(const float* in, float* out, size_t count,
         float y = x;
         switch (act) {
             case 2: y = x > 0.f ? x : x * neg_slope; break;                 /* relu */
-            case 1: y = 1.0f / ((float)exp(-x) + 1.0f); break;               /* sigmoid */
-            case 3: y = (float)tanh(x); break;                               /* tanh */
-            case 4: y = x > 0.f ? x : 0.f; y = y < coef ? y : coef; break;   /* clipped relu */
-            case 5: y = x > 0.f ? x : coef * ((float)exp(x) - 1.f); break;   /* elu */
+            /* the reference's templates call the C double-precision exp / tanh on the promoted float and only
+             * round when storing (test_saber_activation.cpp:36-66): restated expression for expression */
+            case 1: y = (float)(1.0f / (exp(-x) + 1.0f)); break;                   /* sigmoid */
+            case 3: y = (float)tanh(x); break;                                     /* tanh */
+            case 4: y = x > 0.f ? x : 0.f; y = y < coef ? y : coef; break;         /* clipped relu */
+            case 5: y = x > 0.f ? x : (float)(coef * (exp(x) - 1)); break;         /* elu */
             default: break;
         }
         out[i] = y;

@@ -328,6 +328,53 @@ def scale_f32(x, outer, c, inner, w, b):
     return out
 
 
+# ---- the reference's own op-test oracles (oracle/_ref, compiled from /root/reference): pin the restatements above
+def ref_pool_f32(x, window, pad, stride, ptype):
+    x = np.ascontiguousarray(x, np.float32)
+    n, c, h, w = x.shape
+    oh, ow = pool_out_size(h, w, window[0], window[1], pad[0], pad[1], stride[0], stride[1])
+    out = np.zeros((n, c, oh, ow), np.float32)
+    ref_lib().ref_pooling_cpu_f32(_p(x), _p(out), n, c, h, w, oh, ow, window[0], window[1], pad[0], pad[1],
+                                  stride[0], stride[1], int(ptype))
+    return out
+
+
+def ref_fc_f32(x, w, bias):
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    m = x.shape[0]
+    k = x.size // m
+    n_out = w.size // k
+    out = np.zeros((m, n_out), np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    ref_lib().ref_fc_cpu_f32(_p(x), _p(w), _p(b), _p(out), m, k, n_out)
+    return out
+
+
+def ref_softmax_f32(x, axis):
+    x = np.ascontiguousarray(x, np.float32)
+    n, c, h, w = x.shape
+    out = np.zeros(x.shape, np.float32)
+    ref_lib().ref_softmax_cpu_f32(_p(x), _p(out), n, c, h, w, axis)
+    return out
+
+
+def ref_eltwise_f32(a, b, op=2, c0=1.0, c1=1.0, relu=False):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    out = np.zeros(a.shape, np.float32)
+    ref_lib().ref_eltwise_cpu_f32(_p(a), _p(b), _p(out), a.size, op, _f(c0), _f(c1), int(relu))
+    return out
+
+
+def ref_activation_f32(x, act, neg_slope=0.0, coef=1.0):
+    x = np.ascontiguousarray(x, np.float32)
+    n, c, h, w = x.shape
+    out = np.zeros(x.shape, np.float32)
+    ref_lib().ref_activation_f32(_p(x), _p(out), n, c, h, w, act, _f(neg_slope), _f(coef))
+    return out
+
+
 def tensor_cmp(a, b, use_ref=False):
     a = np.ascontiguousarray(a, np.float32).ravel()
     b = np.ascontiguousarray(b, np.float32).ravel()

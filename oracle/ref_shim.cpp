@@ -11,7 +11,18 @@
 #include "test/saber/conv_func_helper.h"
 #include "saber/core/tensor_op.h"
 
+#include <cmath>
+#include <limits>
+
 using namespace anakin::saber;
+
+// The naive CPU oracles the reference's op tests compare against live inside test .cpp files that also
+// instantiate the (unbuildable) optimised ops. The Makefile cuts exactly those function templates out of the
+// sources where they lie into _ref/ref_test_oracles.inc at build time (never committed, removed after the
+// compile):  pooling_cpu_func  test_saber_pooling.cpp:14-104     fc_cpu_base  test_saber_fc.cpp:14-47
+//            Count, softmax_cpu  test_saber_softmax.cpp:11-79     eltwise_cpu  test_saber_eltwise.cpp:16-98
+//            activation_basic    test_saber_activation.cpp:16-137
+#include "_ref/ref_test_oracles.inc"
 
 static Tensor<X86>* wrap(void* data, DataType dt, LayoutType lt, int n, int c, int h, int w) {
     // Layout_NHWC shapes are given as (n,h,w,c) in Shape order.
@@ -61,6 +72,65 @@ void ref_pool_basic_check_int8(const void* src, void* dst, int is_unsigned, int 
     Tensor<X86>* tout = wrap(dst, dt, Layout_NHWC, n, c, oh, ow);
     pool_basic_check_int8<X86>(*tin, *tout, kernel_w, kernel_h, stride_w, stride_h, pad_w, pad_h,
                                static_cast<PoolingType>(pooling_type));
+    delete tin;
+    delete tout;
+}
+
+void ref_pooling_cpu_f32(const float* src, float* dst, int n, int c, int h, int w, int oh, int ow, int window_h,
+                         int window_w, int pad_h, int pad_w, int stride_h, int stride_w, int pooling_type) {
+    Tensor<X86>* tin = wrap(const_cast<float*>(src), AK_FLOAT, Layout_NCHW, n, c, h, w);
+    Tensor<X86>* tout = wrap(dst, AK_FLOAT, Layout_NCHW, n, c, oh, ow);
+    PoolingParam<X86> param(window_h, window_w, pad_h, pad_w, stride_h, stride_w,
+                            static_cast<PoolingType>(pooling_type));
+    std::vector<Tensor<X86>*> in{tin}, out{tout};
+    pooling_cpu_func<float, X86, X86>(in, out, param);
+    delete tin;
+    delete tout;
+}
+
+void ref_fc_cpu_f32(const float* src, const float* weights, const float* bias, float* dst, int m, int k, int n_out) {
+    Tensor<X86>* tin = wrap(const_cast<float*>(src), AK_FLOAT, Layout_NCHW, m, k, 1, 1);
+    Tensor<X86>* tout = wrap(dst, AK_FLOAT, Layout_NCHW, m, n_out, 1, 1);
+    Tensor<X86>* tw = wrap(const_cast<float*>(weights), AK_FLOAT, Layout_NCHW, 1, 1, n_out, k);
+    Tensor<X86>* tb = bias ? wrap(const_cast<float*>(bias), AK_FLOAT, Layout_NCHW, 1, 1, 1, n_out) : nullptr;
+    FcParam<X86> param(tw, tb, n_out);
+    std::vector<Tensor<X86>*> in{tin}, out{tout};
+    fc_cpu_base<float, X86, X86>(in, out, param);
+    delete tin;
+    delete tout;
+    delete tw;
+    delete tb;
+}
+
+void ref_softmax_cpu_f32(const float* src, float* dst, int n, int c, int h, int w, int axis) {
+    Tensor<X86>* tin = wrap(const_cast<float*>(src), AK_FLOAT, Layout_NCHW, n, c, h, w);
+    Tensor<X86>* tout = wrap(dst, AK_FLOAT, Layout_NCHW, n, c, h, w);
+    SoftmaxParam<X86> param(axis);
+    std::vector<Tensor<X86>*> in{tin}, out{tout};
+    softmax_cpu<float, X86, X86>(in, out, param);
+    delete tin;
+    delete tout;
+}
+
+void ref_eltwise_cpu_f32(const float* a, const float* b, float* dst, int size, int op, float c0, float c1, int relu) {
+    Tensor<X86>* ta = wrap(const_cast<float*>(a), AK_FLOAT, Layout_NCHW, 1, 1, 1, size);
+    Tensor<X86>* tb = wrap(const_cast<float*>(b), AK_FLOAT, Layout_NCHW, 1, 1, 1, size);
+    Tensor<X86>* tout = wrap(dst, AK_FLOAT, Layout_NCHW, 1, 1, 1, size);
+    ActivationParam<X86> act = relu ? ActivationParam<X86>(Active_relu) : ActivationParam<X86>();
+    EltwiseParam<X86> param(static_cast<EltwiseType>(op), std::vector<float>({c0, c1}), act);
+    std::vector<Tensor<X86>*> in{ta, tb}, out{tout};
+    eltwise_cpu<float, X86, X86>(in, out, param);
+    delete ta;
+    delete tb;
+    delete tout;
+}
+
+void ref_activation_f32(const float* src, float* dst, int n, int c, int h, int w, int act, float neg_slope, float coef) {
+    Tensor<X86>* tin = wrap(const_cast<float*>(src), AK_FLOAT, Layout_NCHW, n, c, h, w);
+    Tensor<X86>* tout = wrap(dst, AK_FLOAT, Layout_NCHW, n, c, h, w);
+    ActivationParam<X86> param(static_cast<ActiveType>(act), neg_slope, coef);
+    std::vector<Tensor<X86>*> in{tin}, out{tout};
+    activation_basic<float, X86, X86>(in, out, param);
     delete tin;
     delete tout;
 }

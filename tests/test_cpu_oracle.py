@@ -183,3 +183,51 @@ def test_softmax_eltwise_activation_oracles(oracle):
     a, b = rng.uniform(-1, 1, 50).astype(np.float32), rng.uniform(-1, 1, 50).astype(np.float32)
     np.testing.assert_array_equal(oracle.eltwise_f32(a, b, 2, 1.0, 1.0, True), np.maximum(a + b, 0))
     np.testing.assert_array_equal(oracle.activation_f32(a, 2, 0.0), np.maximum(a, 0))
+
+
+# ---- the restated op oracles against the reference's own test oracles (test_saber_{pooling,fc,softmax,eltwise,
+# activation}.cpp function templates, compiled from /root/reference into oracle/_ref by `make -C oracle ref`)
+@pytest.mark.parametrize("ptype", [1, 2, 3])            # max, avg incl. padding, avg excl. padding
+@pytest.mark.parametrize("window,pad,stride", [((2, 2), (0, 0), (2, 2)), ((3, 3), (1, 1), (2, 2)), ((3, 3), (0, 0), (2, 2)),
+                                               ((3, 2), (1, 0), (1, 2)), ((2, 2), (1, 1), (1, 1)), ((7, 7), (0, 0), (1, 1))])
+def test_pool_f32_matches_reference_test_oracle(oracle, ptype, window, pad, stride):
+    rng = np.random.default_rng(hash((ptype, window, pad, stride)) % 2 ** 31)
+    for shape in [(1, 3, 7, 7), (2, 4, 12, 21), (3, 2, 24, 24)]:
+        x = rng.uniform(-1, 1, shape).astype(np.float32)
+        np.testing.assert_array_equal(oracle.pool_f32(x, window, pad, stride, ptype),
+                                      oracle.ref_pool_f32(x, window, pad, stride, ptype))
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 16, 4), (3, 100, 37), (8, 2048, 1000), (2, 25088, 16)])
+@pytest.mark.parametrize("bias", [False, True])
+def test_fc_f32_matches_reference_test_oracle(oracle, m, k, n, bias):
+    rng = np.random.default_rng(m * 131 + k + n)
+    x = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    w = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    b = rng.uniform(-1, 1, n).astype(np.float32) if bias else None
+    np.testing.assert_array_equal(oracle.fc_f32(x, w, b), oracle.ref_fc_f32(x, w, b))
+
+
+@pytest.mark.parametrize("shape", [(1, 1000, 1, 1), (8, 1000, 1, 1), (2, 5, 3, 4), (3, 21, 7, 2)])
+@pytest.mark.parametrize("axis", [1, 2, 3])
+def test_softmax_matches_reference_test_oracle(oracle, shape, axis):
+    rng = np.random.default_rng(sum(shape) + axis)
+    x = rng.uniform(-6, 6, shape).astype(np.float32)
+    outer, inner = int(np.prod(shape[:axis])), int(np.prod(shape[axis + 1:]))
+    np.testing.assert_array_equal(oracle.softmax_f32(x, outer, shape[axis], inner), oracle.ref_softmax_f32(x, axis))
+
+
+@pytest.mark.parametrize("op,coeff", [(2, (1.0, 1.0)), (2, (0.5, -1.5)), (1, (1.0, 1.0)), (3, (1.0, 1.0))])   # sum, prod, max
+@pytest.mark.parametrize("relu", [False, True])
+def test_eltwise_matches_reference_test_oracle(oracle, op, coeff, relu):
+    rng = np.random.default_rng(op * 7 + int(relu))
+    a = rng.uniform(-2, 2, 4099).astype(np.float32)
+    b = rng.uniform(-2, 2, 4099).astype(np.float32)
+    np.testing.assert_array_equal(oracle.eltwise_f32(a, b, op, coeff[0], coeff[1], relu),
+                                  oracle.ref_eltwise_f32(a, b, op, coeff[0], coeff[1], relu))
+
+
+@pytest.mark.parametrize("act,coef", [(2, 1.0), (1, 1.0), (3, 1.0), (4, 1.5), (5, 0.7)])   # relu sigmoid tanh clipped elu
+def test_activation_matches_reference_test_oracle(oracle, act, coef):
+    x = np.random.default_rng(act).uniform(-4, 4, (2, 3, 5, 7)).astype(np.float32)
+    np.testing.assert_array_equal(oracle.activation_f32(x, act, 0.0, coef), oracle.ref_activation_f32(x, act, 0.0, coef))
