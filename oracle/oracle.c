@@ -8,9 +8,11 @@
  * Every function cites the reference file:line it restates.  The float functions
  * follow the reference's own naive test oracles (test/saber/...), which the
  * reference's tests treat as ground truth at 1e-3; the int8 functions follow the
- * x86 Saber int8 path (saber/funcs/impl/x86/...).  Parity pin: tests/test_oracle_ref.py
- * compares these restatements with the reference's own conv_func_helper.h compiled
- * from /root/reference into oracle/_ref/ (bit-exact on the shared subset).
+ * x86 Saber int8 path (saber/funcs/impl/x86/...).  Parity pin: tests/test_cpu_oracle.py
+ * compares these restatements with the reference's own code compiled from /root/reference
+ * into oracle/_ref/ (make ref): conv_func_helper.h (conv fp32 / int8, int8 pooling),
+ * tensor_cmp_host, and the op tests' oracle templates (fp32 pooling, fc, softmax, eltwise,
+ * activation) -- bit-exact on everything they share.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC oracle.c -o liboracle.so -lm
  * (-ffp-contract=off: the reference epilogues are separate mul/add except where an
