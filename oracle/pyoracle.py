@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 _REF = os.path.join(_HERE, "_ref", "libanakin_ref_oracle.so")
+_REF_SHAPES = os.path.join(_HERE, "_ref", "libanakin_ref_shapes.so")
 
 DT_FLOAT, DT_INT8, DT_UINT8 = 1, 3, 7
 
@@ -22,7 +23,7 @@ def build(ref=True):
     src = os.path.join(_HERE, "oracle.c")
     if (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
-    if ref and os.path.isdir("/root/reference/test/saber") and not os.path.exists(_REF):
+    if ref and os.path.isdir("/root/reference/test/saber") and not (os.path.exists(_REF) and os.path.exists(_REF_SHAPES)):
         subprocess.check_call(["make", "-C", _HERE, "ref"])
 
 
@@ -38,6 +39,22 @@ def lib():
         _lib.oracle_conv_out_size.restype = C.c_int
         _lib.oracle_num_threads.restype = C.c_int
     return _lib
+
+
+_ref_shapes = None
+
+
+def ref_pool_out_size(h, w, wh, ww, ph, pw, sh, sw, global_pooling=False, floor_as_conv=False):
+    """The reference's own Pooling<X86,AK_FLOAT>::compute_output_shape (oracle/_ref); None when not built."""
+    global _ref_shapes
+    if _ref_shapes is None:
+        if not os.path.exists(_REF_SHAPES):
+            return None
+        _ref_shapes = C.CDLL(_REF_SHAPES)
+    oh, ow = C.c_int(), C.c_int()
+    _ref_shapes.ref_pooling_output_shape(1, 1, h, w, wh, ww, ph, pw, sh, sw, int(global_pooling), int(floor_as_conv),
+                                         C.byref(oh), C.byref(ow))
+    return oh.value, ow.value
 
 
 def ref_lib():

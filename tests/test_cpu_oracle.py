@@ -121,6 +121,39 @@ def test_pool_shape_rule(oracle):
     assert oracle.pool_out_size(7, 7, 7, 7, 0, 0, 1, 1, global_pooling=True) == (1, 1)
 
 
+def test_pool_shape_rule_matches_reference_compute_output_shape(oracle):
+    """Exhaustive sweep of the restated rule -- and of the product's host-side b200_pool_out_hw -- against the
+    reference's own Pooling::compute_output_shape compiled from saber/funcs/pooling.h (oracle/_ref)."""
+    import ctypes as C
+    if oracle.ref_pool_out_size(8, 8, 2, 2, 0, 0, 2, 2) is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    from anakin_b200 import saber_abi as A
+    lib = A.load()
+    n = 0
+    for h, w in [(7, 7), (12, 13), (14, 14), (21, 24), (56, 56), (112, 112), (224, 224)]:
+        for win in (1, 2, 3, 5, 7):
+            for pad in (0, 1, 2, 3):
+                for stride in (1, 2, 3):
+                    for floor in (False, True):
+                        if win > h + 2 * pad or pad >= win:
+                            continue
+                        want = oracle.ref_pool_out_size(h, w, win, win, pad, pad, stride, stride, False, floor)
+                        assert oracle.pool_out_size(h, w, win, win, pad, pad, stride, stride, False, floor) == want, \
+                            (h, w, win, pad, stride, floor)
+                        d = A.PoolDesc()
+                        d.dtype, d.type, d.n, d.h, d.w, d.c = A.FLOAT, 1, 1, h, w, 16
+                        d.window_h = d.window_w = win
+                        d.pad_h = d.pad_w = pad
+                        d.stride_h = d.stride_w = stride
+                        d.global_pooling, d.floor_as_conv = 0, int(floor)
+                        oh, ow = C.c_int32(), C.c_int32()
+                        assert lib.b200_pool_out_hw(C.byref(d), C.byref(oh), C.byref(ow)) == A.SUCCESS
+                        assert (oh.value, ow.value) == want, (h, w, win, pad, stride, floor)
+                        n += 1
+        assert oracle.pool_out_size(h, w, 3, 3, 0, 0, 1, 1, True) == oracle.ref_pool_out_size(h, w, 3, 3, 0, 0, 1, 1, True)
+    assert n > 500
+
+
 def test_bn_fold_equals_unfused_ops(oracle):
     """parameter_fusion.cpp:86-131: conv -> BN -> Scale equals the folded conv."""
     rng = np.random.default_rng(9)
