@@ -23,7 +23,8 @@ def build(ref=True):
     src = os.path.join(_HERE, "oracle.c")
     if (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
-    if ref and os.path.isdir("/root/reference/test/saber") and not (os.path.exists(_REF) and os.path.exists(_REF_SHAPES)):
+    if ref and os.path.isdir("/root/reference/test/saber") and not all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in
+                    ("libanakin_ref_oracle.so", "libanakin_ref_shapes.so", "libanakin_ref_fold.so")):
         subprocess.check_call(["make", "-C", _HERE, "ref"])
 
 
@@ -242,6 +243,27 @@ def fold_bn_scale(w, bias, bn_scale_factor, eps, mean, var, gamma, beta_s):
     mean, var, gamma, beta_s = f32(mean), f32(var), f32(gamma), f32(beta_s)
     lib().oracle_fold_bn_scale(_p(w), _p(b), k, w.size // k, _f(bn_scale_factor), _f(eps), _p(mean),
                                _p(var), _p(gamma), _p(beta_s))
+    return w, b
+
+
+_REF_FOLD = os.path.join(_HERE, "_ref", "libanakin_ref_fold.so")
+_ref_fold = None
+
+
+def ref_fold_bn_scale(w, bias, bn_scale_factor, eps, mean, var, gamma, beta_s):
+    """The reference's own WeightsFusion<float,X86>::update_weights (oracle/_ref); None when not built."""
+    global _ref_fold
+    if _ref_fold is None:
+        if not os.path.exists(_REF_FOLD):
+            return None
+        _ref_fold = C.CDLL(_REF_FOLD)
+    w = np.ascontiguousarray(w, np.float32).copy()
+    k, c, r, s_ = w.shape
+    b = np.zeros(k, np.float32) if bias is None else np.ascontiguousarray(bias, np.float32).copy()
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    mean, var, gamma, beta_s = f32(mean), f32(var), f32(gamma), f32(beta_s)
+    _ref_fold.ref_fold_bn_scale(_p(w), _p(b), k, c, r, s_, int(bias is not None), _f(bn_scale_factor), _f(eps),
+                                _p(mean), _p(var), _p(gamma), _p(beta_s), int(beta_s is not None))
     return w, b
 
 

@@ -154,6 +154,28 @@ def test_pool_shape_rule_matches_reference_compute_output_shape(oracle):
     assert n > 500
 
 
+@pytest.mark.parametrize("conv_bias", [False, True])
+@pytest.mark.parametrize("scale_bias", [False, True])
+@pytest.mark.parametrize("factor", [1.0, 0.0, 0.999])
+def test_bn_fold_matches_reference_update_weights(oracle, conv_bias, scale_bias, factor):
+    """oracle_fold_bn_scale vs the reference's WeightsFusion<float,X86>::update_weights compiled from
+    framework/utils/parameter_fusion.cpp:86-131 (oracle/_ref): bit-exact folded weights and bias."""
+    rng = np.random.default_rng(int(conv_bias) * 4 + int(scale_bias) * 2 + int(factor * 10))
+    k, c, r = 37, 19, 3
+    w = rng.standard_normal((k, c, r, r)).astype(np.float32)
+    b = rng.uniform(-1, 1, k).astype(np.float32) if conv_bias else None
+    mean = rng.uniform(-0.1, 0.1, k).astype(np.float32)
+    var = rng.uniform(0.5, 1.5, k).astype(np.float32)
+    gamma = rng.uniform(0.8, 1.2, k).astype(np.float32)
+    beta = rng.uniform(-0.1, 0.1, k).astype(np.float32) if scale_bias else None
+    want = oracle.ref_fold_bn_scale(w, b, factor, 1e-5, mean, var, gamma, beta)
+    if want is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    got = oracle.fold_bn_scale(w, b, factor, 1e-5, mean, var, gamma, beta)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
+
+
 def test_bn_fold_equals_unfused_ops(oracle):
     """parameter_fusion.cpp:86-131: conv -> BN -> Scale equals the folded conv."""
     rng = np.random.default_rng(9)
