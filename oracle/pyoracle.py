@@ -24,7 +24,8 @@ def build(ref=True):
     if (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
     if ref and os.path.isdir("/root/reference/test/saber") and not all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in
-                    ("libanakin_ref_oracle.so", "libanakin_ref_shapes.so", "libanakin_ref_fold.so")):
+                    ("libanakin_ref_oracle.so", "libanakin_ref_shapes.so", "libanakin_ref_fold.so",
+                     "libanakin_ref_quant.so")):
         subprocess.check_call(["make", "-C", _HERE, "ref"])
 
 
@@ -244,6 +245,41 @@ def fold_bn_scale(w, bias, bn_scale_factor, eps, mean, var, gamma, beta_s):
     lib().oracle_fold_bn_scale(_p(w), _p(b), k, w.size // k, _f(bn_scale_factor), _f(eps), _p(mean),
                                _p(var), _p(gamma), _p(beta_s))
     return w, b
+
+
+_REF_QUANT = os.path.join(_HERE, "_ref", "libanakin_ref_quant.so")
+_ref_quant = None
+
+
+def _ref_quant_lib():
+    global _ref_quant
+    if _ref_quant is None and os.path.exists(_REF_QUANT):
+        _ref_quant = C.CDLL(_REF_QUANT)
+    return _ref_quant
+
+
+def ref_quant_weights_per_oc(w):
+    """utils::ScaleUtils::scale_conv_weights_to_nchw_host of the reference (oracle/_ref); None when not built."""
+    L = _ref_quant_lib()
+    if L is None:
+        return None
+    w = np.ascontiguousarray(w, np.float32)
+    k, c, r, s_ = w.shape
+    out = np.zeros(w.shape, np.int8)
+    sc = np.zeros(k, np.float32)
+    L.ref_quant_weights_per_oc(_p(w), k, c, r, s_, _p(out), _p(sc))
+    return out, sc
+
+
+def ref_quant_fp32(x, scale, unsigned=False):
+    """scale_fp32_int8 / scale_fp32_uint8 of the reference (oracle/_ref); None when not built."""
+    L = _ref_quant_lib()
+    if L is None:
+        return None
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.shape, np.uint8 if unsigned else np.int8)
+    (L.ref_quant_fp32_u8 if unsigned else L.ref_quant_fp32_s8)(_p(x), x.size, _f(scale), _p(out))
+    return out
 
 
 _REF_FOLD = os.path.join(_HERE, "_ref", "libanakin_ref_fold.so")

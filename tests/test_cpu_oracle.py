@@ -176,6 +176,27 @@ def test_bn_fold_matches_reference_update_weights(oracle, conv_bias, scale_bias,
     np.testing.assert_array_equal(got[1], want[1])
 
 
+def test_int8_quantisation_helpers_match_reference_scale_utils(oracle):
+    """The x86 INT8 quantisation rules restated in oracle.c vs the reference's own utils::ScaleUtils
+    (saber/funcs/impl/x86/x86_utils.h:293-372) compiled into oracle/_ref: per-output-channel weight quantisation
+    (truncating cast), activation quantisation to s8 (roundf + clamp) and to u8 (scale * 127/255, truncation)."""
+    rng = np.random.default_rng(11)
+    w = (rng.standard_normal((48, 20, 3, 3)) * rng.uniform(0.01, 3.0, (48, 1, 1, 1))).astype(np.float32)
+    want = oracle.ref_quant_weights_per_oc(w)
+    if want is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    got = oracle.quant_weights_per_oc(w)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
+    x = np.concatenate([rng.uniform(-3, 3, 5000), [0.5, -0.5, 1.5, -1.5, 2.5, 126.5, 127.5, -128.5, 3e4, -3e4]]).astype(np.float32)
+    for scale in (0.013, 0.02362, 1.0):
+        np.testing.assert_array_equal(oracle.quant_fp32_s8(x * scale, scale), oracle.ref_quant_fp32(x * scale, scale))
+    xu = np.concatenate([rng.uniform(0, 3, 5000), [0.0, 0.999, 1.0, 254.9, 255.0]]).astype(np.float32)
+    for scale in (0.013, 0.02362):
+        np.testing.assert_array_equal(oracle.quant_fp32_u8(xu * scale * 127 / 255, scale),
+                                      oracle.ref_quant_fp32(xu * scale * 127 / 255, scale, unsigned=True))
+
+
 def test_bn_fold_equals_unfused_ops(oracle):
     """parameter_fusion.cpp:86-131: conv -> BN -> Scale equals the folded conv."""
     rng = np.random.default_rng(9)
