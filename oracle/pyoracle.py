@@ -25,7 +25,7 @@ def build(ref=True):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
     if ref and os.path.isdir("/root/reference/test/saber") and not all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in
                     ("libanakin_ref_oracle.so", "libanakin_ref_shapes.so", "libanakin_ref_fold.so",
-                     "libanakin_ref_quant.so")):
+                     "libanakin_ref_quant.so", "libanakin_ref_gemmconv.so")):
         subprocess.check_call(["make", "-C", _HERE, "ref"])
 
 
@@ -279,6 +279,35 @@ def ref_quant_fp32(x, scale, unsigned=False):
     x = np.ascontiguousarray(x, np.float32)
     out = np.zeros(x.shape, np.uint8 if unsigned else np.int8)
     (L.ref_quant_fp32_u8 if unsigned else L.ref_quant_fp32_s8)(_p(x), x.size, _f(scale), _p(out))
+    return out
+
+
+_REF_GEMMCONV = os.path.join(_HERE, "_ref", "libanakin_ref_gemmconv.so")
+_ref_gemmconv = None
+
+
+def ref_gemm_conv_int8(x, w_f32, bias, in_scale, out_dtype, out_scale, stride=(1, 1), pad=(0, 0), dil=(1, 1),
+                       relu=False):
+    """The reference's own x86 INT8 convolution GemmX8S8S32XConv (init + dispatch, oracle/_ref): x NHWC s8|u8,
+    fp32 KCRS weights quantised by the reference itself. None when not built."""
+    global _ref_gemmconv
+    if _ref_gemmconv is None:
+        if not os.path.exists(_REF_GEMMCONV):
+            return None
+        _ref_gemmconv = C.CDLL(_REF_GEMMCONV)
+    x = np.ascontiguousarray(x)
+    w_f32 = np.ascontiguousarray(w_f32, np.float32)
+    n, h, wd, c = x.shape
+    k, _, r, s_ = w_f32.shape
+    oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
+    ow = conv_out_size(wd, pad[1], dil[1], s_, stride[1])
+    out = np.zeros((n, oh, ow, k), _NP[out_dtype])
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    st = _ref_gemmconv.ref_gemm_conv_int8(_p(x), int(x.dtype == np.uint8), _f(in_scale), _p(w_f32), _p(b), _p(out),
+                                          out_dtype, _f(out_scale), n, h, wd, c, k, r, s_, oh, ow, stride[0],
+                                          stride[1], pad[0], pad[1], dil[0], dil[1], int(relu))
+    if st != -1:
+        raise RuntimeError("reference GemmX8S8S32XConv returned SaberStatus %d" % st)
     return out
 
 

@@ -176,6 +176,38 @@ def test_bn_fold_matches_reference_update_weights(oracle, conv_bias, scale_bias,
     np.testing.assert_array_equal(got[1], want[1])
 
 
+# (input unsigned, output dtype, relu): the dtype pairs GemmX8S8S32XConv::dispatch accepts (gemm_x8s8s32x_conv.cpp:287-306);
+# u8 output only with relu -- without it the reference casts negative values with wrap-around (no saturation)
+_GEMM_CONV_DTYPES = [(True, 7, True), (True, 1, False), (True, 1, True), (False, 3, False), (False, 3, True),
+                     (False, 7, True), (False, 1, False)]
+
+
+@pytest.mark.parametrize("xu,odt,relu", _GEMM_CONV_DTYPES)
+@pytest.mark.parametrize("k,pad,stride,dil", [(1, 0, 1, 1), (3, 1, 1, 1), (3, 1, 2, 1), (3, 0, 1, 1), (1, 0, 2, 1), (3, 2, 1, 2)])
+def test_x86_int8_conv_matches_reference_gemm_conv(oracle, xu, odt, relu, k, pad, stride, dil):
+    """The INT8 pipeline the CUDA path is held to -- per-channel weight quantisation, bias pre-scaling, the
+    input/output dtype scale table, integer accumulation, (acc + bias) * scale, relu, round-to-nearest-even -- against
+    the reference's own x86 INT8 convolution GemmX8S8S32XConv run verbatim (oracle/_ref; only MKL's integer GEMM is a
+    stand-in): bit-exact for every dtype pair it supports, bias on and off."""
+    rng = np.random.default_rng(hash((xu, odt, relu, k, pad, stride, dil)) % 2 ** 31)
+    for (n, hw, cin, cout), with_bias in [((1, 12, 16, 32), True), ((3, 21, 8, 4), False), ((2, 7, 64, 40), True)]:
+        x = rng.integers(0, 256, (n, hw, hw, cin)).astype(np.uint8) if xu else rng.integers(-128, 128, (n, hw, hw, cin)).astype(np.int8)
+        w = (rng.standard_normal((cout, cin, k, k)) * rng.uniform(0.02, 0.3, (cout, 1, 1, 1))).astype(np.float32)
+        bias = rng.uniform(-0.5, 0.5, cout).astype(np.float32) if with_bias else None
+        in_scale = 0.0173
+        kw = dict(stride=(stride, stride), pad=(pad, pad), dil=(dil, dil))
+        # an output scale under which nothing leaves the 8-bit range (the reference's cast does not saturate)
+        yf = oracle.ref_gemm_conv_int8(x, w, bias, in_scale, 1, 1.0, relu=relu, **kw)
+        if yf is None:
+            pytest.skip("oracle/_ref not built (no /root/reference here)")
+        out_scale = float(np.abs(yf).max()) / 120.0 + 1e-6
+        want = oracle.ref_gemm_conv_int8(x, w, bias, in_scale, odt, out_scale, relu=relu, **kw)
+        wq, ws = oracle.quant_weights_per_oc(w)
+        sc, bf, _ = oracle.int8_conv_scales(ws, bias, in_scale, 7 if xu else 3, out_scale, odt)
+        got = oracle.conv_s8_nhwc_x86(x, wq, bf if with_bias else None, sc, out_dtype=odt, relu=relu, **kw)
+        np.testing.assert_array_equal(got, want)
+
+
 def test_int8_quantisation_helpers_match_reference_scale_utils(oracle):
     """The x86 INT8 quantisation rules restated in oracle.c vs the reference's own utils::ScaleUtils
     (saber/funcs/impl/x86/x86_utils.h:293-372) compiled into oracle/_ref: per-output-channel weight quantisation
