@@ -16,7 +16,10 @@ In-memory form (plain dicts, no classes):
   node  = {"name": str, "op": str, "ins": [str], "outs": [str], "attrs": {key: value},
            "bit_type": None | "FLOAT" | "INT8", "lane": int, "need_wait": bool}
   attr values: str | bool | int | float | list[int|float|bool|str] | np.ndarray(float32, 4-D)
-               | {"tensor": ndarray, "scale": [float]} (tensor with int8 scale)
+               | {"tensor": ndarray, "scale": [float]} (tensor with int8 scale; an int8 ndarray is stored as the
+                 INT8 payload CacheDate.c, model_io.cpp:204-216)
+               | {"share_from": node_name} (TensorProto.shared: the owner node's tensor of the same key,
+                 model_io.cpp:147-151)
 """
 import struct
 
@@ -99,7 +102,8 @@ def _enc_shape(dims):
 
 def _enc_tensor(arr, scale=None, name=None):
     """TensorProto{name=1,shared=2,share_from=3,shape=8,valid_shape=9,data=10,scale=11}"""
-    arr = np.ascontiguousarray(arr, dtype=np.float32)
+    q8 = isinstance(arr, np.ndarray) and arr.dtype == np.int8
+    arr = np.ascontiguousarray(arr, dtype=np.int8 if q8 else np.float32)
     shape = list(arr.shape)
     while len(shape) < 4:
         shape.insert(0, 1)
@@ -108,7 +112,12 @@ def _enc_tensor(arr, scale=None, name=None):
         out += _f_bytes(1, name)
     out += _f_bytes(8, _enc_shape(shape))
     out += _f_bytes(9, _enc_shape(shape))
-    out += _f_bytes(10, _enc_cache(arr.ravel(), FLOAT))
+    if q8:
+        cache = (_f_bytes(8, arr.tobytes()) if arr.size else b"") + _f_varint(6, INT8) + \
+                (_f_varint(7, arr.size) if arr.size else b"")
+        out += _f_bytes(10, cache)
+    else:
+        out += _f_bytes(10, _enc_cache(arr.ravel(), FLOAT))
     if scale is not None and len(scale):
         out += _f_bytes(11, _enc_cache(list(scale), FLOAT))
     return bytes(out)
@@ -116,6 +125,8 @@ def _enc_tensor(arr, scale=None, name=None):
 
 def _enc_value(v):
     """valueType{s=1,i=2,f=3,b=4,cache_list=8,tensor=10,type=14}"""
+    if isinstance(v, dict) and "share_from" in v:
+        return _f_bytes(10, _f_varint(2, 1) + _f_bytes(3, v["share_from"])) + _f_varint(14, TENSOR)
     if isinstance(v, dict) and "tensor" in v:
         return _f_bytes(10, _enc_tensor(v["tensor"], v.get("scale"))) + _f_varint(14, TENSOR)
     if isinstance(v, np.ndarray):
@@ -150,14 +161,16 @@ def _enc_node(node):
         out += _f_bytes(2, s)
     for s in node.get("outs", []):
         out += _f_bytes(3, s)
-    for k, v in node.get("attrs", {}).items():
+    # map entries in key order: what protobuf's deterministic serialisation (and the C++ writer's std::map) emit
+    for k, v in sorted(node.get("attrs", {}).items(), key=lambda kv: kv[0].encode("utf-8")):
         entry = _f_bytes(1, k) + _f_bytes(2, _enc_value(v))
         out += _f_bytes(10, entry)
     if node.get("lane"):
         out += _f_varint(11, node["lane"])
     if node.get("need_wait"):
         out += _f_varint(12, 1)
-    op = _f_bytes(1, node["op"]) + _f_varint(3, len(node.get("ins", []))) + _f_varint(4, len(node.get("outs", [])))
+    n_in, n_out = len(node.get("ins", [])), len(node.get("outs", []))   # proto3: zero scalars are not emitted
+    op = _f_bytes(1, node["op"]) + (_f_varint(3, n_in) if n_in else b"") + (_f_varint(4, n_out) if n_out else b"")
     out += _f_bytes(15, op)
     bt = _BIT[node.get("bit_type")]
     if bt:
@@ -184,9 +197,9 @@ def dumps(graph):
     for node in graph["nodes"]:
         out += _f_bytes(2, _enc_node(node))
     for field, key in ((3, "edges_in"), (4, "edges_out")):
-        for name, targets in graph.get(key, {}).items():
+        for name, targets in sorted(graph.get(key, {}).items(), key=lambda kv: kv[0].encode("utf-8")):
             out += _f_bytes(field, _f_bytes(1, name) + _f_bytes(2, _enc_list(targets)))
-    for ename, info in graph.get("edges_info", {}).items():
+    for ename, info in sorted(graph.get("edges_info", {}).items(), key=lambda kv: kv[0].encode("utf-8")):
         t = _f_bytes(1, ename)
         if info.get("shared"):
             t += _f_varint(2, 1) + _f_bytes(3, info.get("share_from", ""))
@@ -260,7 +273,7 @@ def _packed_varints(v):
 
 
 def _dec_cache(buf):
-    d = {"s": [], "i": [], "f": None, "b": [], "type": 0, "size": 0}
+    d = {"s": [], "i": [], "f": None, "b": [], "c": b"", "type": 0, "size": 0}
     fchunks = []
     for field, wt, v in _fields(buf):
         if field == 1:
@@ -271,6 +284,8 @@ def _dec_cache(buf):
             fchunks.append(np.frombuffer(v, dtype="<f4") if wt == 2 else np.frombuffer(v, dtype="<f4"))
         elif field == 4:
             d["b"].extend([bool(x) for x in bytes(v)] if wt == 2 else [bool(v)])
+        elif field == 8:
+            d["c"] = bytes(v)
         elif field == 6:
             d["type"] = v
         elif field == 7:
@@ -303,7 +318,8 @@ def _dec_tensor(buf):
         elif field == 9:
             t["valid_shape"] = _dec_shape(v)
         elif field == 10:
-            t["data"] = _dec_cache(v)["f"]
+            c = _dec_cache(v)
+            t["data"] = np.frombuffer(c["c"], dtype=np.int8) if c["type"] == INT8 else c["f"]
         elif field == 11:
             t["scale"] = [float(x) for x in _dec_cache(v)["f"]]
     return t
@@ -337,7 +353,11 @@ def _dec_value(buf):
         return list(c["s"])
     if typ == TENSOR:
         t = _dec_tensor(raw.get(10, b""))
-        arr = np.array(t["data"], dtype=np.float32).reshape(t["shape"]) if t["data"] is not None else None
+        if t["shared"]:
+            return {"share_from": t["share_from"]}
+        arr = None
+        if t["data"] is not None:
+            arr = np.array(t["data"], dtype=np.int8 if t["data"].dtype == np.int8 else np.float32).reshape(t["shape"])
         if t["scale"]:
             return {"tensor": arr, "scale": t["scale"]}
         return arr

@@ -48,6 +48,10 @@ SYMBOLS = {
     "anakin_net_set_cuda_graph": (_i, [_vp, _i]),
     "anakin_net_exec_order": (_sz, [_vp, _vp, _sz]),
     "anakin_net_activation_bytes": (_sz, [_vp]),
+    "anakin_net_activation_bytes_unshared": (_sz, [_vp]),
+    "anakin_net_weight_ptrs": (_i, [_vp, C.POINTER(_vp), _i]),
+    "anakin_weight_arena_stats": (_sz, [C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "anakin_net_create_ex": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
     "anakin_net_profile_ops": (_i, [_vp, _i, _i, C.POINTER(C.c_float), _i]),
     "anakin_net_destroy": (None, [_vp]),
     "anakin_worker_create": (_i, [_cp, _i, _i, C.POINTER(_i), _i, _i, C.POINTER(_vp)]),
@@ -143,11 +147,14 @@ class Graph:
 class Net:
     """Net<NV, P>: init(graph) on a device, prediction(), tensors by node name."""
 
-    def __init__(self, graph, precision="fp32", device=-1):
+    def __init__(self, graph, precision="fp32", device=-1, keep_edges=False):
+        """keep_edges=True gives every edge tensor its own buffer so intermediate tensors can be read back after
+        prediction() (parity tests); the default shares buffers between edges whose live ranges do not overlap."""
         self._lib = load()
         self._h = _vp()
         prec = PRECISIONS[precision] if isinstance(precision, str) else precision
-        _check(self._lib.anakin_net_create(graph._h, prec, device, C.byref(self._h)), "Net.init")
+        _check(self._lib.anakin_net_create_ex(graph._h, prec, device, 1 if keep_edges else 0, C.byref(self._h)),
+               "Net.init")
         self.in_names = [self._lib.anakin_net_input_name(self._h, i).decode()
                          for i in range(self._lib.anakin_net_num_inputs(self._h))]
         self.out_names = [self._lib.anakin_net_output_name(self._h, i).decode()
@@ -233,10 +240,27 @@ class Net:
     def activation_bytes(self):
         return self._lib.anakin_net_activation_bytes(self._h)
 
+    def activation_bytes_unshared(self):
+        return self._lib.anakin_net_activation_bytes_unshared(self._h)
+
+    def weight_ptrs(self):
+        n = self._lib.anakin_net_weight_ptrs(self._h, None, 0)
+        buf = (_vp * max(1, n))()
+        self._lib.anakin_net_weight_ptrs(self._h, buf, n)
+        return [int(buf[i] or 0) for i in range(n)]
+
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.anakin_net_destroy(self._h)
             self._h = _vp()
+
+
+def weight_arena_stats():
+    """(device bytes, entries, hits, misses) of the process-wide packed-weight arena."""
+    lib = load()
+    e, h, m = _sz(), _sz(), _sz()
+    b = lib.anakin_weight_arena_stats(C.byref(e), C.byref(h), C.byref(m))
+    return int(b), e.value, h.value, m.value
 
 
 class Worker:

@@ -53,6 +53,7 @@ constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane qu
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int NUM_THREADS = 64 + EPI_THREADS;      // warp0 TMA, warp1 MMA, then the epilogue warps
 constexpr int MAX_SMEM = 227 * 1024;
+constexpr int kMaxDevices = 64;
 
 struct ConvKParams {
     int32_t M_total, HoWo, Wo;
@@ -77,16 +78,6 @@ struct ConvKParams {
     int32_t split;       // split-K factor = cluster size along z (1, 2 or 4)
     const float* bias;
     const float* scale;
-#ifdef B200_DATAFLOW
-    // Tile-level hand-over between conv layers (experimental build, see "dataflow" below): per-m-tile
-    // completion counters instead of the grid dependency. A null df_in_flags keeps griddepcontrol.wait.
-    const uint32_t* df_in_flags;    // producer layer of the input tensor
-    const uint32_t* df_res_flags;   // producer layer of the residual tensor
-    uint32_t* df_out_flags;         // this layer: every CTA adds 1 to its m-tile's counter once its slice is in memory
-    uint32_t df_in_target, df_res_target;   // increments a complete m-tile has received (grid.y * split of the producer)
-    int32_t df_in_tiles;            // m-tiles of the input's producer
-    int32_t Hin, Win;               // input feature map
-#endif
 };
 
 // Shared memory carve-up (1024-B aligned base):
@@ -470,23 +461,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const bool may_pad = p.KS != p.KS_real;
             const int res_cols_per_panel = p.res_panels > 0 ? p.res_pw / p.res_es : 0;
             int pre_left = npre;
-#ifdef B200_DATAFLOW
-            if (p.df_in_flags != nullptr) {
-                // wait for the producer's m-tiles this tile's im2col window can touch (whole input rows, first
-                // pixel's first row to last pixel's last row: conservative and contiguous in the flat index)
-                const int m_last = min(m0 + BLOCK_M, p.M_total) - 1;
-                const int n_last = m_last / p.HoWo;
-                const int p_last = (m_last - n_last * p.HoWo) / p.Wo;
-                const int h_lo = max(base_h, 0);
-                const int h_hi = min(p_last * p.stride_h - p.pad_h + (p.R - 1) * p.dil_h, p.Hin - 1);
-                const int hw = p.Hin * p.Win;
-                const int t_lo = (n_img * hw + h_lo * p.Win) >> 7;
-                const int t_hi = min((n_last * hw + h_hi * p.Win + p.Win - 1) >> 7, p.df_in_tiles - 1);
-                for (int t = t_lo; t <= t_hi; ++t)
-                    while (static_cast<int32_t>(ld_acquire_gpu(p.df_in_flags + t) - p.df_in_target) < 0) __nanosleep(20);
-                fence_proxy_async_all();
-            } else
-#endif
             pdl_wait_prior_grid();
             TL(2);
             for (int it = it_begin; it < it_end; ++it) {
@@ -524,13 +498,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (++stage == p.stages) { stage = 0; phase ^= 1; stage_sa = ring_sa; full_sa = full_sa0; empty_sa = empty_sa0; }
                 if (it == it_begin && p.res_panels > 0 && own_groups > 0) {
                     // the residual tile is only needed by the epilogue: after the first operand stage is on its way
-#ifdef B200_DATAFLOW
-                    if (p.df_res_flags != nullptr) {   // residual rows = this tile's own rows of its producer
-                        while (static_cast<int32_t>(ld_acquire_gpu(p.df_res_flags + blockIdx.x) - p.df_res_target) < 0)
-                            __nanosleep(20);
-                        fence_proxy_async_all();
-                    }
-#endif
                     mbar_arrive_expect_tx(res_full_bar, p.res_panels * BLOCK_M * p.res_pw);
                     for (int j = 0; j < p.res_panels; ++j)
                         tma_load_2d(&map_res, res_full_bar, res_tile + j * BLOCK_M * p.res_pw,
@@ -710,14 +677,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tma_store_2d(&map_out, out_tile + j * BLOCK_M * p.out_pw, n0_epi + j * cols_per_panel, m0);
             }
             tma_store_commit();
-#ifdef B200_DATAFLOW
-            if (p.df_out_flags != nullptr) {
-                tma_store_wait_all();       // the slice is in memory, not merely read out of shared memory
-                fence_proxy_async_all();
-                __threadfence();
-                red_release_gpu_add(p.df_out_flags + blockIdx.x, 1u);
-            } else
-#endif
             tma_store_wait_read();  // smem may be released once the engine has read it; the writes
                                     // complete before the grid is reported complete
 #ifdef B200_TIMELINE
@@ -727,10 +686,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     }
 
-#ifdef B200_DATAFLOW
-    // a split-K rank whose channel slice is empty stores nothing but still counts towards its m-tile
-    if (own_groups == 0 && threadIdx.x == 64 && p.df_out_flags != nullptr) red_release_gpu_add(p.df_out_flags + blockIdx.x, 1u);
-#endif
     __syncthreads();
     if (warp_idx == 1) {
         tc_fence_after();
@@ -834,17 +789,19 @@ struct b200_conv_plan {
     const void* map_out_ptr;
     const void* map_res_ptr;
     void (*launch)(b200_conv_plan*, void* stream);
-#ifdef B200_DATAFLOW
-    uint32_t* df_flags = nullptr;   // per-m-tile completion counters of this plan (arena of the stream it runs on)
-    void* df_stream = nullptr;
-#endif
 };
 
 template <int KIND, int BN, bool SPLITK>
 static void launch_conv(b200_conv_plan* pl, void* stream) {
     auto kern = conv_igemm_kernel<KIND, BN, SPLITK>;
-    static std::once_flag once;
-    std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM); });
+    // function attributes are per device: a Worker may drive several GPUs from one process
+    static std::atomic<bool> opted_in[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < kMaxDevices && !opted_in[dev].load(std::memory_order_acquire)) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+        opted_in[dev].store(true, std::memory_order_release);
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = pl->grid;
     cfg.blockDim = dim3(NUM_THREADS);
@@ -946,102 +903,7 @@ static int encode_tile_map(CUtensorMap* map, const void* ptr, int dtype, int k_v
     return B200_SUCCESS;
 }
 
-// ----------------------------------------------------------------- dataflow hand-over (experimental build)
-// With -DB200_DATAFLOW and B200_SABER_DATAFLOW=1 consecutive conv layers hand tiles over through per-m-tile
-// counters instead of waiting for the whole previous grid: a plan that runs registers the buffer it writes;
-// a plan whose input (and residual) buffer was written by a registered plan waits on that plan's counters only.
-// Counters live in one arena per stream (= per Net), zeroed by b200_dataflow_begin_step at the top of every
-// prediction(). Requires every activation buffer to have a single producer per step (true for this Net: no
-// buffer sharing). NOT validated on hardware yet: the shipped library is built without the macro.
-#ifdef B200_DATAFLOW
-namespace {
-struct DfArena {
-    uint32_t* base = nullptr;
-    size_t cap = 0, used = 0;   // 32-bit words
-};
-std::mutex g_df_mu;
-std::map<void*, DfArena> g_df_arena;                      // stream -> arena
-std::map<const void*, b200_conv_plan*> g_df_by_out;       // output buffer -> the plan that writes it
-
-bool df_enabled() {
-    static const bool on = [] { const char* e = getenv("B200_SABER_DATAFLOW"); return e && e[0] == '1'; }();
-    return on;
-}
-uint32_t* df_alloc(void* stream, size_t words) {           // caller holds g_df_mu
-    DfArena& a = g_df_arena[stream];
-    if (!a.base) {
-        const size_t cap = 1u << 18;                        // 1 MiB of counters per stream
-        if (cudaMalloc(&a.base, cap * sizeof(uint32_t)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
-        cudaMemset(a.base, 0, cap * sizeof(uint32_t));
-        a.cap = cap;
-    }
-    if (a.used + words > a.cap) return nullptr;
-    uint32_t* p = a.base + a.used;
-    a.used += words;
-    return p;
-}
-// (re)bind the plan's producer links for the buffers of this run
-void df_link(b200_conv_plan* pl, const void* in, const void* res, void* out, void* stream) {
-    std::lock_guard<std::mutex> lk(g_df_mu);
-    ConvKParams& kp = pl->kp;
-    if (!pl->df_flags || pl->df_stream != stream) {
-        pl->df_flags = df_alloc(stream, pl->grid.x);
-        pl->df_stream = stream;
-    }
-    for (auto it = g_df_by_out.begin(); it != g_df_by_out.end();)
-        it = (it->second == pl) ? g_df_by_out.erase(it) : std::next(it);
-    kp.df_out_flags = pl->df_flags;
-    if (pl->df_flags) g_df_by_out[out] = pl;
-    kp.df_in_flags = kp.df_res_flags = nullptr;
-    kp.Hin = pl->desc.h; kp.Win = pl->desc.w;
-    auto producer = [&](const void* buf, int64_t rows) -> b200_conv_plan* {
-        auto it = g_df_by_out.find(buf);
-        if (it == g_df_by_out.end() || it->second == pl) return nullptr;
-        b200_conv_plan* q = it->second;
-        return (q->df_flags && q->df_stream == stream && q->g.M_total == rows) ? q : nullptr;
-    };
-    b200_conv_plan* pin = producer(in, static_cast<int64_t>(pl->desc.n) * pl->desc.h * pl->desc.w);
-    b200_conv_plan* pres = pl->desc.res_dtype >= 0 ? producer(res, pl->g.M_total) : nullptr;
-    if (!pin || (pl->desc.res_dtype >= 0 && !pres)) return;   // any unregistered producer: keep the grid dependency
-    kp.df_in_flags = pin->df_flags;
-    kp.df_in_target = pin->grid.y * pin->grid.z;
-    kp.df_in_tiles = static_cast<int32_t>(pin->grid.x);
-    if (pres) {
-        kp.df_res_flags = pres->df_flags;
-        kp.df_res_target = pres->grid.y * pres->grid.z;
-    }
-}
-void df_forget(b200_conv_plan* pl) {
-    std::lock_guard<std::mutex> lk(g_df_mu);
-    for (auto it = g_df_by_out.begin(); it != g_df_by_out.end();)
-        it = (it->second == pl) ? g_df_by_out.erase(it) : std::next(it);
-}
-}  // namespace
-#endif
-
 extern "C" {
-
-int b200_dataflow_supported(void) {
-#ifdef B200_DATAFLOW
-    return df_enabled() ? 1 : 0;
-#else
-    return 0;
-#endif
-}
-
-int b200_dataflow_begin_step(void* stream) {
-#ifdef B200_DATAFLOW
-    if (!df_enabled()) return B200_SUCCESS;
-    std::lock_guard<std::mutex> lk(g_df_mu);
-    auto it = g_df_arena.find(stream);
-    if (it == g_df_arena.end() || it->second.used == 0) return B200_SUCCESS;
-    if (cudaMemsetAsync(it->second.base, 0, it->second.used * sizeof(uint32_t), static_cast<cudaStream_t>(stream)) != cudaSuccess)
-        return B200_UNKNOWN_ERROR;
-#else
-    (void)stream;
-#endif
-    return B200_SUCCESS;
-}
 
 int b200_conv_out_hw(const b200_conv_desc_t* d, int32_t* ho, int32_t* wo) {
     if (!d) return B200_INVALID_VALUE;
@@ -1294,10 +1156,6 @@ int b200_conv_plan_run(b200_conv_plan_t* pl, const void* in, const void* res, vo
     if (!pl || !in || !out) return B200_INVALID_VALUE;
     const b200_conv_desc_t& d = pl->desc;
     if (d.res_dtype >= 0 && !res) return B200_INVALID_VALUE;
-#ifdef B200_DATAFLOW
-    const bool df_rebind = df_enabled() && (in != pl->map_a_ptr || out != pl->map_out_ptr ||
-                                            (d.res_dtype >= 0 && res != pl->map_res_ptr) || pl->df_stream != stream);
-#endif
     if (in != pl->map_a_ptr) {
         int st = encode_map_a(pl, in);
         if (st != B200_SUCCESS) return st;
@@ -1314,9 +1172,6 @@ int b200_conv_plan_run(b200_conv_plan_t* pl, const void* in, const void* res, vo
     } else if (d.res_dtype < 0 && pl->map_res_ptr == nullptr) {
         pl->map_res = pl->map_out;  // placeholder: never dereferenced when res_panels == 0
     }
-#ifdef B200_DATAFLOW
-    if (df_rebind) df_link(pl, in, res, out, stream);
-#endif
     pl->launch(pl, stream);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
@@ -1327,9 +1182,6 @@ int b200_conv_plan_run(b200_conv_plan_t* pl, const void* in, const void* res, vo
 }
 
 void b200_conv_plan_destroy(b200_conv_plan_t* pl) {
-#ifdef B200_DATAFLOW
-    if (pl) df_forget(pl);
-#endif
     delete pl;
 }
 

@@ -91,8 +91,13 @@ size_t anakin_graph_describe(anakin_graph_t* g, char* buf, size_t cap) {
 void anakin_graph_destroy(anakin_graph_t* g) { delete g; }
 
 int anakin_net_create(anakin_graph_t* g, int precision, int device, anakin_net_t** out) {
+    return anakin_net_create_ex(g, precision, device, 0, out);
+}
+
+int anakin_net_create_ex(anakin_graph_t* g, int precision, int device, int flags, anakin_net_t** out) {
     if (!g || !out) return fail("null argument");
     auto* n = new anakin_net();
+    if (flags & ANAKIN_NET_KEEP_EDGES) n->net.set_share_activations(false);
     Status st = n->net.init(g->g, to_precision(precision), device);
     if (!st) { std::string m = st.info(); delete n; return fail(m); }
     n->ins = n->net.get_in_names();
@@ -184,6 +189,16 @@ int anakin_net_profile_ops(anakin_net_t* n, int iters, int reps, float* ms, int 
     return 0;
 }
 size_t anakin_net_activation_bytes(anakin_net_t* n) { return n ? n->net.activation_bytes() : 0; }
+size_t anakin_net_activation_bytes_unshared(anakin_net_t* n) { return n ? n->net.activation_bytes_unshared() : 0; }
+int anakin_net_weight_ptrs(anakin_net_t* n, const void** out, int cap) {
+    if (!n) return 0;
+    std::vector<const void*> v = n->net.weight_device_ptrs();
+    for (int i = 0; out && i < cap && i < static_cast<int>(v.size()); ++i) out[i] = v[i];
+    return static_cast<int>(v.size());
+}
+size_t anakin_weight_arena_stats(size_t* entries, size_t* hits, size_t* misses) {
+    return saber::weight_arena_stats(entries, hits, misses);
+}
 void anakin_net_destroy(anakin_net_t* n) { delete n; }
 
 int anakin_worker_create(const char* model_path, int precision, int threads, const int* devices, int n_devices,

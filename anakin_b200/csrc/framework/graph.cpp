@@ -86,7 +86,9 @@ struct CacheData {
     std::vector<int> i;
     std::vector<float> f;
     std::vector<bool> b;
+    std::string c;          // CacheDate.c: int8 payload (tensor.proto field 8)
     int type = 0;
+    long long size = -1;    // CacheDate.size (field 7); -1 = absent
 };
 
 CacheData read_cache(Reader r) {
@@ -111,7 +113,9 @@ CacheData read_cache(Reader r) {
                 if (wt == 2) { while (!sub.done()) c.b.push_back(sub.varint() != 0); }
                 else c.b.push_back(v != 0);
                 break;
+            case 8: c.c = sub.str(); break;
             case 6: c.type = static_cast<int>(v); break;
+            case 7: c.size = static_cast<long long>(v); break;
             default: break;
         }
     }
@@ -135,8 +139,11 @@ std::vector<int> read_shape(Reader r) {
 }
 
 struct TensorData {
-    std::vector<int> shape;
+    std::vector<int> shape, valid_shape;
     std::vector<float> data, scale;
+    std::string q8;          // int8 codes when data_type == P_INT8
+    int data_type = P_FLOAT;
+    long long data_size = -1;
     bool shared = false;
     std::string share_from;
 };
@@ -149,7 +156,15 @@ TensorData read_tensor(Reader r) {
             case 2: t.shared = v != 0; break;
             case 3: t.share_from = sub.str(); break;
             case 8: t.shape = read_shape(sub); break;
-            case 10: t.data = std::move(read_cache(sub).f); break;
+            case 9: t.valid_shape = read_shape(sub); break;
+            case 10: {
+                CacheData c = read_cache(sub);
+                t.data = std::move(c.f);
+                t.q8 = std::move(c.c);
+                // proto3 drops a zero enum: an absent type with int8 bytes present still means INT8
+                t.data_type = c.type == P_INT8 || (c.type == 0 && !t.q8.empty() && t.data.empty()) ? P_INT8 : P_FLOAT;
+                t.data_size = c.size;
+            } break;
             case 11: t.scale = read_cache(sub).f; break;
             default: break;
         }
@@ -157,18 +172,33 @@ TensorData read_tensor(Reader r) {
     return t;
 }
 
-PBlockPtr make_block(const std::vector<int>& shape, const float* data, size_t n, const std::vector<float>& scale) {
+// model_io.cpp:152-216: a FLOAT tensor becomes an fp32 block, an INT8 tensor an int8 block carrying its
+// per-output-channel scales; the real shape allocates, a present valid_shape re-shapes. A payload that does not
+// fill the shape is an error here (the reference would read past the repeated field and abort).
+PBlockPtr make_block(const TensorData& t, std::string* err) {
     PBlockPtr b = std::make_shared<PBlock>();
-    std::vector<int> sh = shape;
+    std::vector<int> sh = t.shape;
     while (sh.size() < 4) sh.insert(sh.begin(), 1);
-    b->h.re_alloc(Shape(sh, saber::Layout_NCHW), saber::AK_FLOAT);
+    const bool q8 = t.data_type == P_INT8;
+    b->h.re_alloc(Shape(sh, saber::Layout_NCHW), q8 ? saber::AK_INT8 : saber::AK_FLOAT);
     const size_t cnt = static_cast<size_t>(b->h.valid_size());
-    if (cnt && data) memcpy(b->h.mutable_data(), data, std::min(cnt, n) * sizeof(float));
-    b->h.set_scale(scale);
+    const size_t have = q8 ? t.q8.size() : t.data.size();
+    if (have != cnt) {
+        if (err) *err = "tensor payload holds " + std::to_string(have) + " elements, shape needs " + std::to_string(cnt);
+        return nullptr;
+    }
+    if (cnt) {
+        if (q8) memcpy(b->h.mutable_data(), t.q8.data(), cnt);
+        else memcpy(b->h.mutable_data(), t.data.data(), cnt * sizeof(float));
+    }
+    b->h.set_scale(t.scale);
+    if (t.valid_shape.size() == 4 && t.valid_shape != sh) b->h.set_shape(Shape(t.valid_shape, saber::Layout_NCHW));
     return b;
 }
 
-bool read_value(Reader r, AttrValue& out) {
+// `share_from` receives the owner node's name when the value is a shared tensor (TensorProto.shared): the caller
+// points the attribute at that node's block once every node is parsed (model_io.cpp:147-151).
+bool read_value(Reader r, AttrValue& out, std::string* share_from, std::string* err) {
     int type = P_STR;
     std::string s; int i = 0; float f = 0.f; bool b = false;
     CacheData cache; TensorData tensor; bool has_tensor = false;
@@ -199,7 +229,17 @@ bool read_value(Reader r, AttrValue& out) {
             }
         case P_TENSOR:
             if (!has_tensor) return false;
-            out = make_block(tensor.shape, tensor.data.data(), tensor.data.size(), tensor.scale);
+            if (tensor.shared) {
+                if (tensor.share_from.empty()) { if (err) *err = "shared tensor without share_from"; return false; }
+                if (share_from) *share_from = tensor.share_from;
+                out = PBlockPtr();
+                return true;
+            }
+            {
+                PBlockPtr blk = make_block(tensor, err);
+                if (!blk) return false;
+                out = blk;
+            }
             return true;
         default: return false;
     }
@@ -222,7 +262,7 @@ std::string enc_shape(const std::vector<int>& dims) {
     return sh.buf;
 }
 
-std::string enc_value(const AttrValue& v) {
+std::string enc_value(const AttrValue& v, const std::string* share_from = nullptr) {
     Writer w;
     if (auto p = std::get_if<std::string>(&v)) {
         w.f_bytes(1, *p);
@@ -263,18 +303,31 @@ std::string enc_value(const AttrValue& v) {
         w.f_bytes(8, c.buf);
         w.f_varint(14, P_CACHE_LIST);
     } else if (auto p = std::get_if<PBlockPtr>(&v)) {
-        const PBlock& b = **p;
-        std::vector<int> dims = {b.h.num(), b.h.channel(), b.h.height(), b.h.width()};
         Writer t;
-        t.f_bytes(8, enc_shape(dims));
-        t.f_bytes(9, enc_shape(dims));
-        Writer c;
-        write_cache_floats(c, b.data(), static_cast<size_t>(b.count()));
-        t.f_bytes(10, c.buf);
-        if (!b.h.get_scale().empty()) {
-            Writer sc;
-            write_cache_floats(sc, b.h.get_scale().data(), b.h.get_scale().size());
-            t.f_bytes(11, sc.buf);
+        if (share_from && !share_from->empty()) {
+            // graph.cpp:700-718 (save): a shared weight is written as a reference to its owner node
+            t.f_varint(2, 1);
+            t.f_bytes(3, *share_from);
+        } else {
+            const PBlock& b = **p;
+            std::vector<int> dims = {b.h.num(), b.h.channel(), b.h.height(), b.h.width()};
+            t.f_bytes(8, enc_shape(dims));
+            t.f_bytes(9, enc_shape(dims));
+            Writer c;
+            const size_t n = static_cast<size_t>(b.count());
+            if (b.is_int8()) {
+                if (n) c.f_bytes(8, b.h.data(), n);
+                c.f_varint(6, P_INT8);
+                if (n) c.f_varint(7, n);
+            } else {
+                write_cache_floats(c, b.data(), n);
+            }
+            t.f_bytes(10, c.buf);
+            if (!b.h.get_scale().empty()) {
+                Writer sc;
+                write_cache_floats(sc, b.h.get_scale().data(), b.h.get_scale().size());
+                t.f_bytes(11, sc.buf);
+            }
         }
         w.f_bytes(10, t.buf);
         w.f_varint(14, P_TENSOR);
@@ -309,14 +362,15 @@ Status GraphIO::parse(GraphCore& g, const void* data, size_t len) {
                     case 2: n->ins.push_back(s2.str()); break;
                     case 3: n->outs.push_back(s2.str()); break;
                     case 10: {
-                        std::string key; AttrValue val; bool got = false;
+                        std::string key, from, err; AttrValue val; bool got = false;
                         int f3, w3; uint64_t v3; Reader s3(nullptr, 0);
                         while (s2.next(f3, w3, v3, s3)) {
                             if (f3 == 1) key = s3.str();
-                            else if (f3 == 2) got = read_value(s3, val);
+                            else if (f3 == 2) got = read_value(s3, val, &from, &err);
                         }
-                        if (!got) return Status::ANAKINFAIL("bad attr " + key + " in node " + n->name);
+                        if (!got) return Status::ANAKINFAIL("bad attr " + key + " in node " + n->name + (err.empty() ? "" : ": " + err));
                         n->attrs[key] = val;
+                        if (!from.empty()) n->share_pairs[key] = from;
                     } break;
                     case 11: n->lane = static_cast<int>(v2); break;
                     case 12: n->need_wait = v2 != 0; break;
@@ -371,6 +425,18 @@ Status GraphIO::parse(GraphCore& g, const void* data, size_t len) {
         }
     }
     if (!r.ok) return Status::ANAKINFAIL("malformed GraphProto");
+    // shared weights: the attribute points at the owner node's block of the same key (model_io.cpp:147-151;
+    // resolved after all nodes are read, so the owner may also follow its users in the file)
+    for (auto& kv : g._nodes) {
+        for (auto& sp : kv.second->share_pairs) {
+            NodePtr owner = g[sp.second];
+            if (!owner || !owner->has_attr<PBlockPtr>(sp.first) || !owner->get_attr<PBlockPtr>(sp.first) ||
+                owner->share_pairs.count(sp.first))
+                return Status::ANAKINFAIL("node " + kv.first + " shares '" + sp.first + "' from " + sp.second +
+                                          ", which does not own such a tensor");
+            kv.second->attrs[sp.first] = owner->get_attr<PBlockPtr>(sp.first);
+        }
+    }
     // arcs: the edges_in / edges_out maps are authoritative (parser.cpp:160-227)
     for (auto& kv : edges_in) {
         NodePtr n = g[kv.first];
@@ -418,15 +484,16 @@ std::string GraphIO::serialize(GraphCore& g) {
         for (auto& kv : n.attrs) {
             Writer e;
             e.f_bytes(1, kv.first);
-            e.f_bytes(2, enc_value(kv.second));
+            auto sp = n.share_pairs.find(kv.first);
+            e.f_bytes(2, enc_value(kv.second, sp == n.share_pairs.end() ? nullptr : &sp->second));
             nw.f_bytes(10, e.buf);
         }
         if (n.lane) nw.f_varint(11, static_cast<uint64_t>(n.lane));
         if (n.need_wait) nw.f_varint(12, 1);
         Writer op;
         op.f_bytes(1, n.op);
-        op.f_varint(3, n.ins.size());
-        op.f_varint(4, n.outs.size());
+        if (!n.ins.empty()) op.f_varint(3, n.ins.size());     // proto3: zero scalars are not emitted
+        if (!n.outs.empty()) op.f_varint(4, n.outs.size());
         nw.f_bytes(15, op.buf);
         if (n.bit_type == saber::AK_INT8) nw.f_varint(16, P_INT8);
         else if (n.bit_type == saber::AK_FLOAT) nw.f_varint(16, P_FLOAT);

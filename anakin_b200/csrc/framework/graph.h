@@ -40,13 +40,17 @@ private:
 template <typename T>
 using PTuple = std::vector<T>;
 
-// Weight block: fp32 host tensor (4-D) + optional int8 scale. The device image is built by the
-// consuming op (packed for tcgen05), once.
+// Weight block: host tensor (4-D), fp32 -- or int8 codes with per-output-channel scales when the model file
+// stores quantised weights (model_io.cpp:204-216). The device image is built by the consuming op (packed for
+// tcgen05) once per device and shared by every Net that uses the block (saber_funcs.cpp, WeightArena).
 struct PBlock {
     saber::Tensor<saber::NVHX86> h;
     saber::Tensor<saber::NVHX86>& h_tensor() { return h; }
+    bool is_int8() const { return h.get_dtype() == saber::AK_INT8; }
     const float* data() const { return static_cast<const float*>(h.data()); }
     float* mutable_data() { return static_cast<float*>(h.mutable_data()); }
+    const int8_t* data_q8() const { return static_cast<const int8_t*>(h.data()); }
+    int8_t* mutable_data_q8() { return static_cast<int8_t*>(h.mutable_data()); }
     long long count() const { return h.valid_size(); }
 };
 typedef std::shared_ptr<PBlock> PBlockPtr;
@@ -65,6 +69,7 @@ struct Node {
     saber::DataType bit_type = saber::AK_INVALID;  // NodeProto.bit_type
     int lane = 0;
     bool need_wait = false;
+    std::map<std::string, std::string> share_pairs;  // attr key -> node that owns the shared weight (node.h set_share_pair)
 
     template <typename T>
     bool has_attr(const std::string& k) const {

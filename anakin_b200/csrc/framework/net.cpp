@@ -1,6 +1,8 @@
 // Net / Worker implementation -- see net.h for the reference mapping.
 #include "net.h"
 
+#include <algorithm>
+#include <stdexcept>
 #include <set>
 
 namespace anakin {
@@ -34,7 +36,7 @@ bool op_supports_int8(const std::string& op) {
     // who gets an INT8 kernel at all (ANAKIN_REGISTER_OP_HELPER(..., INT8))
     static const std::set<std::string> s = {
         "Convolution", "ConvRelu", "ConvBatchnorm", "ConvBatchnormScale", "ConvBatchnormScaleRelu", "ConvScale",
-        "ConvScaleRelu", "ConvEltwise", "Dense", "Pooling", "Eltwise", "EltwiseRelu", "Split", "Input"};
+        "ConvScaleRelu", "ConvEltwise", "Dense", "Pooling", "Eltwise", "EltwiseRelu", "Split", "Gather", "Input"};
     return s.count(op) != 0;
 }
 
@@ -62,6 +64,8 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
     _out_names = graph.get_outs();
     const char* env = getenv("B200_ANAKIN_CUDA_GRAPH");
     if (env && env[0] == '0') _use_cuda_graph = false;
+    env = getenv("B200_ANAKIN_SHARE_ACTIVATIONS");
+    if (env && env[0] == '0') _share_activations = false;
 
     // ---- 1. operators, precision per node (net.cpp:230-288, calibrator_factory.h:155-174)
     struct Built {
@@ -146,7 +150,8 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
         _node_tensor[nm] = t.get();
     }
 
-    // ---- 3. shapes, init (weights packed once per op), memory
+    // ---- 3. shapes for every edge, then memory, then init (weights packed once per device, see WeightArena)
+    std::vector<ExecOp> all;
     for (auto& b : built) {
         ExecOp e;
         e.name = b.node->name;
@@ -156,24 +161,84 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
         e.outs.push_back(_node_tensor[b.node->name]);
         Status st = b.op->InferShape(e.ins, e.outs);
         if (!st) return Status::ANAKINFAIL("InferShape(" + e.name + "): " + st.info());
-        if (!b.op->is_alias()) {
-            if (e.outs[0]->storage_bytes())
-                CUDA_CHECK(cudaMemsetAsync(e.outs[0]->mutable_data(), 0, e.outs[0]->storage_bytes(), _stream));
-            st = b.op->Init(_ctx, e.ins, e.outs);
-            if (!st) return Status::ANAKINFAIL("Init(" + e.name + "): " + st.info());
-            _exec.push_back(e);
-        }
+        all.push_back(e);
     }
-    _act_bytes = 0;
-    for (auto& kv : _owned) _act_bytes += kv.second->storage_bytes();
+    plan_activation_memory(all);
+    for (auto& kv : _owned)
+        if (kv.second->storage_bytes())
+            CUDA_CHECK(cudaMemsetAsync(kv.second->mutable_data(), 0, kv.second->storage_bytes(), _stream));
+    for (auto& e : all) {
+        if (e.op->is_alias()) continue;
+        Status st = e.op->Init(_ctx, e.ins, e.outs);
+        if (!st) return Status::ANAKINFAIL("Init(" + e.name + "): " + st.info());
+        _exec.push_back(e);
+    }
+    // weight uploads and the zero fills above used synchronous copies / this stream: nothing is pending after this
     CUDA_CHECK(cudaStreamSynchronize(_stream));
+    CUDA_CHECK(cudaDeviceSynchronize());
     return Status::OK();
 }
 
+// Activation memory (the reference's MemoryScheduler pass + Net::init_memory, framework/graph/llvm/optimizer/
+// memory_scheduler.cpp, framework/core/net/net.cpp:812-898): an edge tensor is live from the op that writes it to
+// the last op that reads it (through alias nodes); tensors whose live ranges do not overlap share one buffer.
+// Greedy best-fit over the execution order. Kept out of the pool: graph inputs / outputs (the user reads and
+// writes them between predictions) and tensors with channel padding (their never-written padding must stay 0).
+void NetCore::plan_activation_memory(const std::vector<ExecOp>& all) {
+    _act_bytes = 0;
+    _act_bytes_unshared = 0;
+    for (auto& kv : _owned) _act_bytes_unshared += kv.second->storage_bytes();
+    if (!_share_activations) { _act_bytes = _act_bytes_unshared; return; }
+    std::map<DTensor*, int> def, last;
+    std::vector<const ExecOp*> run;
+    for (auto& e : all) if (!e.op->is_alias()) run.push_back(&e);
+    for (size_t i = 0; i < run.size(); ++i) {
+        for (DTensor* t : run[i]->outs) if (!def.count(t)) def[t] = static_cast<int>(i);
+        for (DTensor* t : run[i]->ins) last[t] = static_cast<int>(i);
+    }
+    std::set<DTensor*> pinned;
+    for (auto& n : _in_names) pinned.insert(_node_tensor[n]);
+    for (auto& n : _out_names) pinned.insert(_node_tensor[n]);
+    struct Slot { size_t bytes = 0; int free_at = -1; std::vector<DTensor*> users; };
+    std::vector<Slot> slots;
+    std::vector<std::pair<int, DTensor*>> order;
+    for (auto& kv : _owned) {
+        DTensor* t = kv.second.get();
+        if (pinned.count(t) || !def.count(t) || t->storage_bytes() == 0 ||
+            (t->get_layout() == Layout_NHWC && t->channel_stored() != t->channel())) {
+            _act_bytes += t->storage_bytes();
+            continue;
+        }
+        order.push_back({def[t], t});
+    }
+    std::sort(order.begin(), order.end());
+    for (auto& od : order) {
+        DTensor* t = od.second;
+        const int d0 = od.first;
+        const int l0 = std::max(last.count(t) ? last[t] : d0, d0);
+        const size_t need = t->storage_bytes();
+        int best = -1;
+        for (size_t i = 0; i < slots.size(); ++i) {
+            if (slots[i].free_at >= d0) continue;   // still read by the op that defines t (or later)
+            if (best < 0) { best = static_cast<int>(i); continue; }
+            const bool fit_i = slots[i].bytes >= need, fit_b = slots[best].bytes >= need;
+            if (fit_i && (!fit_b || slots[i].bytes < slots[best].bytes)) best = static_cast<int>(i);
+            else if (!fit_i && !fit_b && slots[i].bytes > slots[best].bytes) best = static_cast<int>(i);
+        }
+        if (best < 0) { slots.emplace_back(); best = static_cast<int>(slots.size()) - 1; }
+        slots[best].bytes = std::max(slots[best].bytes, need);
+        slots[best].free_at = l0;
+        slots[best].users.push_back(t);
+    }
+    for (auto& sl : slots) {
+        DTensor backing;
+        backing.re_alloc(Shape({1, 1, 1, static_cast<int>((sl.bytes + 15) / 16 * 4)}, Layout_NCHW), AK_FLOAT);
+        for (DTensor* t : sl.users) t->share_from(backing);
+        _act_bytes += sl.bytes;
+    }
+}
+
 void NetCore::run_eager() {
-    // experimental tile-level hand-over between conv layers (off unless the library was built with it and
-    // B200_SABER_DATAFLOW=1): zero this stream's completion counters at the top of the step
-    b200_dataflow_begin_step(_stream);
     for (auto& e : _exec) (*e.op)(_ctx, e.ins, e.outs);
 }
 
@@ -231,6 +296,13 @@ std::vector<float> NetCore::profile_ops(int iters, int reps) {
     return ms;
 }
 
+std::vector<const void*> NetCore::weight_device_ptrs() const {
+    std::vector<const void*> v;
+    for (auto& e : _exec)
+        if (const void* p = e.op->weight_device_ptr()) v.push_back(p);
+    return v;
+}
+
 void NetCore::sync() { CUDA_CHECK(cudaStreamSynchronize(_stream)); }
 
 NetCore::DTensor* NetCore::get_in(const std::string& in_name) { return get_tensor_from_node(in_name); }
@@ -285,6 +357,7 @@ void WorkerCore::thread_main(int tid) {
             w->_ready_cv.notify_all();
         }
     };
+    bool init_failed = false;
     {
         ReadyMark mark{this};
         // first thread loads + optimises the graph, every thread builds its own Net (worker.cpp:13-39)
@@ -296,13 +369,34 @@ void WorkerCore::thread_main(int tid) {
                 for (auto& kv : _reshape) g->Reshape(kv.first, kv.second);
                 st = g->Optimize();
             }
-            if (!st) { _init_errors.push_back(st.info()); return; }
-            _graph = g;
+            if (!st) { _init_errors.push_back(st.info()); init_failed = true; }
+            else _graph = g;
         }
-        Status st = net.init(*_graph, _precision, device);
-        if (!st) { _init_errors.push_back(st.info()); return; }
-        if (_inputs.empty()) _inputs = net.get_in_names();
-        if (_outputs.empty()) _outputs = net.get_out_names();
+        if (!init_failed) {
+            Status st = net.init(*_graph, _precision, device);
+            if (!st) { _init_errors.push_back(st.info()); init_failed = true; }
+        }
+        if (!init_failed) {
+            if (_inputs.empty()) _inputs = net.get_in_names();
+            if (_outputs.empty()) _outputs = net.get_out_names();
+        }
+    }
+    if (init_failed) {
+        // a thread without a Net still drains the queue, completing every request with the init error: callers
+        // blocked in sync_prediction().get() / async_get_result() return instead of waiting forever
+        std::string why;
+        { std::lock_guard<std::mutex> lk(_graph_mu); why = _init_errors.empty() ? "Net init failed" : _init_errors.front(); }
+        while (true) {
+            std::shared_ptr<Task> task;
+            {
+                std::unique_lock<std::mutex> lk(_mu);
+                _cv.wait(lk, [this] { return _stop || !_tasks.empty(); });
+                if (_stop && _tasks.empty()) return;
+                task = _tasks.front();
+                _tasks.pop_front();
+            }
+            task->done.set_exception(std::make_exception_ptr(std::runtime_error("Worker: " + why)));
+        }
     }
     while (true) {
         std::shared_ptr<Task> task;

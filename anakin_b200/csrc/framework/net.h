@@ -53,7 +53,14 @@ public:
     Precision precision() const { return _precision; }
     void set_use_cuda_graph(bool v);
     bool cuda_graph_active() const { return _graph_exec != nullptr; }
+    // device bytes held by edge tensors after buffer sharing / what one buffer per edge would take
     size_t activation_bytes() const { return _act_bytes; }
+    size_t activation_bytes_unshared() const { return _act_bytes_unshared; }
+    // false: every edge keeps its own buffer, so intermediate tensors stay readable after prediction()
+    // (parity tests); default true, or B200_ANAKIN_SHARE_ACTIVATIONS=0. Call before init().
+    void set_share_activations(bool v) { _share_activations = v; }
+    // device pointers of the packed weights of every launched op that has some (arena sharing is visible here)
+    std::vector<const void*> weight_device_ptrs() const;
     // Per-op device time (ms), averaged over `iters` eager runs with a CUDA-event pair around every
     // op on the compute stream (the reference's -DENABLE_OP_TIMER, net.cpp:445-449,494-506).
     // reps > 1: each op is launched `reps` times back to back inside its event pair, which hides the
@@ -68,6 +75,7 @@ private:
     };
     void run_eager();
     void drop_cuda_graph();
+    void plan_activation_memory(const std::vector<ExecOp>& all);
 
     Precision _precision = Precision::FP32;
     int _device = 0;
@@ -81,7 +89,8 @@ private:
     int _eager_runs = 0;
     cudaGraph_t _graph = nullptr;
     cudaGraphExec_t _graph_exec = nullptr;
-    size_t _act_bytes = 0;
+    size_t _act_bytes = 0, _act_bytes_unshared = 0;
+    bool _share_activations = true;
 };
 
 template <typename Ttype, Precision Ptype, OpRunType RunType = OpRunType::ASYNC>

@@ -5,6 +5,7 @@
 //             conv_relu_pool,conv_eltwise,eltwise_relu}.cpp
 #include "operators.h"
 
+#include <map>
 #include <mutex>
 
 namespace anakin {
@@ -28,8 +29,10 @@ namespace {
 
 PBlockPtr clone_block(const PBlockPtr& src) {
     PBlockPtr b = std::make_shared<PBlock>();
-    b->h.re_alloc(src->h.valid_shape(), AK_FLOAT);
-    memcpy(b->h.mutable_data(), src->h.data(), static_cast<size_t>(src->h.valid_size()) * sizeof(float));
+    const DataType dt = src->is_int8() ? AK_INT8 : AK_FLOAT;
+    b->h.re_alloc(src->h.valid_shape(), dt);
+    memcpy(b->h.mutable_data(), src->h.data(),
+           static_cast<size_t>(src->h.valid_size()) * (dt == AK_INT8 ? 1 : sizeof(float)));
     b->h.set_scale(src->h.get_scale());
     return b;
 }
@@ -70,6 +73,48 @@ void fold_bn_scale(PBlock& w, PBlock& bias, int n, float bn_scale_factor, float 
         bp[i] += beta;
     }
 }
+
+// WeightsFusion<char>::update_weights, framework/utils/parameter_fusion.cpp:406-456: quantised weights keep their
+// codes; the per-output-channel weight scale absorbs alpha (a negative alpha flips the channel's codes), the bias
+// is updated as in the float case.
+void fold_bn_scale_q8(PBlock& w, PBlock& bias, int n, float bn_scale_factor, float eps, const std::vector<float>& mean,
+                      const std::vector<float>& var, const std::vector<float>& scale_w, const std::vector<float>& scale_b,
+                      bool scale_bias_term) {
+    int8_t* wp = w.mutable_data_q8();
+    float* bp = bias.mutable_data();
+    std::vector<float> w_scale = w.h.get_scale();
+    if (static_cast<int>(w_scale.size()) < n) w_scale.resize(n, w_scale.empty() ? 1.f : w_scale.back());
+    const long long chw = w.count() / n;
+    bn_scale_factor = (bn_scale_factor == 0) ? 1.f : 1.f / bn_scale_factor;
+    for (int i = 0; i < n; ++i) {
+        float alpha = var[i] * bn_scale_factor + eps;
+        alpha = 1.f / sqrtf(alpha);
+        float beta = -1.f * (mean[i] * bn_scale_factor);
+        beta = beta * alpha;
+        alpha = scale_w[i] * alpha;
+        if (scale_bias_term) beta = beta * scale_w[i] + scale_b[i];
+        else beta = beta * scale_w[i];
+        w_scale[i] *= alpha;
+        if (w_scale[i] < 0) {
+            w_scale[i] = fabsf(w_scale[i]);
+            for (long long j = 0; j < chw; ++j) wp[i * chw + j] = static_cast<int8_t>(-wp[i * chw + j]);
+        }
+        bp[i] *= alpha;
+        bp[i] += beta;
+    }
+    w.h.set_scale(w_scale);
+}
+
+// Folded weight / bias blocks are a function of the graph node alone: every Net built from one Graph (the
+// per-thread Nets of a Worker, worker.cpp:10-53) shares them, and through them the packed device image
+// (saber_funcs.cpp WeightArena) -- the role of the reference's process-wide GraphGlobalMem
+// (framework/graph/graph_global_mem.h:78-250). Entries die with their last Net.
+struct FoldedBlocks {
+    PBlockPtr w, b;
+    bool folded = false;   // BatchNorm / Scale already applied (by the first Net that used the node)
+};
+std::mutex g_fold_mu;
+std::map<std::pair<const PBlock*, std::string>, std::weak_ptr<FoldedBlocks>> g_fold_cache;
 
 PoolingParam<NV> parse_pooling(const Node& n, const std::string& pre) {
     auto pool_size = n.get_attr<PTuple<int>>(pre + "pool_size");
@@ -139,12 +184,22 @@ public:
         auto weights = GET_PARAMETER(PBlockPtr, weight_1);
         if (weights->h.num() != filter_num) return Status::ANAKINFAIL("weight_1 shape does not match filter_num");
 
-        // folded copies owned by the op: the graph's blocks stay pristine, so several Nets
-        // (Worker threads, multi-GPU replicas) can be built from one Graph
-        _w = clone_block(weights);
-        _b = bias_term ? clone_block(GET_PARAMETER(PBlockPtr, weight_2)) : zero_block(filter_num);
+        // folded copies, one per graph node: the graph's blocks stay pristine, and every Net built from this
+        // Graph (Worker threads, multi-GPU replicas) shares the same folded host blocks
         _has_bias = bias_term || has_bn || has_scale;
-        if (has_bn || has_scale) {
+        std::lock_guard<std::mutex> fold_lock(g_fold_mu);
+        const auto fold_key = std::make_pair(static_cast<const PBlock*>(weights.get()), n.name);
+        if (auto hit = g_fold_cache[fold_key].lock()) {
+            _folded = hit;
+        } else {
+            _folded = std::make_shared<FoldedBlocks>();
+            _folded->w = clone_block(weights);
+            _folded->b = bias_term ? clone_block(GET_PARAMETER(PBlockPtr, weight_2)) : zero_block(filter_num);
+            g_fold_cache[fold_key] = _folded;
+        }
+        _w = _folded->w;
+        _b = _folded->b;
+        if ((has_bn || has_scale) && !_folded_done()) {
             std::vector<float> mean(filter_num, 0.f), var(filter_num, 1.f), gamma(filter_num, 1.f), beta_s(filter_num, 0.f);
             float factor = 1.f, eps = 0.f;
             bool scale_bias = false;
@@ -165,8 +220,10 @@ public:
             if (static_cast<int>(mean.size()) < filter_num || static_cast<int>(var.size()) < filter_num ||
                 static_cast<int>(gamma.size()) < filter_num)
                 return Status::ANAKINFAIL("batchnorm/scale parameter size mismatch in " + n.name);
-            fold_bn_scale(*_w, *_b, filter_num, factor, eps, mean, var, gamma, beta_s, scale_bias);
+            if (_w->is_int8()) fold_bn_scale_q8(*_w, *_b, filter_num, factor, eps, mean, var, gamma, beta_s, scale_bias);
+            else fold_bn_scale(*_w, *_b, filter_num, factor, eps, mean, var, gamma, beta_s, scale_bias);
         }
+        _folded->folded = true;
         ActivationParam<NV> act;
         if (has_relu) act = ActivationParam<NV>(Active_relu, n.get_attr_or<float>("relu_0_alpha", 0.f));
         _relu_out = has_relu;
@@ -222,9 +279,16 @@ public:
         else SABER_CHECK(_f_conv(ins, o, _conv, ctx));
     }
     int output_signedness() const override { return _relu_out ? 1 : 0; }
+    const void* weight_device_ptr() const override {
+        if (_is_eltwise) return const_cast<saber::ConvEltwise<NV, D>&>(_f_elt).impl().engine().weight_device_ptr();
+        if (_has_pool) return const_cast<saber::ConvPooling<NV, D>&>(_f_pool).impl().engine().weight_device_ptr();
+        return const_cast<saber::Conv<NV, D>&>(_f_conv).impl().engine().weight_device_ptr();
+    }
 
 private:
+    bool _folded_done() const { return _folded && _folded->folded; }
     bool _is_eltwise = false, _has_pool = false, _has_bias = false, _relu_out = false;
+    std::shared_ptr<FoldedBlocks> _folded;
     PBlockPtr _w, _b;
     ConvParam<NV> _conv;
     EltwiseParam<NV> _elt;
@@ -260,6 +324,9 @@ public:
     void operator()(OpContext<NV>& ctx, const TensorVec& ins, TensorVec& outs) override {
         TensorVec o = outs;
         SABER_CHECK(_f(ins, o, _param, ctx));
+    }
+    const void* weight_device_ptr() const override {
+        return const_cast<saber::Fc<NV, D>&>(_f).impl().engine().weight_device_ptr();
     }
 
 private:
@@ -403,6 +470,7 @@ void register_all_operators() {
             f->Register("Input", make<InputOp>);
             f->Register("Output", make<AliasOp>);
             f->Register("Split", make<AliasOp>);
+            f->Register("Gather", make<AliasOp>);   // framework/operators/gather.cpp: launches nothing
             f->Register("Pooling", make<PoolingOp>);
             f->Register("Eltwise", make<EltwiseOp>);
             f->Register("EltwiseRelu", make<EltwiseOp>);

@@ -37,6 +37,9 @@ public:
     virtual int output_signedness() const { return 0; }
     // true when the op launches nothing and its outputs alias its first input
     virtual bool is_alias() const { return false; }
+    // device address of the op's packed weights (null for weightless ops); Nets built from one Graph on one
+    // device report the same address (WeightArena)
+    virtual const void* weight_device_ptr() const { return nullptr; }
     const graph::NodePtr& node() const { return _node; }
 
 protected:

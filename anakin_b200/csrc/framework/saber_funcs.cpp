@@ -9,8 +9,41 @@
 
 #include <cuda_fp16.h>
 
+#include <map>
+#include <mutex>
+
 namespace anakin {
 namespace saber {
+
+// ---------------------------------------------------------------------------------------------------------
+// WeightArena: one packed device image per (device, host weight block, packing signature), shared by every
+// ConvEngine that asks for it -- the per-thread Nets of a Worker all point at the same device weights, as the
+// reference's Nets share the PBlocks of the process-wide GraphGlobalMem (framework/graph/graph_global_mem.h:78-250,
+// framework/core/net/worker.cpp:10-53). Entries are reference counted and freed with their last user.
+struct DevWeights {
+    DeviceBuffer w, bias, scale;
+};
+namespace {
+std::mutex g_arena_mu;
+std::map<std::string, std::weak_ptr<DevWeights>> g_arena;
+size_t g_arena_hits = 0, g_arena_misses = 0;
+
+template <typename T>
+void key_add(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+}  // namespace
+
+size_t weight_arena_stats(size_t* entries, size_t* hits, size_t* misses) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    size_t bytes = 0, n = 0;
+    for (auto it = g_arena.begin(); it != g_arena.end();) {
+        if (auto p = it->second.lock()) { bytes += p->w.bytes + p->bias.bytes + p->scale.bytes; ++n; ++it; }
+        else it = g_arena.erase(it);
+    }
+    if (entries) *entries = n;
+    if (hits) *hits = g_arena_hits;
+    if (misses) *misses = g_arena_misses;
+    return bytes;
+}
 
 struct ConvEngine::Impl {
     Spec spec;
@@ -24,7 +57,7 @@ struct ConvEngine::Impl {
 
     b200_conv_desc_t desc;
     b200_conv_plan_t* plan = nullptr;
-    DeviceBuffer w_dev, bias_dev, scale_dev;
+    std::shared_ptr<DevWeights> dw;   // packed weights / bias / scale tables, shared through the WeightArena
     bool need_in_transform = false;
     bool stem = false;       // input transform = stem pack (R x S conv over RGB -> R x 1 conv over X2)
     int stem_taps = 0;
@@ -40,6 +73,7 @@ struct ConvEngine::Impl {
 };
 
 ConvEngine::ConvEngine() : _p(new Impl()) {}
+const void* ConvEngine::weight_device_ptr() const { return _p->dw ? _p->dw->w.ptr : nullptr; }
 ConvEngine::~ConvEngine() { delete _p; }
 
 b200_pool_desc_t make_pool_desc(const Tensor<NV>& in, const PoolingParam<NV>& p) {
@@ -65,7 +99,6 @@ static SaberStatus upload(DeviceBuffer& buf, const void* src, size_t bytes) {
 SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Tensor<NV>* residual,
                                 Tensor<NV>& out, Context<NV>& ctx) {
     Impl& P = *_p;
-    (void)ctx;
     const float res_scale = spec.residual_scale;
     const DataType res_dt = residual ? residual->get_dtype() : AK_INVALID;
     if (P.ready && P.in_shape == in.valid_shape() && P.out_shape == out.valid_shape() &&
@@ -109,7 +142,7 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
             s = Shape({in.num(), P.stem_taps * 4, in.height() + 2 * spec.pad_h, wo}, Layout_NHWC);
         }
         if (P.in_scratch.re_alloc(s, sdt) != SaberSuccess) return SaberOutOfMem;
-        CUDA_CHECK(cudaMemset(P.in_scratch.mutable_data(), 0, P.in_scratch.storage_bytes()));
+        CUDA_CHECK(cudaMemsetAsync(P.in_scratch.mutable_data(), 0, P.in_scratch.storage_bytes(), ctx.get_compute_stream()));
         if (op == AK_INT8) {
             if (in.get_scale().empty()) return SaberInvalidValue;
             P.in_inv_scale = 1.f / in.get_scale()[0];
@@ -176,7 +209,7 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         Shape s({d.n, spec.k, conv_out_size(d.h, d.pad_h, d.dil_h, d.r, d.stride_h),
                  conv_out_size(d.w, d.pad_w, d.dil_w, d.s, d.stride_w)}, Layout_NHWC);
         if (P.conv_out_scratch.re_alloc(s, out.get_dtype()) != SaberSuccess) return SaberOutOfMem;
-        CUDA_CHECK(cudaMemset(P.conv_out_scratch.mutable_data(), 0, P.conv_out_scratch.storage_bytes()));
+        CUDA_CHECK(cudaMemsetAsync(P.conv_out_scratch.mutable_data(), 0, P.conv_out_scratch.storage_bytes(), ctx.get_compute_stream()));
         P.conv_out_scratch.set_scale(out.get_scale());
         cout = &P.conv_out_scratch;
         P.pool_desc = make_pool_desc(P.conv_out_scratch, spec.pool);
@@ -185,118 +218,170 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
     d.ldc = cout->channel_stored();
     if (residual && residual->channel_stored() != d.ldc) return SaberInvalidValue;
 
-    // ---- 4. weights, bias, scales
-    const float* w = static_cast<const float*>(spec.weights->data());
+    // ---- 4. weights, bias, scales: looked up in / built into the WeightArena
+    const bool wq8 = spec.weights->get_dtype() == AK_INT8;   // model file carries int8 codes + per-channel scales
+    const float* w = wq8 ? nullptr : static_cast<const float*>(spec.weights->data());
+    const int8_t* wq = wq8 ? static_cast<const int8_t*>(spec.weights->data()) : nullptr;
+    const std::vector<float>& wq_scale = spec.weights->get_scale();
+    if (wq8 && wq_scale.empty()) return SaberInvalidValue;
+    auto wq_scale_of = [&](int oc) { return wq_scale[static_cast<size_t>(oc) < wq_scale.size() ? oc : wq_scale.size() - 1]; };
     const size_t per_k = static_cast<size_t>(spec.is_fc ? spec.c_per_group : spec.c_per_group * spec.r * spec.s);
     const bool has_bias = spec.bias && spec.bias->valid_size() >= spec.k && spec.bias->data();
     const float* b = has_bias ? static_cast<const float*>(spec.bias->data()) : nullptr;
-    std::vector<float> bias_f(spec.k, 0.f), scale_f;
-
-    if (P.depthwise) {
-        if (op == AK_INT8) return SaberUnImplError;
-        // weights [c][1][r][s] -> [r][s][c_stored]
-        const int RS = spec.r * spec.s;
-        if (op == AK_HALF) {
-            std::vector<__half> ww(static_cast<size_t>(RS) * cs, __float2half(0.f));
-            for (int c = 0; c < spec.k; ++c)
-                for (int i = 0; i < RS; ++i) ww[static_cast<size_t>(i) * cs + c] = __float2half(w[c * RS + i]);
-            if (upload(P.w_dev, ww.data(), ww.size() * sizeof(__half)) != SaberSuccess) return SaberOutOfMem;
-        } else {
-            std::vector<float> ww(static_cast<size_t>(RS) * cs, 0.f);
-            for (int c = 0; c < spec.k; ++c)
-                for (int i = 0; i < RS; ++i) ww[static_cast<size_t>(i) * cs + c] = w[c * RS + i];
-            if (upload(P.w_dev, ww.data(), ww.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+    const DataType odt = cout->get_dtype();
+    float in_scale = 1.f, out_scale = 1.f;
+    if (op == AK_INT8 && !P.depthwise) {
+        if (cin->get_scale().empty()) return SaberInvalidValue;
+        in_scale = cin->get_scale()[0];
+        if (odt != AK_FLOAT) {
+            if (cout->get_scale().empty()) return SaberInvalidValue;
+            out_scale = cout->get_scale()[0];
         }
-        std::vector<float> bb(cs, 0.f);
-        for (int i = 0; i < spec.k; ++i) bb[i] = b ? b[i] : 0.f;
-        if (upload(P.bias_dev, bb.data(), bb.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
-        d.c = cs; d.k = cs; d.ldc = cout->channel_stored();
-    } else {
-        // operand-typed KCRS image (fc: permuted into the stored-K order), then the tcgen05 pack
-        const int es = op == AK_INT8 ? 1 : (op == AK_HALF ? 2 : 4);
-        const int c_img = spec.is_fc ? d.c : c_real;
-        const int RS = spec.is_fc ? 1 : (stem ? spec.r : spec.r * spec.s);
-        std::vector<uint8_t> img(static_cast<size_t>(spec.k) * c_img * RS * es, 0);
-        std::vector<float> w_scale(spec.k, 1.f);
-        for (int oc = 0; oc < spec.k; ++oc) {
-            const float* wr = w + static_cast<size_t>(oc) * per_k;
-            float sw = 1.f;
-            if (op == AK_INT8) {
-                float mx = 0.f;
-                for (size_t i = 0; i < per_k; ++i) { float a = fabsf(wr[i]); mx = a > mx ? a : mx; }
-                sw = mx / 127.f;
-                if (sw == 0.f) sw = 1.f;
-                w_scale[oc] = sw;
+    }
+    if (P.depthwise) { d.c = cs; d.k = cs; d.ldc = cout->channel_stored(); }
+
+    // everything the device image depends on
+    std::string key;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        key_add(key, dev);
+        key_add(key, spec.weights->data());
+        key_add(key, b);
+        const int32_t sig[] = {math, d.c, d.k, d.r, d.s, static_cast<int32_t>(cin_dt), static_cast<int32_t>(odt), c_real,
+                               spec.is_fc ? 1 : 0, stem ? 1 : 0, P.depthwise ? 1 : 0, spec.c_per_group, spec.r, spec.s};
+        key_add(key, sig);
+        key_add(key, in_scale);
+        key_add(key, out_scale);
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        auto it = g_arena.find(key);
+        if (it != g_arena.end()) P.dw = it->second.lock();
+        else P.dw.reset();
+        if (P.dw) ++g_arena_hits;
+    }
+    if (!P.dw) {
+        std::shared_ptr<DevWeights> dw = std::make_shared<DevWeights>();
+        std::vector<float> bias_f(spec.k, 0.f), scale_f;
+        if (P.depthwise) {
+            if (op == AK_INT8) return SaberUnImplError;
+            // weights [c][1][r][s] -> [r][s][c_stored]
+            const int RS = spec.r * spec.s;
+            auto wv = [&](int c, int i) { return wq8 ? wq[c * RS + i] * wq_scale_of(c) : w[c * RS + i]; };
+            if (op == AK_HALF) {
+                std::vector<__half> ww(static_cast<size_t>(RS) * cs, __float2half(0.f));
+                for (int c = 0; c < spec.k; ++c)
+                    for (int i = 0; i < RS; ++i) ww[static_cast<size_t>(i) * cs + c] = __float2half(wv(c, i));
+                if (upload(dw->w, ww.data(), ww.size() * sizeof(__half)) != SaberSuccess) return SaberOutOfMem;
+            } else {
+                std::vector<float> ww(static_cast<size_t>(RS) * cs, 0.f);
+                for (int c = 0; c < spec.k; ++c)
+                    for (int i = 0; i < RS; ++i) ww[static_cast<size_t>(i) * cs + c] = wv(c, i);
+                if (upload(dw->w, ww.data(), ww.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
             }
-            for (int ci = 0; ci < c_img; ++ci) {
-                for (int rs = 0; rs < RS; ++rs) {
-                    float v;
-                    if (spec.is_fc) {
-                        const int col = col_map[ci];
-                        if (col < 0) continue;
-                        v = wr[col];
-                    } else if (stem) {
-                        // ci = tap*4 + ch, rs = filter row: w[oc][ch][r][tap]
-                        const int tap = ci >> 2, ch = ci & 3;
-                        if (tap >= spec.s || ch >= spec.c_per_group) continue;
-                        v = wr[(static_cast<size_t>(ch) * spec.r + rs) * spec.s + tap];
+            std::vector<float> bb(cs, 0.f);
+            for (int i = 0; i < spec.k; ++i) bb[i] = b ? b[i] : 0.f;
+            if (upload(dw->bias, bb.data(), bb.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+        } else {
+            // operand-typed KCRS image (fc: permuted into the stored-K order), then the tcgen05 pack
+            const int es = op == AK_INT8 ? 1 : (op == AK_HALF ? 2 : 4);
+            const int c_img = spec.is_fc ? d.c : c_real;
+            const int RS = spec.is_fc ? 1 : (stem ? spec.r : spec.r * spec.s);
+            std::vector<uint8_t> img(static_cast<size_t>(spec.k) * c_img * RS * es, 0);
+            std::vector<float> w_scale(spec.k, 1.f);
+            for (int oc = 0; oc < spec.k; ++oc) {
+                const size_t row = static_cast<size_t>(oc) * per_k;
+                float sw = 1.f;
+                if (op == AK_INT8) {
+                    if (wq8) {
+                        sw = wq_scale_of(oc);     // codes are used as stored (model_io.cpp:204-216)
                     } else {
-                        v = wr[static_cast<size_t>(ci) * RS + rs];
+                        float mx = 0.f;
+                        for (size_t i = 0; i < per_k; ++i) { float a = fabsf(w[row + i]); mx = a > mx ? a : mx; }
+                        sw = mx / 127.f;
+                        if (sw == 0.f) sw = 1.f;
                     }
-                    const size_t o = (static_cast<size_t>(oc) * c_img + ci) * RS + rs;
-                    if (op == AK_INT8) reinterpret_cast<int8_t*>(img.data())[o] = static_cast<int8_t>(v / sw);
-                    else if (op == AK_HALF) reinterpret_cast<__half*>(img.data())[o] = __float2half(v);
-                    else reinterpret_cast<float*>(img.data())[o] = v;
+                    w_scale[oc] = sw;
+                }
+                const float deq = wq8 ? wq_scale_of(oc) : 1.f;
+                for (int ci = 0; ci < c_img; ++ci) {
+                    for (int rs = 0; rs < RS; ++rs) {
+                        size_t idx;
+                        if (spec.is_fc) {
+                            const int col = col_map[ci];
+                            if (col < 0) continue;
+                            idx = row + col;
+                        } else if (stem) {
+                            // ci = tap*4 + ch, rs = filter row: w[oc][ch][r][tap]
+                            const int tap = ci >> 2, ch = ci & 3;
+                            if (tap >= spec.s || ch >= spec.c_per_group) continue;
+                            idx = row + (static_cast<size_t>(ch) * spec.r + rs) * spec.s + tap;
+                        } else {
+                            idx = row + static_cast<size_t>(ci) * RS + rs;
+                        }
+                        const size_t o = (static_cast<size_t>(oc) * c_img + ci) * RS + rs;
+                        if (op == AK_INT8) {
+                            reinterpret_cast<int8_t*>(img.data())[o] = wq8 ? wq[idx] : static_cast<int8_t>(w[idx] / sw);
+                        } else {
+                            const float v = wq8 ? wq[idx] * deq : w[idx];
+                            if (op == AK_HALF) reinterpret_cast<__half*>(img.data())[o] = __float2half(v);
+                            else reinterpret_cast<float*>(img.data())[o] = v;
+                        }
+                    }
                 }
             }
-        }
-        const size_t pbytes = b200_conv_packed_weight_bytes(&d);
-        if (pbytes == 0) return SaberInvalidValue;
-        std::vector<uint8_t> packed(pbytes);
-        SaberStatus st = static_cast<SaberStatus>(b200_conv_pack_weights(&d, img.data(), c_img, packed.data()));
-        if (st != SaberSuccess) return st;
-        if (upload(P.w_dev, packed.data(), pbytes) != SaberSuccess) return SaberOutOfMem;
+            const size_t pbytes = b200_conv_packed_weight_bytes(&d);
+            if (pbytes == 0) return SaberInvalidValue;
+            std::vector<uint8_t> packed(pbytes);
+            SaberStatus st = static_cast<SaberStatus>(b200_conv_pack_weights(&d, img.data(), c_img, packed.data()));
+            if (st != SaberSuccess) return st;
+            if (upload(dw->w, packed.data(), pbytes) != SaberSuccess) return SaberOutOfMem;
 
-        if (op == AK_INT8) {
-            if (cin->get_scale().empty()) return SaberInvalidValue;
-            const float in_scale = cin->get_scale()[0];
-            const float u = 127.f / 255.f;
-            const DataType odt = cout->get_dtype();
-            float out_scale = 1.f;
-            if (odt != AK_FLOAT) {
-                if (cout->get_scale().empty()) return SaberInvalidValue;
-                out_scale = cout->get_scale()[0];
+            if (op == AK_INT8) {
+                const float u = 127.f / 255.f;
+                scale_f.assign(spec.k, 1.f);
+                for (int i = 0; i < spec.k; ++i) {
+                    float s;
+                    if (cin_dt == AK_INT8 && odt == AK_INT8) s = (w_scale[i] * in_scale) / out_scale;
+                    else if (cin_dt == AK_UINT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale * u) / (out_scale * u);
+                    else if (cin_dt == AK_UINT8 && odt == AK_INT8) s = (w_scale[i] * in_scale * u) / out_scale;
+                    else if (cin_dt == AK_UINT8 && odt == AK_FLOAT) s = w_scale[i] * in_scale * u;
+                    else if (cin_dt == AK_INT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale) / (out_scale * u);
+                    else s = w_scale[i] * in_scale;
+                    scale_f[i] = s;
+                    const float inv = (cin_dt == AK_UINT8) ? (1.f / (w_scale[i] * in_scale * u))
+                                                           : (1.f / (w_scale[i] * in_scale));
+                    bias_f[i] = b ? b[i] * inv : 0.f;
+                }
+                if (upload(dw->scale, scale_f.data(), scale_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+            } else {
+                for (int i = 0; i < spec.k; ++i) bias_f[i] = b ? b[i] : 0.f;
             }
-            scale_f.assign(spec.k, 1.f);
-            for (int i = 0; i < spec.k; ++i) {
-                float s;
-                if (cin_dt == AK_INT8 && odt == AK_INT8) s = (w_scale[i] * in_scale) / out_scale;
-                else if (cin_dt == AK_UINT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale * u) / (out_scale * u);
-                else if (cin_dt == AK_UINT8 && odt == AK_INT8) s = (w_scale[i] * in_scale * u) / out_scale;
-                else if (cin_dt == AK_UINT8 && odt == AK_FLOAT) s = w_scale[i] * in_scale * u;
-                else if (cin_dt == AK_INT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale) / (out_scale * u);
-                else s = w_scale[i] * in_scale;
-                scale_f[i] = s;
-                const float inv = (cin_dt == AK_UINT8) ? (1.f / (w_scale[i] * in_scale * u))
-                                                       : (1.f / (w_scale[i] * in_scale));
-                bias_f[i] = b ? b[i] * inv : 0.f;
-            }
-            if (residual) {
-                const DataType rdt = residual->get_dtype();
-                if (rdt == AK_INT8 && odt == AK_UINT8) d.sum_scale = res_scale * (255.f / 127.f) / out_scale;
-                else if (rdt == AK_UINT8 && odt == AK_INT8) d.sum_scale = res_scale * (127.f / 255.f) / out_scale;
-                else d.sum_scale = res_scale / out_scale;
-            }
-            if (upload(P.scale_dev, scale_f.data(), scale_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+            if (upload(dw->bias, bias_f.data(), bias_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+        }
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        auto it = g_arena.find(key);
+        std::shared_ptr<DevWeights> other = it != g_arena.end() ? it->second.lock() : nullptr;
+        if (other) {
+            P.dw = other;          // another thread built the same image meanwhile: keep one
         } else {
-            for (int i = 0; i < spec.k; ++i) bias_f[i] = b ? b[i] : 0.f;
-            d.sum_scale = 1.f;  // eltwise coeff 1 (ConvEltwise fuses only Add with coeff {1,1})
+            g_arena[key] = dw;
+            P.dw = dw;
+            ++g_arena_misses;
         }
-        if (upload(P.bias_dev, bias_f.data(), bias_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
-
+    }
+    d.sum_scale = 1.f;  // float: eltwise coeff 1 (ConvEltwise fuses only Add with coeff {1,1})
+    if (op == AK_INT8 && residual) {
+        const DataType rdt = residual->get_dtype();
+        if (rdt == AK_INT8 && odt == AK_UINT8) d.sum_scale = res_scale * (255.f / 127.f) / out_scale;
+        else if (rdt == AK_UINT8 && odt == AK_INT8) d.sum_scale = res_scale * (127.f / 255.f) / out_scale;
+        else d.sum_scale = res_scale / out_scale;
+    }
+    if (!P.depthwise) {
         SaberStatus pst = static_cast<SaberStatus>(b200_conv_plan_create(
-            &d, P.w_dev.ptr, static_cast<const float*>(P.bias_dev.ptr),
-            op == AK_INT8 ? static_cast<const float*>(P.scale_dev.ptr) : nullptr, &P.plan));
+            &d, P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
+            op == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, &P.plan));
         if (pst != SaberSuccess) return pst;
     }
 
@@ -335,8 +420,8 @@ SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Te
     void* dst = P.spec.has_pool ? P.conv_out_scratch.mutable_data() : out.mutable_data();
     SaberStatus st;
     if (P.depthwise) {
-        st = static_cast<SaberStatus>(b200_dwconv_run(&P.desc, src, P.w_dev.ptr,
-                                                      static_cast<const float*>(P.bias_dev.ptr), nullptr, dst, stream));
+        st = static_cast<SaberStatus>(b200_dwconv_run(&P.desc, src, P.dw->w.ptr,
+                                                      static_cast<const float*>(P.dw->bias.ptr), nullptr, dst, stream));
     } else {
         st = static_cast<SaberStatus>(b200_conv_plan_run(P.plan, src, residual ? residual->data() : nullptr, dst, stream));
     }

@@ -40,11 +40,17 @@ public:
     SaberStatus prepare(const Spec& spec, const Tensor<NV>& in, const Tensor<NV>* residual, Tensor<NV>& out,
                         Context<NV>& ctx);
     SaberStatus run(const Tensor<NV>& in, const Tensor<NV>* residual, Tensor<NV>& out, cudaStream_t stream);
+    // device address of the packed weight image this engine runs on (shared between engines through the arena)
+    const void* weight_device_ptr() const;
 
 private:
     struct Impl;
     Impl* _p;
 };
+
+// Live packed-weight images of this process: total device bytes; optionally entry count and how many
+// ConvEngine::prepare calls found their image already built (hits) or had to build it (misses).
+ANAKIN_EXPORT size_t weight_arena_stats(size_t* entries, size_t* hits, size_t* misses);
 
 // ------------------------------------------------------------------------------------- conv
 template <typename T, DataType OpDtype>
@@ -80,6 +86,8 @@ public:
         return s;
     }
 
+    const ConvEngine& engine() const { return _eng; }
+
 private:
     ConvEngine _eng;
 };
@@ -113,6 +121,8 @@ public:
         return _eng.run(*in[0], res, *out[0], this->_ctx->get_compute_stream());
     }
 
+    const ConvEngine& engine() const { return _eng; }
+
 private:
     ConvEngine _eng;
 };
@@ -135,6 +145,8 @@ public:
     SaberStatus dispatch(const TensorVec& in, TensorVec& out, ConvPoolingParam<T>& p) override {
         return _eng.run(*in[0], nullptr, *out[0], this->_ctx->get_compute_stream());
     }
+
+    const ConvEngine& engine() const { return _eng; }
 
 private:
     ConvEngine _eng;
@@ -166,6 +178,8 @@ public:
     SaberStatus dispatch(const TensorVec& in, TensorVec& out, FcParam<T>& p) override {
         return _eng.run(*in[0], nullptr, *out[0], this->_ctx->get_compute_stream());
     }
+
+    const ConvEngine& engine() const { return _eng; }
 
 private:
     ConvEngine _eng;

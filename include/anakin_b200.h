@@ -52,6 +52,11 @@ ANAKIN_API void anakin_graph_destroy(anakin_graph_t* g);
 /* ---- Net (reference framework/core/net/net.h:35-328) */
 /* Net<NV, precision>::init(graph) on `device` (-1 = current). */
 ANAKIN_API int anakin_net_create(anakin_graph_t* g, int precision, int device, anakin_net_t** out);
+/* flags: ANAKIN_NET_KEEP_EDGES = one buffer per edge tensor instead of the MemoryScheduler-style sharing
+ * (framework/graph/llvm/optimizer/memory_scheduler.cpp), so that intermediate tensors stay readable after
+ * prediction() -- parity tests and debugging only. */
+#define ANAKIN_NET_KEEP_EDGES 1
+ANAKIN_API int anakin_net_create_ex(anakin_graph_t* g, int precision, int device, int flags, anakin_net_t** out);
 ANAKIN_API int anakin_net_num_inputs(anakin_net_t* n);
 ANAKIN_API int anakin_net_num_outputs(anakin_net_t* n);
 ANAKIN_API const char* anakin_net_input_name(anakin_net_t* n, int idx);
@@ -75,7 +80,13 @@ ANAKIN_API int anakin_net_launched_ops(anakin_net_t* n);      /* kernels-launchi
 ANAKIN_API int anakin_net_cuda_graph_active(anakin_net_t* n);
 ANAKIN_API int anakin_net_set_cuda_graph(anakin_net_t* n, int enable);
 ANAKIN_API size_t anakin_net_exec_order(anakin_net_t* n, char* buf, size_t cap); /* "name:op\n" per launched op */
-ANAKIN_API size_t anakin_net_activation_bytes(anakin_net_t* n);
+ANAKIN_API size_t anakin_net_activation_bytes(anakin_net_t* n);          /* device bytes of edge tensors, after sharing */
+ANAKIN_API size_t anakin_net_activation_bytes_unshared(anakin_net_t* n); /* one buffer per edge */
+/* device addresses of the packed weights of every launched op that has some; returns their count. Nets built
+ * from one Graph on one device share them (the reference's GraphGlobalMem, graph_global_mem.h:78-250). */
+ANAKIN_API int anakin_net_weight_ptrs(anakin_net_t* n, const void** out, int cap);
+/* live packed-weight images of this process: total device bytes (+ entries, lookups that hit / missed) */
+ANAKIN_API size_t anakin_weight_arena_stats(size_t* entries, size_t* hits, size_t* misses);
 /* Per-op device time in ms (same order as anakin_net_exec_order), mean of `iters` eager runs with a
  * CUDA-event pair around every op -- the reference's ENABLE_OP_TIMER (net.cpp:445-449,494-506).
  * reps > 1 launches each op `reps` times back to back inside its pair (steady-state device time). */

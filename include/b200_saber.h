@@ -162,15 +162,6 @@ B200_API void b200_conv_plan_destroy(b200_conv_plan_t* plan);
 /* Introspection for tests / roofline: tile shape and grid the plan chose. */
 B200_API int b200_conv_plan_info(const b200_conv_plan_t* plan, int32_t* block_n, int32_t* grid_x,
                         int32_t* grid_y, int32_t* k_steps, int32_t* smem_bytes);
-/* Tile-level hand-over between consecutive conv plans of one stream (experimental; compiled in only with
- * -DB200_DATAFLOW and switched on by B200_SABER_DATAFLOW=1 -- the default library returns 0 / does nothing).
- * When active, a caller that runs a sequence of plans per step must call b200_dataflow_begin_step(stream) at the
- * top of every step (it zeroes the per-tile completion counters of that stream), and every activation buffer must
- * be written by exactly one plan per step. Replaces nothing in the reference (its Net is one stream, one op at a
- * time, net.cpp:417-509); see DESIGN.md section 9. */
-B200_API int b200_dataflow_supported(void);
-B200_API int b200_dataflow_begin_step(void* stream);
-
 /* split-K factor of the plan (= cluster size along z; 1 when the k loop is not split), 0 for a null plan. */
 B200_API int b200_conv_plan_split(const b200_conv_plan_t* plan);
 

@@ -221,3 +221,27 @@ def test_cpp_api_example_builds_and_refuses_without_gpu():
             pytest.skip("covered by the gpu test")
         r = subprocess.run([exe, model, "2", "int8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stdout, r.stdout
+
+
+def test_worker_init_failure_fails_requests_instead_of_hanging():
+    """A Worker whose Nets cannot be built (here: no sm_100 GPU) completes every queued request with the init
+    error; sync_prediction / async_get_result must not block forever (net.cpp thread_main)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible: the Nets build")
+    from anakin_b200 import api, modelzoo
+    with tempfile.TemporaryDirectory() as d:
+        model = os.path.join(d, "tiny.anakin.bin")
+        modelzoo.save(modelzoo.build("tiny_resnet", 1, "int8"), model)
+        w = api.Worker(model, "int8", threads=2)
+        x = np.zeros((1, 3, 32, 32), np.float32)
+        for _ in range(3):   # without wait_ready(): requests race the failing init
+            with pytest.raises(api.AnakinError, match="no CPU fallback"):
+                w.sync_prediction(x, 10)
+        with pytest.raises(api.AnakinError, match="no CPU fallback"):
+            w.wait_ready()
+        out = np.zeros(10, np.float32)
+        w.async_prediction_ptr(x.ctypes.data, x.size, out.ctypes.data, out.size)
+        with pytest.raises(api.AnakinError, match="no CPU fallback"):
+            w.async_get_result()
+        del w

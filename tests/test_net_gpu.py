@@ -26,9 +26,10 @@ def _build(name, batch, precision):
     return g, G
 
 
-def _run(G, precision, x, graph=True):
+def _run(G, precision, x, graph=True, keep_edges=True):
+    """keep_edges: one buffer per edge, so that intermediate tensors can be read back after prediction()."""
     from anakin_b200 import api
-    net = api.Net(G, precision)
+    net = api.Net(G, precision, keep_edges=keep_edges)
     if not graph:
         net.set_cuda_graph(False)
     net.set_input("input_0", x)
@@ -310,3 +311,38 @@ def test_worker_async_prediction_pipelined_matches_single_net():
             np.testing.assert_array_equal(got, want[i])
         assert any((want[0] != want[i]).any() for i in range(1, nreq)), "inputs must differ for the order check"
         del w
+
+
+def test_activation_sharing_and_weight_arena():
+    """MemoryScheduler-style edge buffer sharing (memory_scheduler.cpp, net.cpp:812-898) must not change results and
+    must shrink the footprint; two Nets of one Graph on one device share every packed weight image
+    (graph_global_mem.h:78-250, worker.cpp:10-53)."""
+    from anakin_b200 import api, modelzoo
+    batch = 2
+    gold = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
+    g, G = _build("resnet50", batch, "int8")
+    x = modelzoo.synthetic_input(batch)
+    b0, e0, h0, m0 = api.weight_arena_stats()
+    keep = _run(G, "int8", x, keep_edges=True)
+    b1, e1, h1, m1 = api.weight_arena_stats()
+    shared = _run(G, "int8", x, keep_edges=False)
+    b2, e2, h2, m2 = api.weight_arena_stats()
+    # same answers with shared buffers, over graph replays too
+    want = keep.get_output()
+    np.testing.assert_array_equal(shared.get_output(), want)
+    shared.prediction(); shared.prediction(); shared.sync()
+    np.testing.assert_array_equal(shared.get_output(), want)
+    assert (want.argmax(1) == gold["top1_int8"][:batch]).all()
+    # footprint: >= 4x smaller than one buffer per edge
+    assert shared.activation_bytes_unshared() == keep.activation_bytes()
+    assert shared.activation_bytes() * 4 <= shared.activation_bytes_unshared(), (
+        shared.activation_bytes(), shared.activation_bytes_unshared())
+    # weights: the second Net built nothing new and points at the first Net's device images
+    n_w = len(keep.weight_ptrs())
+    assert n_w >= 54 and m1 - m0 == n_w and e1 - e0 == n_w
+    assert m2 == m1 and e2 == e1 and b2 == b1 and h2 - h1 == n_w
+    assert keep.weight_ptrs() == shared.weight_ptrs() and all(keep.weight_ptrs())
+    del keep, shared
+    import gc
+    gc.collect()
+    assert api.weight_arena_stats()[1] == e0      # images are freed with their last Net
