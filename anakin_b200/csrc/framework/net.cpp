@@ -17,6 +17,9 @@ NetCore::~NetCore() {
     drop_cuda_graph();
     _exec.clear();
     _owned.clear();
+    if (_fork_ev) cudaEventDestroy(_fork_ev);
+    if (_join_ev) cudaEventDestroy(_join_ev);
+    if (_side_stream) cudaStreamDestroy(_side_stream);
     if (_stream) cudaStreamDestroy(_stream);
 }
 
@@ -57,7 +60,13 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
     }
     _precision = precision;
     if (!_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking));
+    if (!_side_stream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&_side_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&_fork_ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&_join_ev, cudaEventDisableTiming));
+    }
     _ctx = Context<NV>(_device, _stream);
+    _side_ctx = Context<NV>(_device, _side_stream);
     drop_cuda_graph();
     _exec.clear(); _owned.clear(); _node_tensor.clear(); _eager_runs = 0;
     _in_names = graph.get_ins();
@@ -163,13 +172,14 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
         if (!st) return Status::ANAKINFAIL("InferShape(" + e.name + "): " + st.info());
         all.push_back(e);
     }
+    plan_side_ops(all);
     plan_activation_memory(all);
     for (auto& kv : _owned)
         if (kv.second->storage_bytes())
             CUDA_CHECK(cudaMemsetAsync(kv.second->mutable_data(), 0, kv.second->storage_bytes(), _stream));
     for (auto& e : all) {
         if (e.op->is_alias()) continue;
-        Status st = e.op->Init(_ctx, e.ins, e.outs);
+        Status st = e.op->Init(e.side_join >= 0 ? _side_ctx : _ctx, e.ins, e.outs);
         if (!st) return Status::ANAKINFAIL("Init(" + e.name + "): " + st.info());
         _exec.push_back(e);
     }
@@ -177,6 +187,34 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
     CUDA_CHECK(cudaStreamSynchronize(_stream));
     CUDA_CHECK(cudaDeviceSynchronize());
     return Status::OK();
+}
+
+// Off-chain ops (the reference's ParallScheduler gives such nodes their own lane / stream,
+// framework/graph/llvm/scheduler.cpp + net.cpp:430-444,480-492): an op whose result is not read by the op that
+// follows it -- the projection shortcut `resXa_branch1`, read only by `branch2c` three ops later -- runs on a second
+// stream, forked after the ops before it and joined in front of its first reader. Inside the captured CUDA graph
+// this is a parallel branch, so the shortcut convolution leaves the critical path of the request.
+void NetCore::plan_side_ops(std::vector<ExecOp>& all) {
+    const char* env = getenv("B200_ANAKIN_SIDE_STREAM");
+    if (env && env[0] == '0') return;
+    std::vector<ExecOp*> run;
+    for (auto& e : all) if (!e.op->is_alias()) run.push_back(&e);
+    std::set<DTensor*> outs;
+    for (auto& n : _out_names) outs.insert(_node_tensor[n]);
+    int busy_until = -1;   // one side stream: do not stack side ops
+    for (size_t i = 0; i + 2 < run.size(); ++i) {
+        ExecOp& e = *run[i];
+        if (static_cast<int>(i) <= busy_until || e.outs.size() != 1 || outs.count(e.outs[0])) continue;
+        if (e.op_name.compare(0, 4, "Conv") != 0) continue;
+        int first_reader = -1;
+        for (size_t j = i + 1; j < run.size() && first_reader < 0; ++j)
+            for (DTensor* t : run[j]->ins) if (t == e.outs[0]) first_reader = static_cast<int>(j);
+        if (first_reader <= static_cast<int>(i) + 1) continue;
+        // nothing in between may touch the tensors this op writes or reads-and-shares (in-place ops do not exist here)
+        e.side_join = first_reader;
+        run[first_reader]->wait_side = true;
+        busy_until = first_reader;
+    }
 }
 
 // Activation memory (the reference's MemoryScheduler pass + Net::init_memory, framework/graph/llvm/optimizer/
@@ -194,7 +232,9 @@ void NetCore::plan_activation_memory(const std::vector<ExecOp>& all) {
     for (auto& e : all) if (!e.op->is_alias()) run.push_back(&e);
     for (size_t i = 0; i < run.size(); ++i) {
         for (DTensor* t : run[i]->outs) if (!def.count(t)) def[t] = static_cast<int>(i);
-        for (DTensor* t : run[i]->ins) last[t] = static_cast<int>(i);
+        // a side-stream op may still be reading its inputs until the op that joins it
+        const int until = run[i]->side_join >= 0 ? std::max(run[i]->side_join, static_cast<int>(i)) : static_cast<int>(i);
+        for (DTensor* t : run[i]->ins) last[t] = std::max(last.count(t) ? last[t] : 0, until);
     }
     std::set<DTensor*> pinned;
     for (auto& n : _in_names) pinned.insert(_node_tensor[n]);
@@ -239,7 +279,19 @@ void NetCore::plan_activation_memory(const std::vector<ExecOp>& all) {
 }
 
 void NetCore::run_eager() {
-    for (auto& e : _exec) (*e.op)(_ctx, e.ins, e.outs);
+    size_t ev = 0;
+    for (auto& e : _exec) {
+        if (e.wait_side) CUDA_CHECK(cudaStreamWaitEvent(_stream, _join_ev, 0));
+        if (e.side_join >= 0) {
+            (void)ev;
+            CUDA_CHECK(cudaEventRecord(_fork_ev, _stream));
+            CUDA_CHECK(cudaStreamWaitEvent(_side_stream, _fork_ev, 0));
+            (*e.op)(_side_ctx, e.ins, e.outs);
+            CUDA_CHECK(cudaEventRecord(_join_ev, _side_stream));
+        } else {
+            (*e.op)(_ctx, e.ins, e.outs);
+        }
+    }
 }
 
 void NetCore::prediction() {
@@ -281,7 +333,7 @@ std::vector<float> NetCore::profile_ops(int iters, int reps) {
     for (int it = 0; it < iters + 1; ++it) {  // first pass is a warm-up
         for (size_t i = 0; i < n; ++i) {
             CUDA_CHECK(cudaEventRecord(ev[2 * i], _stream));
-            for (int r = 0; r < reps; ++r) (*_exec[i].op)(_ctx, _exec[i].ins, _exec[i].outs);
+            for (int r = 0; r < reps; ++r) (*_exec[i].op)(_ctx, _exec[i].ins, _exec[i].outs);   // all on one stream here
             CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], _stream));
         }
         CUDA_CHECK(cudaStreamSynchronize(_stream));

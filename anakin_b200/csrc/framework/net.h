@@ -72,15 +72,19 @@ private:
         std::string name, op_name;
         ops::OperatorPtr op;
         std::vector<DTensor*> ins, outs;
+        int side_join = -1;       // >= 0: runs on the side stream, joined in front of exec op `side_join`
+        bool wait_side = false;   // first reader of a side op's result
     };
     void run_eager();
     void drop_cuda_graph();
     void plan_activation_memory(const std::vector<ExecOp>& all);
+    void plan_side_ops(std::vector<ExecOp>& all);
 
     Precision _precision = Precision::FP32;
     int _device = 0;
-    cudaStream_t _stream = nullptr;
-    saber::Context<saber::NV> _ctx;
+    cudaStream_t _stream = nullptr, _side_stream = nullptr;
+    cudaEvent_t _fork_ev = nullptr, _join_ev = nullptr;
+    saber::Context<saber::NV> _ctx, _side_ctx;
     std::vector<ExecOp> _exec;
     std::map<std::string, std::shared_ptr<DTensor>> _owned;  // producer node -> tensor
     std::map<std::string, DTensor*> _node_tensor;            // every node -> its (possibly aliased) output

@@ -90,6 +90,37 @@ __device__ __forceinline__ void tma_load_im2col_4d_sa(const CUtensorMap* m, uint
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_sa), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
 }
+// Tiled 4-D load (dims C, W, H, N of an NHWC tensor): the box lands densely as [h][w][c] rows; coordinates may be
+// negative / past the edge, those elements are zero-filled -- the halo of a convolution slab.
+__device__ __forceinline__ void tma_load_4d_sa(const CUtensorMap* m, uint32_t bar_sa, uint32_t dst_sa, int32_t c,
+                                               int32_t w, int32_t h, int32_t n) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_sa),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_sa), "r"(c), "r"(w), "r"(h), "r"(n)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_sa, int32_t c, int32_t w, int32_t h,
+                                             int32_t n) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src_sa), "r"(c), "r"(w), "r"(h), "r"(n)
+                 : "memory");
+}
+// non-blocking probe of an mbarrier phase (true: the phase with this parity has completed)
+__device__ __forceinline__ bool mbar_try_wait_sa(uint32_t bar_sa, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_sa), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tc_commit_sa(uint32_t bar_sa) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_sa)
                  : "memory");

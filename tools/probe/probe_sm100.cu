@@ -61,31 +61,48 @@ __global__ void __launch_bounds__(128, 1) mma_cost_kernel(uint32_t idesc, int n_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_ptr;
-    if (threadIdx.x == 0) {
-        const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, version 1, SW128
-        const uint32_t base16 = smem_u32(smem) >> 4;
-        // warm-up
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t a_lo = ((base16 + 2 * (i & 3)) & 0x3FFF) | (1u << 16), b_lo = ((base16 + 1024 + 2 * (i & 3)) & 0x3FFF) | (1u << 16);
-            tc_mma_lohi<KIND>(tmem, a_lo, hi, b_lo, hi, idesc, i > 0);
+    // warp 1, one elected lane, everything derived from warp-uniform values: the compiler keeps the descriptors in
+    // uniform registers and emits back-to-back UTC*MMA (a divergent `threadIdx.x == 0` makes it wrap every MMA in an
+    // ELECT / R2UR waterfall loop, which costs ~120 clk per MMA by itself)
+    if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, version 1, SW128
+            const uint32_t base16 = smem_u32(smem) >> 4;
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t a_lo = ((base16 + 2 * (i & 3)) & 0x3FFF) | (1u << 16), b_lo = ((base16 + 1024 + 2 * (i & 3)) & 0x3FFF) | (1u << 16);
+                tc_mma_lohi<KIND>(tmem, a_lo, hi, b_lo, hi, idesc, i > 0);
+            }
+            tc_commit(&bar);
+            mbar_wait(&bar, 0);
+            tc_fence_after();
+            const uint32_t d1 = tmem + (n_acc > 1 ? 256u : 0u);
+            const uint32_t a_base = (base16 & 0x3FFF) | (1u << 16), b_base = ((base16 + 1024) & 0x3FFF) | (1u << 16);
+            const long long t0 = clock64();
+            if (mode == 0) {
+                for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        // stage (u >> 2) of the ring, 32-byte k slice (u & 3)
+                        const uint32_t off = (u >> 2) * (49152u >> 4) + 2u * (u & 3);
+                        tc_mma_lohi<KIND>((u & 1) ? d1 : tmem, a_base + off, hi, b_base + off, hi, idesc, 1);
+                    }
+                }
+            } else {
+                for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t off = (u >> 2) * (49152u >> 4) + 2u * (u & 3);
+                        mma_ts<KIND>(tmem, tmem + 448 + 8 * (u & 3), (static_cast<uint64_t>(hi) << 32) | (b_base + off), idesc, 1);
+                    }
+                }
+            }
+            const long long t1 = clock64();
+            tc_commit(&bar);
+            mbar_wait(&bar, 1);
+            const long long t2 = clock64();
+            if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
         }
-        tc_commit(&bar);
-        mbar_wait(&bar, 0);
-        tc_fence_after();
-        const long long t0 = clock64();
-        for (int i = 0; i < n_mma; ++i) {
-            const int st = (i >> 2) & 3, q = i & 3;
-            const uint32_t a16 = base16 + st * (49152 >> 4) + 2 * q, b16 = base16 + st * (49152 >> 4) + 1024 + 2 * q;
-            const uint32_t a_lo = (a16 & 0x3FFF) | (1u << 16), b_lo = (b16 & 0x3FFF) | (1u << 16);
-            const uint32_t d = tmem + (n_acc > 1 ? (i % n_acc) * 256 : 0);
-            if (mode == 0) tc_mma_lohi<KIND>(d, a_lo, hi, b_lo, hi, idesc, 1);
-            else mma_ts<KIND>(d, tmem + 448 + 8 * q, (static_cast<uint64_t>(hi) << 32) | b_lo, idesc, 1);
-        }
-        const long long t1 = clock64();
-        tc_commit(&bar);
-        mbar_wait(&bar, 1);
-        const long long t2 = clock64();
-        if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        __syncwarp();
     }
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tmem); }
@@ -105,16 +122,17 @@ static void run_mma_cost() {
     CK(cudaFuncSetAttribute(mma_cost_kernel<KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(mma_cost_kernel<KIND_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(mma_cost_kernel<KIND_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    printf("== 1. tcgen05.mma cost (clk per MMA, K = 32 bytes; issue-only / issue+drain over 256 MMAs)\n");
+    printf("== 1. tcgen05.mma cost (clk per MMA, K = 32 bytes; issue-only / issue+drain over 512 MMAs)\n");
     printf("%-6s %-4s %-4s %-5s %-5s %-6s %10s %10s\n", "kind", "M", "N", "mode", "accs", "grid", "issue", "total");
     const int Ms[2] = {128, 64};
-    const int Ns[6] = {16, 32, 64, 128, 192, 256};
+    const int Ns[7] = {8, 16, 32, 64, 128, 192, 256};
     for (int kind = 0; kind < 3; ++kind)
         for (int mi = 0; mi < 2; ++mi)
-            for (int ni = 0; ni < 6; ++ni)
+            for (int ni = 0; ni < 7; ++ni)
                 for (int mode = 0; mode < 2; ++mode)
                     for (int grid : {1, 148}) {
                         const int M = Ms[mi], N = Ns[ni];
+                        if (N == 8 && M == 128) continue;   // M=128 needs N % 16 == 0
                         if (kind == 2 && mode == 1) continue;
                         if (kind != 0 && (grid != 1 || M == 64)) continue;
                         if (mode == 1 && (M == 64 || grid != 1)) continue;
@@ -122,7 +140,7 @@ static void run_mma_cost() {
                             if (accs == 2 && (N > 256 || mode == 1 || grid != 1)) continue;
                             const uint32_t id = idesc_for(kind, M, N);
                             long long h[2];
-                            const int n_mma = 256;
+                            const int n_mma = 512;
                             if (kind == 0) mma_cost_kernel<KIND_I8><<<grid, 128, smem>>>(id, n_mma, mode, accs, d_out);
                             else if (kind == 1) mma_cost_kernel<KIND_F16><<<grid, 128, smem>>>(id, n_mma, mode, accs, d_out);
                             else mma_cost_kernel<KIND_TF32><<<grid, 128, smem>>>(id, n_mma, mode, accs, d_out);
@@ -285,20 +303,22 @@ static void run_ingest() {
 // ------------------------------------------------------------------------------------------------ 3. row-shifted descriptor
 // A slab: 160 rows x 128 B (SW128, written with the absolute-address swizzle a TMA load would use). For a shift s the MMA reads
 // rows [s, s+128). B: 32 rows x 128 B. D[128 x 32] = sum_k A[s+i][k] * B[j][k], checked against the host.
-__global__ void __launch_bounds__(128, 1) shift_kernel(const int8_t* a_rows, const int8_t* b_rows, int shift, int base_off_mode, int32_t* d_out) {
+__global__ void __launch_bounds__(128, 1) shift_kernel(const int8_t* a_rows, const int8_t* b_rows, int shift, int base_off_mode, int32_t* d_out, int rb) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_ptr;
     uint8_t* a_s = smem;              // 160 x 128 = 20480 B
     uint8_t* b_s = smem + 20480;      // 32 x 128
-    for (int i = threadIdx.x; i < 160 * 8; i += blockDim.x) {
-        const int row = i >> 3, c16 = i & 7;
-        *reinterpret_cast<uint4*>(a_s + row * 128 + ((c16 ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(a_rows + row * 128 + c16 * 16);
+    const int cpr = rb >> 4;                                  // 16-byte chunks per row
+    const int lg = rb == 128 ? 7 : (rb == 64 ? 6 : 5);
+    for (int i = threadIdx.x; i < 160 * cpr; i += blockDim.x) {
+        const int row = i / cpr, c16 = i % cpr, sw = (row >> (7 - lg)) & (cpr - 1);
+        *reinterpret_cast<uint4*>(a_s + row * rb + ((c16 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(a_rows + row * 128 + c16 * 16);
     }
-    for (int i = threadIdx.x; i < 32 * 8; i += blockDim.x) {
-        const int row = i >> 3, c16 = i & 7;
-        *reinterpret_cast<uint4*>(b_s + row * 128 + ((c16 ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(b_rows + row * 128 + c16 * 16);
+    for (int i = threadIdx.x; i < 32 * cpr; i += blockDim.x) {
+        const int row = i / cpr, c16 = i % cpr, sw = (row >> (7 - lg)) & (cpr - 1);
+        *reinterpret_cast<uint4*>(b_s + row * rb + ((c16 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(b_rows + row * 128 + c16 * 16);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
@@ -311,10 +331,11 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const int8_t* a_rows, con
     if (threadIdx.x == 0) {
         const uint32_t idesc = make_idesc(2, 1, 1, 128, 32);
         const uint32_t bo = base_off_mode ? static_cast<uint32_t>(shift & 7) : 0u;
-        const uint32_t hi_a = (1024u >> 4) | (1u << 14) | (bo << 17) | (2u << 29);
-        const uint32_t hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
-        const uint32_t a16 = (smem_u32(a_s) + shift * 128) >> 4, b16 = smem_u32(b_s) >> 4;
-        for (int q = 0; q < 4; ++q)
+        const uint32_t lt = rb == 128 ? 2u : (rb == 64 ? 4u : 6u);
+        const uint32_t hi_a = ((8u * rb) >> 4) | (1u << 14) | (bo << 17) | (lt << 29);
+        const uint32_t hi_b = ((8u * rb) >> 4) | (1u << 14) | (lt << 29);
+        const uint32_t a16 = (smem_u32(a_s) + shift * rb) >> 4, b16 = smem_u32(b_s) >> 4;
+        for (int q = 0; q < rb / 32; ++q)
             tc_mma_lohi<KIND_I8>(tmem, ((a16 + 2 * q) & 0x3FFF) | (1u << 16), hi_a, ((b16 + 2 * q) & 0x3FFF) | (1u << 16), hi_b, idesc, q > 0);
         tc_commit(&bar);
     }
@@ -342,10 +363,12 @@ static void run_shift() {
     CK(cudaMalloc(&da, a.size())); CK(cudaMalloc(&db, b.size())); CK(cudaMalloc(&dd, 128 * 32 * 4));
     CK(cudaMemcpy(da, a.data(), a.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db, b.data(), b.size(), cudaMemcpyHostToDevice));
+    for (int rb : {128, 64, 32})
     for (int mode = 0; mode < 2; ++mode)
         for (int shift : {0, 1, 2, 3, 7, 8, 9, 16, 18, 31}) {
+            if (mode == 1 && rb != 128) continue;
             CK(cudaMemset(dd, 0xff, 128 * 32 * 4));
-            shift_kernel<<<1, 128, 20480 + 4096 + 1024>>>(da, db, shift, mode, dd);
+            shift_kernel<<<1, 128, 20480 + 4096 + 1024>>>(da, db, shift, mode, dd, rb);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("shift kernel failed: %s\n", cudaGetErrorString(e)); exit(1); }
             std::vector<int32_t> h(128 * 32);
@@ -354,10 +377,10 @@ static void run_shift() {
             for (int i = 0; i < 128; ++i)
                 for (int j = 0; j < 32; ++j) {
                     int32_t acc = 0;
-                    for (int k = 0; k < 128; ++k) acc += int32_t(a[(i + shift) * 128 + k]) * int32_t(b[j * 128 + k]);
+                    for (int k = 0; k < rb; ++k) acc += int32_t(a[(i + shift) * 128 + k]) * int32_t(b[j * 128 + k]);
                     bad += acc != h[i * 32 + j];
                 }
-            printf("  base_offset %-8s shift %-3d : %d\n", mode ? "shift&7" : "0", shift, bad);
+            printf("  row %3d B  base_offset %-8s shift %-3d : %d\n", rb, mode ? "shift&7" : "0", shift, bad);
         }
     cudaFree(da); cudaFree(db); cudaFree(dd);
 }
