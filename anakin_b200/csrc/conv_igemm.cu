@@ -43,28 +43,6 @@
 
 namespace b200 {
 
-// ----------------------------------------------------------------- phase timeline (debug builds only)
-// -DB200_TIMELINE (tools/timeline.py builds it into anakin_b200/lib_tl) records per-CTA SM-clock stamps of
-// the pipeline phases; the shipped library compiles all of it out.
-#ifdef B200_TIMELINE
-struct TlRec {
-    unsigned long long gt0, gt1;
-    long long clk[8];
-    uint32_t bx, by, bz, smid, K, KS, bn, stages;
-};
-constexpr unsigned TL_CAP = 1u << 15;
-__device__ TlRec g_tl[TL_CAP];
-__device__ unsigned g_tl_n;
-__device__ __forceinline__ unsigned long long tl_globaltimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define TL(slot) do { g_tl[tl_idx].clk[slot] = clock64(); } while (0)
-#else
-#define TL(slot) do { } while (0)
-#endif
-
 // ----------------------------------------------------------------- the kernel
 #ifndef B200_CTAS_PER_SM
 #define B200_CTAS_PER_SM 2   // register budget: 65536 / (320 threads x CTAs)
@@ -484,6 +462,16 @@ static void load_driver_entry_points() {
 
 using namespace b200;
 
+namespace b200 {
+// conv_slab.cu
+bool slab_plan_setup(b200_conv_plan* pl);
+int encode_weights_map(b200_conv_plan* pl, int bn);
+#ifdef B200_TIMELINE
+int slab_debug_timeline(void* out, int max_recs);
+#endif
+int slab_bind_maps(b200_conv_plan* pl, void* encode_tiled_fn, const void* in, const void* res, void* out);
+}  // namespace b200
+
 
 template <int KIND, int BN, bool SPLITK>
 static void launch_conv(b200_conv_plan* pl, void* stream) {
@@ -596,6 +584,27 @@ static int encode_tile_map(CUtensorMap* map, const void* ptr, int dtype, int k_v
     }
     return B200_SUCCESS;
 }
+
+namespace b200 {
+// weights tensor map: [k rows][KS*chunk_el] K-major, box {chunk_el, bn} (bn = the tile width of the kernel that runs)
+int encode_weights_map(b200_conv_plan* pl, int bn) {
+    const b200_conv_desc_t* d = &pl->desc;
+    const Geometry& g = pl->g;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.KS) * g.chunk_el,
+                          static_cast<cuuint64_t>(d->k) * (d->math == B200_MATH_TF32X3 ? 2 : 1)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(g.KS) * g.chunk};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(g.chunk_el), static_cast<cuuint32_t>(bn)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&pl->map_b, tma_dtype(d->math), 2, const_cast<void*>(pl->weights), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_width(g.chunk),
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[b200_saber] cuTensorMapEncodeTiled(weights) failed: %d\n", static_cast<int>(r));
+        return B200_INVALID_VALUE;
+    }
+    return B200_SUCCESS;
+}
+}  // namespace b200
 
 extern "C" {
 
@@ -738,22 +747,7 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     if (!ok) { delete pl; return B200_UNIMPL_ERROR; }
     pl->idesc = make_idesc(c_fmt, a_fmt, b_fmt, BLOCK_M, bn);
 
-    // ---- weights tensor map: [k rows][KS*chunk_el] K-major, box {chunk_el, bn}
-    {
-        cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.KS) * g.chunk_el,
-                              static_cast<cuuint64_t>(d->k) * (d->math == B200_MATH_TF32X3 ? 2 : 1)};
-        cuuint64_t strides[1] = {static_cast<cuuint64_t>(g.KS) * g.chunk};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(g.chunk_el), static_cast<cuuint32_t>(bn)};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encode_tiled(&pl->map_b, tma_dtype(d->math), 2, const_cast<void*>(packed_weights_dev), dims,
-                                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_width(g.chunk),
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            fprintf(stderr, "[b200_saber] cuTensorMapEncodeTiled(weights) failed: %d\n", static_cast<int>(r));
-            delete pl;
-            return B200_INVALID_VALUE;
-        }
-    }
+    if (encode_weights_map(pl, bn) != B200_SUCCESS) { delete pl; return B200_INVALID_VALUE; }
 
     ConvKParams& kp = pl->kp;
     memset(&kp, 0, sizeof(kp));
@@ -772,6 +766,12 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     kp.bias = bias_dev; kp.scale = scale_dev;
     kp.out_es = out_es;
     kp.res_es = res_es;
+
+    // ---- stride-1 R x S layers: the slab-staged kernel (conv_slab.cu) when it applies
+    if (slab_plan_setup(pl)) {
+        *plan_out = pl;
+        return B200_SUCCESS;
+    }
 
     // ---- pipeline depth: as deep as the k loop needs, within the shared-memory budget. A grid that
     // exceeds one wave keeps two CTAs per SM resident (epilogue of one overlaps the main loop of the
@@ -850,6 +850,17 @@ int b200_conv_plan_run(b200_conv_plan_t* pl, const void* in, const void* res, vo
     if (!pl || !in || !out) return B200_INVALID_VALUE;
     const b200_conv_desc_t& d = pl->desc;
     if (d.res_dtype >= 0 && !res) return B200_INVALID_VALUE;
+    if (pl->slab) {
+        int st = slab_bind_maps(pl, reinterpret_cast<void*>(g_encode_tiled), in, res, out);
+        if (st != B200_SUCCESS) return st;
+        pl->launch(pl, stream);
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) {
+            fprintf(stderr, "[b200_saber] conv (slab) launch failed: %s\n", cudaGetErrorString(e));
+            return B200_UNKNOWN_ERROR;
+        }
+        return B200_SUCCESS;
+    }
     if (in != pl->map_a_ptr) {
         int st = encode_map_a(pl, in);
         if (st != B200_SUCCESS) return st;
@@ -892,6 +903,8 @@ int b200_conv_plan_info(const b200_conv_plan_t* pl, int32_t* block_n, int32_t* g
 
 int b200_conv_plan_split(const b200_conv_plan_t* pl) { return pl ? static_cast<int>(pl->grid.z) : 0; }
 
+int b200_conv_plan_is_slab(const b200_conv_plan_t* pl) { return pl && pl->slab ? 1 : 0; }
+
 int b200_fc_desc(b200_conv_desc_t* d, int32_t math, int32_t in_dtype, int32_t out_dtype, int32_t m, int32_t k_in,
                  int32_t n_out) {
     if (!d) return B200_INVALID_VALUE;
@@ -916,6 +929,9 @@ extern "C" B200_API int b200_debug_timeline(void* out, int max_recs) {
     if (out && n) cudaMemcpyFromSymbol(out, b200::g_tl, n * sizeof(b200::TlRec));
     const unsigned zero = 0;
     cudaMemcpyToSymbol(b200::g_tl_n, &zero, sizeof(zero));
-    return static_cast<int>(n);
+    // records of the slab kernel live in its own translation unit
+    const int more = b200::slab_debug_timeline(out ? static_cast<char*>(out) + n * sizeof(b200::TlRec) : nullptr,
+                                               max_recs - static_cast<int>(n));
+    return static_cast<int>(n) + more;
 }
 #endif

@@ -1,0 +1,545 @@
+// Slab-staged stride-1 R x S convolution on tcgen05 tensor cores (sm_100a).
+//
+// The TMA-im2col kernel (conv_igemm.cu) fetches the A operand once per filter tap: a 3x3 layer pulls every input
+// pixel through the SM's L2 port nine times, and that port (~78 GB/s per SM measured, tools/probe) is what bounds a
+// convolution at inference batch sizes. Here a CTA owns a th x tw rectangle of one image's output. Per input-channel
+// chunk it stages the (th+R-1) x (tw+S-1) input rectangle ONCE -- one tiled 4-D TMA box, halo zero-filled by the
+// engine -- as rows of `chunk` bytes (the slab), and the R*S taps are MMAs whose A descriptors simply start
+// (r*PW + s) rows further into the slab: the shared-memory swizzle is a function of the absolute address
+// (verified for SWIZZLE_32/64/128B, tools/probe/probe_sm100.cu), so a row-shifted view of a TMA-written tile is a
+// valid K-major operand. GEMM row m = i*PW + j is output pixel (p0+i, q0+j); the S-1 extra columns per row are
+// computed and dropped.
+//
+// Replaces the same reference entry points as conv_igemm.cu for 3x3 / 5x5 / 7x7 stride-1 layers
+// (saber/funcs/impl/cuda/saber_conv.cpp:17-585, sass winograd_conv* / direct_conv* families,
+//  third-party/sass/include/sass_funcs.h:54-427).
+//
+// Pipelines: slab slots (full_a / empty_a) and weight-tile slots (full_b / empty_b) are separate mbarrier rings fed
+// by one producer thread that issues whichever load has a free slot; warp 1 issues the MMAs; warps 2..9 run the
+// same fused epilogue as the im2col kernel, compacting the dropped columns while they stage the tile, and one
+// thread stores it with a 4-D TMA box (which also clips the ragged image edges).
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "conv_common.cuh"
+
+namespace b200 {
+
+int encode_weights_map(b200_conv_plan* pl, int bn);   // conv_igemm.cu
+
+constexpr int SLAB_MAX_A = 4;    // slab slots
+constexpr int SLAB_MAX_B = 16;   // weight-tile slots
+
+// smem: [slab ring][weight ring][residual tile][bias | scale][barriers: full_a, empty_a, full_b, empty_b,
+//       tmem_full, res_full][tmem ptr]
+__host__ __device__ constexpr int slab_tail_bytes(int bn) {
+    return 2 * bn * 4 + (2 * SLAB_MAX_A + 2 * SLAB_MAX_B + 2) * 8 + 16;
+}
+
+template <int KIND, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+                 const ConvKParams p, const SlabParams sp, const uint32_t idesc) {
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* slab_ring = smem + sp.a_off;
+    uint8_t* b_ring = smem + sp.b_off;
+    uint8_t* res_tile = smem + sp.epi_off;
+    float* bias_s = reinterpret_cast<float*>(res_tile + p.res_panels * BLOCK_M * p.res_pw);
+    float* scale_s = bias_s + BN;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(scale_s + BN);
+    uint64_t* empty_a = full_a + SLAB_MAX_A;
+    uint64_t* full_b = empty_a + SLAB_MAX_A;
+    uint64_t* empty_b = full_b + SLAB_MAX_B;
+    uint64_t* tmem_full_bar = empty_b + SLAB_MAX_B;
+    uint64_t* res_full_bar = tmem_full_bar + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full_bar + 1);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+#ifdef B200_TIMELINE
+    uint32_t& tl_idx = tmem_ptr_smem[1];
+    if (threadIdx.x == 0) {
+        tl_idx = atomicAdd(&g_tl_n, 1u) & (TL_CAP - 1);
+        TlRec& r = g_tl[tl_idx];
+        r.gt0 = tl_globaltimer();
+        r.clk[0] = clock64();
+        r.bx = blockIdx.x; r.by = blockIdx.y; r.bz = 0;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(r.smid));
+        r.K = p.K; r.KS = p.CC * p.R * p.S; r.bn = BN; r.stages = sp.SA * 100 + sp.SB;
+    }
+#endif
+
+    // tile of this CTA
+    int t = blockIdx.x;
+    const int tj = t % sp.tiles_w; t /= sp.tiles_w;
+    const int ti = t % sp.tiles_h;
+    const int n_img = t / sp.tiles_h;
+    const int p0 = ti * sp.th, q0 = tj * sp.tw;
+    const int n0 = blockIdx.y * BN;
+    const int own_groups = max(0, min(BN, p.K - n0) + 15) >> 4;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+        if (p.res_panels > 0) tma_prefetch_desc(&map_res);
+        for (int i = 0; i < sp.SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < sp.SB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(res_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp_idx == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) TL(1);
+
+    pdl_launch_dependents();
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            // Two rings, one thread: slab slots (one input-channel chunk each) and weight-group slots (the S taps of
+            // one filter row of one chunk, S tiled loads on one barrier). All ring state is carried incrementally --
+            // no division in the loop -- and whichever ring has a free slot is fed first.
+            const uint32_t full_a_sa = smem_u32(full_a), empty_a_sa = smem_u32(empty_a);
+            const uint32_t full_b_sa = smem_u32(full_b), empty_b_sa = smem_u32(empty_b);
+            const uint32_t slab_sa = smem_u32(slab_ring), bring_sa = smem_u32(b_ring);
+            const int total_g = p.CC * p.R;                    // weight groups, consumed in (cc, r) order
+            const uint32_t group_bytes = static_cast<uint32_t>(sp.btile_bytes) * p.S;
+            const int k_tap = p.CC * p.chunk_el;               // k distance between consecutive taps (tap-major packing)
+            // weight group state
+            int gb = 0, g_slot = 0, g_r = 0;
+            uint32_t g_phase = 1;                              // parity to wait on the empty barrier (first trip: free)
+            int g_k = 0;                                       // k coordinate of (cc, r, s = 0)
+            int g_kcc = 0;                                     // cc * chunk_el
+            auto issue_group = [&]() {
+                const uint32_t bar = full_b_sa + 8 * g_slot;
+                mbar_arrive_expect_tx_sa(bar, group_bytes);
+                uint32_t dst = bring_sa + g_slot * group_bytes;
+                int k = g_k;
+                for (int s2 = 0; s2 < p.S; ++s2) {
+                    tma_load_2d_sa(&map_b, bar, dst, k, n0);
+                    dst += sp.btile_bytes;
+                    k += k_tap;
+                }
+                ++gb;
+                if (++g_slot == sp.SB) { g_slot = 0; g_phase ^= 1; }
+                if (++g_r == p.R) { g_r = 0; g_kcc += p.chunk_el; g_k = g_kcc; }
+                else g_k += p.S * k_tap;
+            };
+            // weights do not depend on the previous kernel: the first ring trip goes out before the grid dependency
+            const int npre = min(sp.SB, total_g);
+            for (int i = 0; i < npre; ++i) issue_group();
+            pdl_wait_prior_grid();
+            TL(2);
+            int ia = 0, a_slot = 0;
+            uint32_t a_phase = 1;
+            int a_c = 0;
+            while (ia < p.CC || gb < total_g) {
+                if (ia < p.CC && (ia < sp.SA || mbar_try_wait_sa(empty_a_sa + 8 * a_slot, a_phase))) {
+                    mbar_arrive_expect_tx_sa(full_a_sa + 8 * a_slot, sp.slab_box_bytes);
+                    tma_load_4d_sa(&map_a, full_a_sa + 8 * a_slot, slab_sa + a_slot * sp.slab_bytes, a_c, q0 - p.pad_w,
+                                   p0 - p.pad_h, n_img);
+                    if (ia == 0 && p.res_panels > 0 && own_groups > 0) {
+                        // the residual tile is only needed by the epilogue: after the first slab is on its way
+                        const int cols = p.res_pw / p.res_es;
+                        mbar_arrive_expect_tx(res_full_bar, p.res_panels * sp.th * sp.tw * p.res_pw);
+#pragma unroll 1
+                        for (int j = 0; j < p.res_panels; ++j)
+                            tma_load_4d_sa(&map_res, smem_u32(res_full_bar), smem_u32(res_tile) + j * BLOCK_M * p.res_pw,
+                                           n0 + j * cols, q0, p0, n_img);
+                    }
+                    ++ia;
+                    a_c += p.chunk_el;
+                    if (++a_slot == sp.SA) { a_slot = 0; a_phase ^= 1; }
+                }
+                if (gb < total_g && (gb < sp.SB || mbar_try_wait_sa(empty_b_sa + 8 * g_slot, g_phase))) issue_group();
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t lt = layout_type_for_chunk(p.chunk);
+            const uint32_t hi = ((8u * p.chunk) >> 4) | (1u << 14) | (lt << 29);   // SBO = 8 rows, version 1, swizzle
+            const uint32_t lbo = 1u << 16;
+            const uint32_t slab_d0 = (smem_u32(slab_ring) >> 4) | lbo, bring_d0 = (smem_u32(b_ring) >> 4) | lbo;
+            const uint32_t full_a_sa = smem_u32(full_a), empty_a_sa = smem_u32(empty_a);
+            const uint32_t full_b_sa = smem_u32(full_b), empty_b_sa = smem_u32(empty_b);
+            const uint32_t row16 = static_cast<uint32_t>(p.chunk) >> 4;            // one slab row in 16-byte units
+            const uint32_t slab16 = static_cast<uint32_t>(sp.slab_bytes) >> 4;
+            const uint32_t btile16 = static_cast<uint32_t>(sp.btile_bytes) >> 4;
+            const uint32_t pw16 = static_cast<uint32_t>(sp.PW) * row16;
+            uint32_t accum = 0;
+            // ring state, carried incrementally
+            uint32_t a_full = full_a_sa, a_empty = empty_a_sa, a_desc = slab_d0, a_phase = 0;
+            int a_slot = 0;
+            uint32_t b_full = full_b_sa, b_empty = empty_b_sa, b_desc = bring_d0, b_phase = 0;
+            int b_slot = 0;
+            const uint32_t group16 = btile16 * p.S;
+#pragma unroll 1
+            for (int cc = 0; cc < p.CC; ++cc) {
+                mbar_wait_sa(a_full, a_phase);
+                tc_fence_after();
+#ifdef B200_TIMELINE
+                if (cc == 0) TL(3);
+#endif
+                uint32_t a_row = a_desc;      // descriptor of tap (r, 0)
+#pragma unroll 1
+                for (int r = 0; r < p.R; ++r) {
+                    mbar_wait_sa(b_full, b_phase);
+                    tc_fence_after();
+                    uint32_t a_tap = a_row, b_tile = b_desc;
+#pragma unroll 1
+                    for (int s2 = 0; s2 < p.S; ++s2) {
+                        // the 32-byte k slices of one chunk: descriptors differ by 2 (x 16 B), independent adds
+                        tc_mma_lohi<KIND>(tmem_base, a_tap, hi, b_tile, hi, idesc, accum);
+                        accum = 1;
+                        if (sp.mma_per_tap > 1) tc_mma_lohi<KIND>(tmem_base, a_tap + 2, hi, b_tile + 2, hi, idesc, 1);
+                        if (sp.mma_per_tap > 2) {
+                            tc_mma_lohi<KIND>(tmem_base, a_tap + 4, hi, b_tile + 4, hi, idesc, 1);
+                            tc_mma_lohi<KIND>(tmem_base, a_tap + 6, hi, b_tile + 6, hi, idesc, 1);
+                        }
+                        a_tap += row16;
+                        b_tile += btile16;
+                    }
+                    tc_commit_sa(b_empty);    // the group's slot is free once these MMAs retire
+                    b_full += 8; b_empty += 8; b_desc += group16;
+                    if (++b_slot == sp.SB) { b_slot = 0; b_phase ^= 1; b_full = full_b_sa; b_empty = empty_b_sa; b_desc = bring_d0; }
+                    a_row += pw16;
+                }
+                tc_commit_sa(a_empty);
+                a_full += 8; a_empty += 8; a_desc += slab16;
+                if (++a_slot == sp.SA) { a_slot = 0; a_phase ^= 1; a_full = full_a_sa; a_empty = empty_a_sa; a_desc = slab_d0; }
+            }
+            tc_commit(tmem_full_bar);
+            TL(4);
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps =====================
+        for (int i = threadIdx.x - 64; i < BN; i += EPI_THREADS) {
+            const bool ok = (n0 + i) < p.K;
+            bias_s[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n0 + i) : 0.f;
+            scale_s[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0 + i) : 1.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        mbar_wait(tmem_full_bar, 0);   // every MMA retired: both operand rings are free
+        tc_fence_after();
+        if (threadIdx.x == 64) TL(5);
+    }
+
+    constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+    if (warp_idx >= 2 && own_groups > 0) {
+        const int quarter = warp_idx & 3;
+        const int m = quarter * 32 + lane;
+        // GEMM row -> staging row: kept pixels are compacted to i*tw + j (the dense [th][tw] order the store box
+        // reads); dropped rows go to the unused rows behind them, one each, so every thread runs the same code
+        const int i = m / sp.PW, j = m - i * sp.PW;
+        int row;
+        if (i < sp.th && j < sp.tw) row = i * sp.tw + j;
+        else if (i < sp.th) row = sp.th * sp.tw + i * (sp.PW - sp.tw) + (j - sp.tw);
+        else row = m;
+        if (p.res_panels > 0) mbar_wait(res_full_bar, 0);
+        tc_fence_after();
+        auto lg2 = [](int pw) { return pw == 128 ? 7 : (pw == 64 ? 6 : (pw == 32 ? 5 : 4)); };
+        uint8_t* out_tile = smem;   // the operand rings, all consumed
+        const PanelRow out_row = make_panel_row(smem_u32(out_tile), lg2(p.out_pw), row);
+        const PanelRow res_row = make_panel_row(smem_u32(res_tile), lg2(p.res_pw ? p.res_pw : 128), row);
+        const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int cbeg = ((warp_idx - 2) >> 2) * COLS_PER_WARP, cend = min(BN, cbeg + COLS_PER_WARP);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            if (n0 + c0 >= p.K) break;
+            uint32_t v0[16];
+            tmem_ld_32x32b_x16(t_row + c0, v0);
+            tmem_ld_wait();
+            epilogue16<KIND>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (warp_idx == 2 && lane == 0) {
+            TL(6);
+            const int cols_per_panel = p.out_pw / p.out_es;
+            for (int jp = 0; jp < p.out_panels; ++jp) {
+                if (n0 + jp * cols_per_panel >= p.K) break;
+                tma_store_4d(&map_out, smem_u32(out_tile) + jp * BLOCK_M * p.out_pw, n0 + jp * cols_per_panel, q0, p0,
+                             n_img);
+            }
+            tma_store_commit();
+            tma_store_wait_read();
+#ifdef B200_TIMELINE
+            TL(7);
+            g_tl[tl_idx].gt1 = tl_globaltimer();
+#endif
+        }
+    }
+
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static CUtensorMapSwizzle slab_swizzle(int bytes) {
+    return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                       : (bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
+}
+static CUtensorMapDataType slab_dtype(int dt) {
+    return dt == B200_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                            : (dt == B200_HALF ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+}
+
+// 4-D tiled map over an NHWC tensor [n][h][w][ldc] of which `c_valid` channels exist; box {box_c, box_w, box_h, 1}.
+static int encode_nhwc_map(void* encode_fn, CUtensorMap* map, const void* ptr, int dtype, int c_valid, int ldc, int w, int h,
+                           int n, int box_c, int box_w, int box_h, int swizzle_bytes) {
+    const int es = dtype_size(dtype);
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(c_valid), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                          static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(ldc) * es, static_cast<cuuint64_t>(w) * ldc * es,
+                             static_cast<cuuint64_t>(h) * w * ldc * es};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = reinterpret_cast<PFN_encodeTiled>(encode_fn)(
+        map, slab_dtype(dtype), 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        slab_swizzle(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[b200_saber] cuTensorMapEncodeTiled(4-D nhwc) failed: %d\n", static_cast<int>(r));
+        return B200_INVALID_VALUE;
+    }
+    return B200_SUCCESS;
+}
+
+template <int KIND, int BN>
+static void launch_slab(b200_conv_plan* pl, void* stream) {
+    auto kern = conv_slab_kernel<KIND, BN>;
+    static std::atomic<bool> opted_in[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < kMaxDevices && !opted_in[dev].load(std::memory_order_acquire)) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+        opted_in[dev].store(true, std::memory_order_release);
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = pl->grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, pl->map_a, pl->map_b, pl->map_out, pl->map_res, pl->kp, pl->sp, pl->idesc);
+    count_launch();
+}
+
+template <int KIND>
+static bool select_slab_launch(b200_conv_plan* pl) {
+    switch (pl->bn) {
+        case 32: pl->launch = launch_slab<KIND, 32>; return true;
+        case 64: pl->launch = launch_slab<KIND, 64>; return true;
+        case 128: pl->launch = launch_slab<KIND, 128>; return true;
+        case 256: pl->launch = launch_slab<KIND, 256>; return true;
+    }
+    return false;
+}
+
+// per-MMA cost in SM clocks (K = 32 bytes, M = 128, both operands in shared memory): measured, tools/probe
+static double mma_clk(int bn) { return bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0; }
+
+// Decide whether the slab variant serves this convolution and set the plan up for it (tile, BN, ring depths, smem).
+// Returns false to leave the plan to the im2col kernel.
+bool slab_plan_setup(b200_conv_plan* pl) {
+    const b200_conv_desc_t& d = pl->desc;
+    const Geometry& g = pl->g;
+    static const bool enabled = [] { const char* e = getenv("B200_SABER_SLAB"); return !(e && e[0] == '0'); }();
+    if (!enabled) return false;
+    if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) { if (atoi(e) > 1) return false; }   // split-K experiments
+    if (d.r * d.s < 2 || d.stride_h != 1 || d.stride_w != 1 || d.dil_h != 1 || d.dil_w != 1) return false;
+    if (d.math == B200_MATH_TF32X3) return false;          // fp32 hi/lo split pass: im2col kernel only (for now)
+    if (g.chunk < 32 || d.s > 16 || d.r > 16) return false;
+    const int out_es = dtype_size(d.out_dtype);
+    const int res_es = d.res_dtype >= 0 ? dtype_size(d.res_dtype) : 0;
+
+    SlabParams sp{};
+    sp.Ho = g.ho; sp.Wo = g.wo;
+    if (g.wo + d.s - 1 <= BLOCK_M) {
+        sp.tw = g.wo;
+        sp.PW = g.wo + d.s - 1;
+        const int th_max = BLOCK_M / sp.PW;
+        const int tiles = (g.ho + th_max - 1) / th_max;
+        sp.th = (g.ho + tiles - 1) / tiles;                 // equal-height tiles
+    } else {
+        sp.PW = BLOCK_M;
+        sp.tw = BLOCK_M - (d.s - 1);
+        sp.th = 1;
+    }
+    sp.tiles_h = (g.ho + sp.th - 1) / sp.th;
+    sp.tiles_w = (g.wo + sp.tw - 1) / sp.tw;
+    const int tiles = d.n * sp.tiles_h * sp.tiles_w;
+    const int rows_alloc = ((BLOCK_M + (d.r - 1) * sp.PW + (d.s - 1)) + 7) & ~7;
+    sp.slab_bytes = rows_alloc * g.chunk;                   // rows of `chunk` bytes; 8 rows = one swizzle period
+    sp.slab_bytes = (sp.slab_bytes + 1023) & ~1023;
+    sp.slab_box_bytes = (sp.th + d.r - 1) * sp.PW * g.chunk;
+    if ((sp.th + d.r - 1) > 256 || sp.PW > 256) return false;
+    sp.mma_per_tap = g.chunk / 32;
+    const int RS = d.r * d.s;
+
+    // ---- BN: cheapest estimated CTA time x waves (ingest ~38.7 B/clk per SM vs MMA issue; measured, tools/probe)
+    const int sms = sm_count();
+    const int kr32 = (d.k + 31) / 32 * 32;
+    const int max_bn = (out_es == 4 || res_es == 4) ? 128 : 256;
+    int best_bn = 0;
+    double best_t = 0;
+    const int cands[4] = {32, 64, 128, 256};
+    for (int ci = 0; ci < 4; ++ci) {
+        const int bn = cands[ci];
+        if (bn > max_bn || (bn > kr32 && bn != 32)) continue;
+        const int ctas = tiles * ((d.k + bn - 1) / bn);
+        const double mma = static_cast<double>(g.CC) * RS * sp.mma_per_tap * mma_clk(bn);
+        const double ingest = (static_cast<double>(g.CC) * sp.slab_box_bytes + static_cast<double>(g.CC) * RS * bn * g.chunk) / 38.7;
+        const double epi = 128.0 * bn * 9.0 / 128.0;
+        const double cta = (mma > ingest ? mma : ingest) + epi + 1500.0;
+        const int per_sm = 2;
+        const double waves = static_cast<double>((ctas + sms - 1) / sms);
+        // co-resident CTAs share the SM's ingest port and tensor pipe: a second CTA on the SM costs a full turn
+        const double tt = waves <= 1.0 ? cta : cta * ((ctas + sms * per_sm - 1) / (sms * per_sm)) * per_sm * 0.75;
+        if (best_bn == 0 || tt < best_t) { best_bn = bn; best_t = tt; }
+    }
+    if (const char* e = getenv("B200_SABER_FORCE_BN")) {
+        const int fb = atoi(e);
+        if ((fb == 32 || fb == 64 || fb == 128 || fb == 256) && fb <= max_bn) best_bn = fb;
+    }
+    if (best_bn == 0) return false;
+    const int bn = best_bn;
+    sp.btile_bytes = bn * g.chunk;
+
+    // ---- shared memory: slab slots + weight slots (the front of which doubles as the output staging tile)
+    ConvKParams& kp = pl->kp;
+    kp.epi_bn = bn;
+    kp.split = 1;
+    kp.out_es = out_es;
+    kp.res_es = res_es;
+    kp.out_pw = bn * out_es >= 128 ? 128 : bn * out_es;
+    kp.out_panels = bn * out_es / kp.out_pw;
+    kp.res_pw = res_es ? (bn * res_es >= 128 ? 128 : bn * res_es) : 0;
+    kp.res_panels = res_es ? bn * res_es / kp.res_pw : 0;
+    const int staging = BLOCK_M * bn * out_es;
+    const int res_bytes = BLOCK_M * bn * res_es;
+    const int fixed = res_bytes + slab_tail_bytes(bn) + 1024;
+    const int half_budget = MAX_SMEM / 2 - 2048;
+    // a weight-ring slot holds one GROUP: the S taps of one filter row of one chunk
+    const int group_bytes = d.s * sp.btile_bytes;
+    const int total_groups = g.CC * d.r;
+    auto fits = [&](int sa, int sb, int budget) { return sa * sp.slab_bytes + sb * group_bytes + fixed <= budget; };
+    int sa = g.CC < 2 ? 1 : 2;
+    int sb = total_groups < 3 ? total_groups : 3;
+    int budget = half_budget;
+    if (!fits(sa, sb, budget)) {
+        budget = MAX_SMEM;
+        while (sb > 2 && !fits(sa, sb, budget)) --sb;
+        if (!fits(sa, sb, budget) && sa > 1) sa = 1;
+        while (sb > 1 && !fits(sa, sb, budget)) --sb;
+        if (!fits(sa, sb, budget)) return false;
+    }
+    // use what is left of the budget: deeper weight ring first (it hides the L2 latency of the k loop), then slabs
+    while (sb < SLAB_MAX_B && sb < total_groups && fits(sa, sb + 1, budget)) ++sb;
+    while (sa < SLAB_MAX_A && sa < g.CC && fits(sa + 1, sb, budget)) ++sa;
+    int ring = sa * sp.slab_bytes + sb * group_bytes;
+    if (ring < staging) {   // the staging tile must fit in the rings it reuses
+        const int extra = (staging - ring + group_bytes - 1) / group_bytes;
+        if (sb + extra > SLAB_MAX_B || !fits(sa, sb + extra, MAX_SMEM)) return false;
+        sb += extra;
+        ring = sa * sp.slab_bytes + sb * group_bytes;
+    }
+    sp.SA = sa; sp.SB = sb;
+    sp.a_off = 0;
+    sp.b_off = sa * sp.slab_bytes;
+    sp.epi_off = ring;
+    pl->smem_bytes = ring + fixed;
+    if (pl->smem_bytes > MAX_SMEM) return false;
+
+    pl->bn = bn;
+    pl->grid = dim3(tiles, (d.k + bn - 1) / bn, 1);
+    bool ok = false;
+    uint32_t a_fmt = 0, b_fmt = 0, c_fmt = 1;
+    if (d.math == B200_MATH_I8) {
+        ok = select_slab_launch<KIND_I8>(pl);
+        a_fmt = (d.in_dtype == B200_INT8) ? 1u : 0u; b_fmt = 1u; c_fmt = 2u;
+    } else if (d.math == B200_MATH_F16) {
+        ok = select_slab_launch<KIND_F16>(pl);
+    } else {
+        ok = select_slab_launch<KIND_TF32>(pl);
+        a_fmt = b_fmt = 2u;
+    }
+    if (!ok) return false;
+    if (encode_weights_map(pl, bn) != B200_SUCCESS) return false;   // the weight box follows THIS kernel's tile width
+    pl->idesc = make_idesc(c_fmt, a_fmt, b_fmt, BLOCK_M, bn);
+    pl->sp = sp;
+    pl->slab = true;
+    return true;
+}
+
+// (re)encode the activation / output / residual maps of a slab plan for the buffers of this run
+int slab_bind_maps(b200_conv_plan* pl, void* encode_tiled_fn, const void* in, const void* res, void* out) {
+    const b200_conv_desc_t& d = pl->desc;
+    const Geometry& g = pl->g;
+    const SlabParams& sp = pl->sp;
+    const int in_dt = d.math == B200_MATH_I8 ? B200_UINT8 : (d.math == B200_MATH_F16 ? B200_HALF : B200_FLOAT);
+    if (in != pl->map_a_ptr) {
+        int st = encode_nhwc_map(encode_tiled_fn, &pl->map_a, in, in_dt, d.c, d.c, d.w, d.h, d.n, g.chunk_el, sp.PW,
+                                 sp.th + d.r - 1, g.chunk);
+        if (st != B200_SUCCESS) return st;
+        pl->map_a_ptr = in;
+    }
+    if (out != pl->map_out_ptr) {
+        int st = encode_nhwc_map(encode_tiled_fn, &pl->map_out, out, d.out_dtype, d.k, d.ldc, g.wo, g.ho, d.n,
+                                 pl->kp.out_pw / pl->kp.out_es, sp.tw, sp.th, pl->kp.out_pw);
+        if (st != B200_SUCCESS) return st;
+        pl->map_out_ptr = out;
+    }
+    if (d.res_dtype >= 0 && res != pl->map_res_ptr) {
+        int st = encode_nhwc_map(encode_tiled_fn, &pl->map_res, res, d.res_dtype, d.k, d.ldc, g.wo, g.ho, d.n,
+                                 pl->kp.res_pw / pl->kp.res_es, sp.tw, sp.th, pl->kp.res_pw);
+        if (st != B200_SUCCESS) return st;
+        pl->map_res_ptr = res;
+    } else if (d.res_dtype < 0 && pl->map_res_ptr == nullptr) {
+        pl->map_res = pl->map_out;
+    }
+    return B200_SUCCESS;
+}
+
+#ifdef B200_TIMELINE
+int slab_debug_timeline(void* out, int max_recs) {
+    unsigned n = 0;
+    cudaMemcpyFromSymbol(&n, g_tl_n, sizeof(n));
+    if (n > TL_CAP) n = TL_CAP;
+    if (max_recs < 0) max_recs = 0;
+    if (static_cast<int>(n) > max_recs) n = max_recs;
+    if (out && n) cudaMemcpyFromSymbol(out, g_tl, n * sizeof(TlRec));
+    const unsigned zero = 0;
+    cudaMemcpyToSymbol(g_tl_n, &zero, sizeof(zero));
+    return static_cast<int>(n);
+}
+#endif
+
+}  // namespace b200

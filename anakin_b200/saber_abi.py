@@ -58,6 +58,7 @@ SYMBOLS = {
     "b200_conv_plan_destroy": (None, [_vp]),
     "b200_conv_plan_info": (C.c_int, [_vp] + [C.POINTER(_i)] * 5),
     "b200_conv_plan_split": (C.c_int, [_vp]),
+    "b200_conv_plan_is_slab": (C.c_int, [_vp]),
     "b200_dwconv_run": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_fc_desc": (C.c_int, [C.POINTER(ConvDesc), _i, _i, _i, _i, _i, _i]),
     "b200_pool_out_hw": (C.c_int, [C.POINTER(PoolDesc), C.POINTER(_i), C.POINTER(_i)]),

@@ -164,6 +164,9 @@ B200_API int b200_conv_plan_info(const b200_conv_plan_t* plan, int32_t* block_n,
                         int32_t* grid_y, int32_t* k_steps, int32_t* smem_bytes);
 /* split-K factor of the plan (= cluster size along z; 1 when the k loop is not split), 0 for a null plan. */
 B200_API int b200_conv_plan_split(const b200_conv_plan_t* plan);
+/* 1 when the plan runs the slab-staged stride-1 R x S kernel (the input rectangle of a tile is staged once per
+ * channel chunk and the filter taps are row-shifted views of it) instead of the TMA-im2col kernel. */
+B200_API int b200_conv_plan_is_slab(const b200_conv_plan_t* plan);
 
 /* ------------------------------------------------------------------------
  * Depthwise convolution (MobileNet). Replaces SaberDepthWiseConv

@@ -205,3 +205,117 @@ def test_conv_float(case, math, with_res, oracle, expect=None):
     if math == "tf32x3":
         scale_ref = float(np.abs(want).max())
         assert max_diff <= 2e-5 * max(1.0, scale_ref), (max_diff, scale_ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Slab-staged stride-1 R x S kernel (conv_slab.cu): the tile's input rectangle is staged once per channel chunk
+# and the filter taps are row-shifted views of it. Shapes cover every swizzle width (32 / 64 / 128-byte chunks),
+# 1 .. 4 channel chunks, all four ResNet feature-map sizes (tiles of 2 x 56, 4 x 28, 7 x 14, 7 x 7 pixels), images
+# wider than one tile (tile = part of a row), ragged tile rows, 5 x 5 / non-square filters, no / asymmetric-free
+# padding, ragged output channels, and every forced tile width.
+# (n, h, w, c, k, r, s, pad_h, pad_w)
+SLAB_CASES = [
+    (2, 14, 14, 256, 256, 3, 3, 1, 1),
+    (8, 7, 7, 512, 512, 3, 3, 1, 1),
+    (2, 28, 28, 128, 128, 3, 3, 1, 1),
+    (1, 56, 56, 64, 64, 3, 3, 1, 1),
+    (1, 12, 12, 32, 48, 3, 3, 1, 1),       # SWIZZLE_32B rows
+    (1, 30, 30, 64, 40, 3, 3, 0, 0),       # no padding, ragged channels
+    (1, 9, 140, 64, 64, 3, 3, 1, 1),       # wider than a tile: two tiles per row, the second one ragged
+    (1, 5, 224, 128, 32, 3, 3, 1, 1),
+    (2, 17, 17, 128, 72, 5, 5, 2, 2),      # 5 x 5, ragged tile rows
+    (1, 20, 20, 64, 64, 1, 7, 0, 3),       # 1 x 7
+    (1, 20, 20, 64, 64, 7, 1, 3, 0),       # 7 x 1
+    (3, 10, 10, 384, 96, 3, 3, 2, 2),      # padding wider than the filter needs, 3 chunks
+]
+
+
+def _slab_io(rng, case, in_unsigned):
+    n, h, w, c, k, r, s, ph, pw = case
+    x = (rng.integers(0, 256, (n, h, w, c)).astype(np.uint8) if in_unsigned
+         else rng.integers(-128, 128, (n, h, w, c)).astype(np.int8))
+    wq = rng.integers(-127, 128, (k, c, r, s)).astype(np.int8)
+    bias = rng.uniform(-2000, 2000, k).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, k).astype(np.float32) * np.float32(1.0 / (40.0 * np.sqrt(c * r * s) * 8))
+    return x, wq, bias, scale
+
+
+@pytest.mark.parametrize("case", SLAB_CASES)
+@pytest.mark.parametrize("variant", ["s8_relu_u8", "u8_res_s8", "s8_f32"])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
+def test_conv_slab_int8_bit_exact(case, variant, bn, oracle, monkeypatch):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev, pad_channels
+    if bn:
+        if SLAB_CASES.index(case) % 3 != (bn // 64) % 3:
+            pytest.skip("forced tile widths are sampled over the shape list")
+        monkeypatch.setenv("B200_SABER_FORCE_BN", str(bn))
+    rng = np.random.default_rng(hash((case, variant)) % (2 ** 31))
+    n, h, w, c, k, r, s, ph, pw = case
+    in_unsigned = variant == "u8_res_s8"
+    x, wq, bias, scale = _slab_io(rng, case, in_unsigned)
+    out_dtype = {"s8_relu_u8": A.UINT8, "u8_res_s8": A.INT8, "s8_f32": A.FLOAT}[variant]
+    if out_dtype == A.FLOAT and bn > 128:
+        pytest.skip("4-byte outputs cap the tile at 128 channels")
+    kw = dict(stride=(1, 1), pad=(ph, pw), dil=(1, 1), relu=variant != "s8_f32")
+    res, sum_scale = None, 1.0
+    oh, ow = h + 2 * ph - r + 1, w + 2 * pw - s + 1
+    if variant == "u8_res_s8":
+        res = rng.integers(0, 256, (n, oh, ow, k)).astype(np.uint8)
+        sum_scale = 0.37
+    want = oracle.conv_s8_nhwc_x86(x, wq, bias, scale, residual=res, sum_scale=sum_scale, out_dtype=out_dtype, **kw)
+    ldc = (k + 15) // 16 * 16 if out_dtype != A.FLOAT else (k + 3) // 4 * 4
+    run = ConvRunner(A.MATH_I8, x.shape, A.UINT8 if in_unsigned else A.INT8, wq, bias, scale,
+                     out_dtype, res_dtype=(A.UINT8 if res is not None else -1), sum_scale=sum_scale, ldc=ldc, **kw)
+    info = run.info()
+    assert info["slab"], info
+    if bn:
+        assert info["block_n"] == bn, info
+    got = run.run(dev(x), dev(pad_channels(res, ldc)) if res is not None else None)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert (got[..., k:] == 0).all(), "padding channels must stay untouched"
+    assert got[..., :k].shape == want.shape
+    bad = np.argwhere(got[..., :k] != want)
+    assert bad.shape[0] == 0, "%d mismatches, first %s (info %s)" % (bad.shape[0], bad[:5], info)
+    # the same plan again into the same buffers (graph replays re-run plans): still exact
+    got2 = run.run(dev(x), dev(pad_channels(res, ldc)) if res is not None else None)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got2.cpu().numpy()[..., :k], want)
+
+
+@pytest.mark.parametrize("case", [(2, 14, 14, 64, 64, 3, 3, 1, 1), (1, 28, 28, 128, 96, 3, 3, 1, 1),
+                                  (1, 6, 150, 32, 32, 3, 3, 1, 1), (2, 9, 9, 256, 128, 5, 5, 2, 2)])
+@pytest.mark.parametrize("math", ["f16", "tf32"])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv_slab_float(case, math, with_res, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev
+    rng = np.random.default_rng(hash((case, math, with_res)) % (2 ** 31))
+    n, h, w, c, k, r, s, ph, pw = case
+    x = rng.uniform(-1, 1, (n, h, w, c)).astype(np.float32)
+    wt = (rng.standard_normal((k, c, r, s)) * np.sqrt(2.0 / (c * r * s))).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, k).astype(np.float32)
+    kw = dict(stride=(1, 1), pad=(ph, pw), dil=(1, 1), relu=True, neg_slope=0.1)
+    oh, ow = h + 2 * ph - r + 1, w + 2 * pw - s + 1
+    res = rng.uniform(-1, 1, (n, oh, ow, k)).astype(np.float32) if with_res else None
+    if math == "f16":
+        xs, ws = x.astype(np.float16), wt.astype(np.float16)
+        x_seen, w_seen = xs.astype(np.float32), ws.astype(np.float32)
+        mk, dt = A.MATH_F16, A.HALF
+        res_in = res.astype(np.float16) if with_res else None
+        res_seen = res_in.astype(np.float32) if with_res else None
+    else:
+        xs, ws = x, wt
+        x_seen, w_seen = _tf32_trunc(x), _tf32_trunc(wt)
+        mk, dt = A.MATH_TF32, A.FLOAT
+        res_in = res_seen = res
+    want = oracle.conv_f32_nhwc(x_seen, w_seen, bias, residual=res_seen, beta=1.0, **kw)
+    run = ConvRunner(mk, xs.shape, dt, ws, bias, None, A.FLOAT, res_dtype=(dt if with_res else -1), sum_scale=1.0, **kw)
+    assert run.info()["slab"], run.info()
+    got = run.run(dev(xs), dev(res_in) if with_res else None)
+    torch.cuda.synchronize()
+    max_ratio, max_diff = oracle.tensor_cmp(want, got.cpu().numpy())
+    assert max_diff < 1e-3 or max_ratio <= 1e-3, (max_ratio, max_diff, run.info())

@@ -46,7 +46,7 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128, 1) mma_cost_kernel(uint32_t idesc, int n_mma, int mode, int n_acc, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_cost_kernel(uint32_t idesc, int n_mma, int mode, int n_acc, long long* out, int a_shift_rows = 0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128, 1) mma_cost_kernel(uint32_t idesc, int n_
             mbar_wait(&bar, 0);
             tc_fence_after();
             const uint32_t d1 = tmem + (n_acc > 1 ? 256u : 0u);
-            const uint32_t a_base = (base16 & 0x3FFF) | (1u << 16), b_base = ((base16 + 1024) & 0x3FFF) | (1u << 16);
+            const uint32_t a_base = ((base16 + 8u * a_shift_rows) & 0x3FFF) | (1u << 16), b_base = ((base16 + 1024) & 0x3FFF) | (1u << 16);
             const long long t0 = clock64();
             if (mode == 0) {
                 for (int i = 0; i < n_mma; i += 8) {
@@ -151,6 +151,15 @@ static void run_mma_cost() {
                                    mode ? "TS" : "SS", accs, grid, h[0] / double(n_mma), h[1] / double(n_mma));
                         }
                     }
+    printf("== 1b. same, A descriptor starting `shift` rows (x 128 B) into the tile (i8, M=128, SS)\n");
+    for (int N : {32, 64, 128, 256})
+        for (int shift : {0, 1, 2, 3, 4, 8, 9, 16, 17, 18}) {
+            long long h[2];
+            mma_cost_kernel<KIND_I8><<<1, 128, smem>>>(idesc_for(0, 128, N), 512, 0, 1, d_out, shift);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost));
+            printf("N %-4d shift %-3d : %8.1f clk/MMA\n", N, shift, h[1] / 512.0);
+        }
     cudaFree(d_out);
 }
 
