@@ -767,12 +767,6 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     kp.out_es = out_es;
     kp.res_es = res_es;
 
-    // ---- stride-1 R x S layers: the slab-staged kernel (conv_slab.cu) when it applies
-    if (slab_plan_setup(pl)) {
-        *plan_out = pl;
-        return B200_SUCCESS;
-    }
-
     // ---- pipeline depth: as deep as the k loop needs, within the shared-memory budget. A grid that
     // exceeds one wave keeps two CTAs per SM resident (epilogue of one overlaps the main loop of the
     // other); a sub-wave grid takes the whole SM for latency hiding on its long k loop.
@@ -842,6 +836,19 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     if (stages * sb + fixed_all > MAX_SMEM) { delete pl; return B200_OUT_OF_MEM; }
     kp.stages = stages;
     pl->smem_bytes = stages * sb + fixed_all;
+    // ---- stride-1 R x S layers: the slab-staged kernel (conv_slab.cu) when it applies and its estimate beats this plan's
+    static const bool verbose = [] { const char* e = getenv("B200_SABER_VERBOSE"); return e && e[0] == '1'; }();
+    if (slab_plan_setup(pl)) {
+        if (verbose)
+            fprintf(stderr, "[b200_saber] plan slab  n%d %dx%d c%d k%d %dx%d | tile %dx%d (pitch %d) BN %d grid %ux%u slabs %d groups %d smem %d\n",
+                    d->n, d->h, d->w, d->c, d->k, d->r, d->s, pl->sp.th, pl->sp.tw, pl->sp.PW, pl->bn, pl->grid.x, pl->grid.y,
+                    pl->sp.SA, pl->sp.SB, pl->smem_bytes);
+        *plan_out = pl;
+        return B200_SUCCESS;
+    }
+    if (verbose)
+        fprintf(stderr, "[b200_saber] plan im2col n%d %dx%d c%d k%d %dx%d s%d | BN %d split %d grid %ux%u stages %d smem %d\n",
+                d->n, d->h, d->w, d->c, d->k, d->r, d->s, d->stride_h, bn, split, pl->grid.x, pl->grid.y, stages, pl->smem_bytes);
     *plan_out = pl;
     return B200_SUCCESS;
 }

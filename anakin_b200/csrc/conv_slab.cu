@@ -35,7 +35,7 @@ constexpr int SLAB_MAX_B = 16;   // weight-tile slots
 // smem: [slab ring][weight ring][residual tile][bias | scale][barriers: full_a, empty_a, full_b, empty_b,
 //       tmem_full, res_full][tmem ptr]
 __host__ __device__ constexpr int slab_tail_bytes(int bn) {
-    return 2 * bn * 4 + (2 * SLAB_MAX_A + 2 * SLAB_MAX_B + 2) * 8 + 16;
+    return 2 * bn * 4 + (3 * SLAB_MAX_A + 2 * SLAB_MAX_B + 2) * 8 + 16;
 }
 
 template <int KIND, int BN>
@@ -43,6 +43,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                  const ConvKParams p, const SlabParams sp, const uint32_t idesc) {
+    // KIND_TF32X3: fp32 operands split as x = hi + lo (hi = top 19 bits); D += Ahi*Whi + Alo*Whi + Ahi*Wlo keeps
+    // ~fp32 accuracy on the tf32 tensor pipe. The epilogue warps split every landed slab into a high plane (in place)
+    // and a low plane (behind it) while they would otherwise idle; W is split on the host at pack time.
+    constexpr bool X3 = (KIND == KIND_TF32X3);
+    constexpr int MK = X3 ? KIND_TF32 : KIND;
+    constexpr int PL = X3 ? 2 : 1;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -54,7 +60,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* scale_s = bias_s + BN;
     uint64_t* full_a = reinterpret_cast<uint64_t*>(scale_s + BN);
     uint64_t* empty_a = full_a + SLAB_MAX_A;
-    uint64_t* full_b = empty_a + SLAB_MAX_A;
+    uint64_t* conv_a = empty_a + SLAB_MAX_A;      // X3: "slab split into hi / lo planes"
+    uint64_t* full_b = conv_a + SLAB_MAX_A;
     uint64_t* empty_b = full_b + SLAB_MAX_B;
     uint64_t* tmem_full_bar = empty_b + SLAB_MAX_B;
     uint64_t* res_full_bar = tmem_full_bar + 1;
@@ -89,7 +96,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tma_prefetch_desc(&map_b);
         tma_prefetch_desc(&map_out);
         if (p.res_panels > 0) tma_prefetch_desc(&map_res);
-        for (int i = 0; i < sp.SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < sp.SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); mbar_init(&conv_a[i], EPI_THREADS); }
         for (int i = 0; i < sp.SB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         mbar_init(tmem_full_bar, 1);
         mbar_init(res_full_bar, 1);
@@ -114,7 +121,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t full_b_sa = smem_u32(full_b), empty_b_sa = smem_u32(empty_b);
             const uint32_t slab_sa = smem_u32(slab_ring), bring_sa = smem_u32(b_ring);
             const int total_g = p.CC * p.R;                    // weight groups, consumed in (cc, r) order
-            const uint32_t group_bytes = static_cast<uint32_t>(sp.btile_bytes) * p.S;
+            const uint32_t plane_bytes = static_cast<uint32_t>(sp.btile_bytes) * p.S;   // the S tiles of one plane
+            const uint32_t group_bytes = PL * plane_bytes;
+            const uint32_t slot_a_bytes = PL * static_cast<uint32_t>(sp.slab_bytes);
             const int k_tap = p.CC * p.chunk_el;               // k distance between consecutive taps (tap-major packing)
             // weight group state
             int gb = 0, g_slot = 0, g_r = 0;
@@ -128,6 +137,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 int k = g_k;
                 for (int s2 = 0; s2 < p.S; ++s2) {
                     tma_load_2d_sa(&map_b, bar, dst, k, n0);
+                    if (X3) tma_load_2d_sa(&map_b, bar, dst + plane_bytes, k, p.K + n0);   // the W-low image follows the W-high one
                     dst += sp.btile_bytes;
                     k += k_tap;
                 }
@@ -147,7 +157,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             while (ia < p.CC || gb < total_g) {
                 if (ia < p.CC && (ia < sp.SA || mbar_try_wait_sa(empty_a_sa + 8 * a_slot, a_phase))) {
                     mbar_arrive_expect_tx_sa(full_a_sa + 8 * a_slot, sp.slab_box_bytes);
-                    tma_load_4d_sa(&map_a, full_a_sa + 8 * a_slot, slab_sa + a_slot * sp.slab_bytes, a_c, q0 - p.pad_w,
+                    tma_load_4d_sa(&map_a, full_a_sa + 8 * a_slot, slab_sa + a_slot * slot_a_bytes, a_c, q0 - p.pad_w,
                                    p0 - p.pad_h, n_img);
                     if (ia == 0 && p.res_panels > 0 && own_groups > 0) {
                         // the residual tile is only needed by the epilogue: after the first slab is on its way
@@ -172,7 +182,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t hi = ((8u * p.chunk) >> 4) | (1u << 14) | (lt << 29);   // SBO = 8 rows, version 1, swizzle
             const uint32_t lbo = 1u << 16;
             const uint32_t slab_d0 = (smem_u32(slab_ring) >> 4) | lbo, bring_d0 = (smem_u32(b_ring) >> 4) | lbo;
-            const uint32_t full_a_sa = smem_u32(full_a), empty_a_sa = smem_u32(empty_a);
+            const uint32_t full_a_sa = smem_u32(X3 ? conv_a : full_a), empty_a_sa = smem_u32(empty_a);
             const uint32_t full_b_sa = smem_u32(full_b), empty_b_sa = smem_u32(empty_b);
             const uint32_t row16 = static_cast<uint32_t>(p.chunk) >> 4;            // one slab row in 16-byte units
             const uint32_t slab16 = static_cast<uint32_t>(sp.slab_bytes) >> 4;
@@ -184,7 +194,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int a_slot = 0;
             uint32_t b_full = full_b_sa, b_empty = empty_b_sa, b_desc = bring_d0, b_phase = 0;
             int b_slot = 0;
-            const uint32_t group16 = btile16 * p.S;
+            const uint32_t plane16 = btile16 * p.S;            // X3: the low-plane tiles sit one plane behind the high ones
+            const uint32_t group16 = PL * plane16;
+            const uint32_t slot_a16 = PL * slab16;
 #pragma unroll 1
             for (int cc = 0; cc < p.CC; ++cc) {
                 mbar_wait_sa(a_full, a_phase);
@@ -201,12 +213,22 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll 1
                     for (int s2 = 0; s2 < p.S; ++s2) {
                         // the 32-byte k slices of one chunk: descriptors differ by 2 (x 16 B), independent adds
-                        tc_mma_lohi<KIND>(tmem_base, a_tap, hi, b_tile, hi, idesc, accum);
-                        accum = 1;
-                        if (sp.mma_per_tap > 1) tc_mma_lohi<KIND>(tmem_base, a_tap + 2, hi, b_tile + 2, hi, idesc, 1);
-                        if (sp.mma_per_tap > 2) {
-                            tc_mma_lohi<KIND>(tmem_base, a_tap + 4, hi, b_tile + 4, hi, idesc, 1);
-                            tc_mma_lohi<KIND>(tmem_base, a_tap + 6, hi, b_tile + 6, hi, idesc, 1);
+                        if (!X3) {
+                            tc_mma_lohi<MK>(tmem_base, a_tap, hi, b_tile, hi, idesc, accum);
+                            accum = 1;
+                            if (sp.mma_per_tap > 1) tc_mma_lohi<MK>(tmem_base, a_tap + 2, hi, b_tile + 2, hi, idesc, 1);
+                            if (sp.mma_per_tap > 2) {
+                                tc_mma_lohi<MK>(tmem_base, a_tap + 4, hi, b_tile + 4, hi, idesc, 1);
+                                tc_mma_lohi<MK>(tmem_base, a_tap + 6, hi, b_tile + 6, hi, idesc, 1);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (uint32_t q = 0; q < 2u * sp.mma_per_tap; q += 2) {
+                                tc_mma_lohi<MK>(tmem_base, a_tap + q, hi, b_tile + q, hi, idesc, accum);
+                                accum = 1;
+                                tc_mma_lohi<MK>(tmem_base, a_tap + slab16 + q, hi, b_tile + q, hi, idesc, 1);
+                                tc_mma_lohi<MK>(tmem_base, a_tap + q, hi, b_tile + plane16 + q, hi, idesc, 1);
+                            }
                         }
                         a_tap += row16;
                         b_tile += btile16;
@@ -217,7 +239,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     a_row += pw16;
                 }
                 tc_commit_sa(a_empty);
-                a_full += 8; a_empty += 8; a_desc += slab16;
+                a_full += 8; a_empty += 8; a_desc += slot_a16;
                 if (++a_slot == sp.SA) { a_slot = 0; a_phase ^= 1; a_full = full_a_sa; a_empty = empty_a_sa; a_desc = slab_d0; }
             }
             tc_commit(tmem_full_bar);
@@ -232,6 +254,32 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             scale_s[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0 + i) : 1.f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (X3) {
+            // split every landed fp32 slab in place: hi = top 19 bits, lo = x - hi (exact in fp32)
+            const int etid = threadIdx.x - 64;
+            const int nvec = sp.slab_box_bytes >> 4;
+            int slot = 0;
+            uint32_t phase = 0;
+#pragma unroll 1
+            for (int cc = 0; cc < p.CC; ++cc) {
+                mbar_wait(&full_a[slot], phase);
+                uint4* hi = reinterpret_cast<uint4*>(slab_ring + slot * PL * sp.slab_bytes);
+                uint4* lo = reinterpret_cast<uint4*>(slab_ring + slot * PL * sp.slab_bytes + sp.slab_bytes);
+                for (int i = etid; i < nvec; i += EPI_THREADS) {
+                    uint4 x = hi[i], h, l;
+                    h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
+                    l.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(h.x)));
+                    l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(h.y)));
+                    l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(h.z)));
+                    l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(h.w)));
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's smem reads
+                mbar_arrive(&conv_a[slot]);
+                if (++slot == sp.SA) { slot = 0; phase ^= 1; }
+            }
+        }
         mbar_wait(tmem_full_bar, 0);   // every MMA retired: both operand rings are free
         tc_fence_after();
         if (threadIdx.x == 64) TL(5);
@@ -263,7 +311,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t v0[16];
             tmem_ld_32x32b_x16(t_row + c0, v0);
             tmem_ld_wait();
-            epilogue16<KIND>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
+            epilogue16<MK>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -366,91 +414,56 @@ static bool select_slab_launch(b200_conv_plan* pl) {
 // per-MMA cost in SM clocks (K = 32 bytes, M = 128, both operands in shared memory): measured, tools/probe
 static double mma_clk(int bn) { return bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0; }
 
-// Decide whether the slab variant serves this convolution and set the plan up for it (tile, BN, ring depths, smem).
-// Returns false to leave the plan to the im2col kernel.
-bool slab_plan_setup(b200_conv_plan* pl) {
-    const b200_conv_desc_t& d = pl->desc;
-    const Geometry& g = pl->g;
-    static const bool enabled = [] { const char* e = getenv("B200_SABER_SLAB"); return !(e && e[0] == '0'); }();
-    if (!enabled) return false;
-    if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) { if (atoi(e) > 1) return false; }   // split-K experiments
-    if (d.r * d.s < 2 || d.stride_h != 1 || d.stride_w != 1 || d.dil_h != 1 || d.dil_w != 1) return false;
-    if (d.math == B200_MATH_TF32X3) return false;          // fp32 hi/lo split pass: im2col kernel only (for now)
-    if (g.chunk < 32 || d.s > 16 || d.r > 16) return false;
+// Whole-kernel time estimate (SM clocks) both conv kernels are compared with: a CTA costs its main loop (the slower
+// of MMA issue and L2 ingest at ~38.7 B/clk per SM, tools/probe) + its epilogue + ~6000 clk of fixed latencies
+// (prologue, first TMA round trip, TMEM read-out, store; tools/timeline.py); CTAs beyond one per SM run in turns, two
+// co-resident CTAs overlapping each other's fixed parts at the price of a shared SM.
+static double conv_time_estimate(int ctas, double loop_clk, int bn, int out_es, bool two_per_sm) {
+    const int sms = sm_count();
+    const double cta = loop_clk + bn * (out_es == 4 ? 12.0 : 9.0) + 6000.0;
+    if (ctas <= sms) return cta;
+    const int r = two_per_sm ? 2 : 1;
+    const double turns = static_cast<double>((ctas + sms * r - 1) / (sms * r));
+    return turns * cta * (r == 2 ? 1.25 : 1.0);
+}
+
+namespace {
+struct SlabLayout {
+    SlabParams sp;
+    int bn, smem_bytes, out_pw, out_panels, res_pw, res_panels;
+    bool two_per_sm;
+    double est_clk;
+};
+
+// Shared-memory layout of one (tile, BN) candidate; false when it cannot fit.
+bool slab_layout(const b200_conv_desc_t& d, const Geometry& g, int th, int tw, int bn, SlabLayout* L) {
+    const bool x3 = d.math == B200_MATH_TF32X3;
+    const int planes = x3 ? 2 : 1;
     const int out_es = dtype_size(d.out_dtype);
     const int res_es = d.res_dtype >= 0 ? dtype_size(d.res_dtype) : 0;
-
     SlabParams sp{};
     sp.Ho = g.ho; sp.Wo = g.wo;
-    if (g.wo + d.s - 1 <= BLOCK_M) {
-        sp.tw = g.wo;
-        sp.PW = g.wo + d.s - 1;
-        const int th_max = BLOCK_M / sp.PW;
-        const int tiles = (g.ho + th_max - 1) / th_max;
-        sp.th = (g.ho + tiles - 1) / tiles;                 // equal-height tiles
-    } else {
-        sp.PW = BLOCK_M;
-        sp.tw = BLOCK_M - (d.s - 1);
-        sp.th = 1;
-    }
-    sp.tiles_h = (g.ho + sp.th - 1) / sp.th;
-    sp.tiles_w = (g.wo + sp.tw - 1) / sp.tw;
-    const int tiles = d.n * sp.tiles_h * sp.tiles_w;
+    sp.th = th; sp.tw = tw; sp.PW = tw + d.s - 1;
+    if (sp.th * sp.PW > BLOCK_M || sp.th + d.r - 1 > 256 || sp.PW > 256) return false;
+    sp.tiles_h = (g.ho + th - 1) / th;
+    sp.tiles_w = (g.wo + tw - 1) / tw;
     const int rows_alloc = ((BLOCK_M + (d.r - 1) * sp.PW + (d.s - 1)) + 7) & ~7;
-    sp.slab_bytes = rows_alloc * g.chunk;                   // rows of `chunk` bytes; 8 rows = one swizzle period
-    sp.slab_bytes = (sp.slab_bytes + 1023) & ~1023;
-    sp.slab_box_bytes = (sp.th + d.r - 1) * sp.PW * g.chunk;
-    if ((sp.th + d.r - 1) > 256 || sp.PW > 256) return false;
+    sp.slab_bytes = (rows_alloc * g.chunk + 1023) & ~1023;   // rows of `chunk` bytes; 8 rows = one swizzle period
+    sp.slab_box_bytes = (th + d.r - 1) * sp.PW * g.chunk;
     sp.mma_per_tap = g.chunk / 32;
-    const int RS = d.r * d.s;
-
-    // ---- BN: cheapest estimated CTA time x waves (ingest ~38.7 B/clk per SM vs MMA issue; measured, tools/probe)
-    const int sms = sm_count();
-    const int kr32 = (d.k + 31) / 32 * 32;
-    const int max_bn = (out_es == 4 || res_es == 4) ? 128 : 256;
-    int best_bn = 0;
-    double best_t = 0;
-    const int cands[4] = {32, 64, 128, 256};
-    for (int ci = 0; ci < 4; ++ci) {
-        const int bn = cands[ci];
-        if (bn > max_bn || (bn > kr32 && bn != 32)) continue;
-        const int ctas = tiles * ((d.k + bn - 1) / bn);
-        const double mma = static_cast<double>(g.CC) * RS * sp.mma_per_tap * mma_clk(bn);
-        const double ingest = (static_cast<double>(g.CC) * sp.slab_box_bytes + static_cast<double>(g.CC) * RS * bn * g.chunk) / 38.7;
-        const double epi = 128.0 * bn * 9.0 / 128.0;
-        const double cta = (mma > ingest ? mma : ingest) + epi + 1500.0;
-        const int per_sm = 2;
-        const double waves = static_cast<double>((ctas + sms - 1) / sms);
-        // co-resident CTAs share the SM's ingest port and tensor pipe: a second CTA on the SM costs a full turn
-        const double tt = waves <= 1.0 ? cta : cta * ((ctas + sms * per_sm - 1) / (sms * per_sm)) * per_sm * 0.75;
-        if (best_bn == 0 || tt < best_t) { best_bn = bn; best_t = tt; }
-    }
-    if (const char* e = getenv("B200_SABER_FORCE_BN")) {
-        const int fb = atoi(e);
-        if ((fb == 32 || fb == 64 || fb == 128 || fb == 256) && fb <= max_bn) best_bn = fb;
-    }
-    if (best_bn == 0) return false;
-    const int bn = best_bn;
     sp.btile_bytes = bn * g.chunk;
-
-    // ---- shared memory: slab slots + weight slots (the front of which doubles as the output staging tile)
-    ConvKParams& kp = pl->kp;
-    kp.epi_bn = bn;
-    kp.split = 1;
-    kp.out_es = out_es;
-    kp.res_es = res_es;
-    kp.out_pw = bn * out_es >= 128 ? 128 : bn * out_es;
-    kp.out_panels = bn * out_es / kp.out_pw;
-    kp.res_pw = res_es ? (bn * res_es >= 128 ? 128 : bn * res_es) : 0;
-    kp.res_panels = res_es ? bn * res_es / kp.res_pw : 0;
+    L->bn = bn;
+    L->out_pw = bn * out_es >= 128 ? 128 : bn * out_es;
+    L->out_panels = bn * out_es / L->out_pw;
+    L->res_pw = res_es ? (bn * res_es >= 128 ? 128 : bn * res_es) : 0;
+    L->res_panels = res_es ? bn * res_es / L->res_pw : 0;
     const int staging = BLOCK_M * bn * out_es;
-    const int res_bytes = BLOCK_M * bn * res_es;
-    const int fixed = res_bytes + slab_tail_bytes(bn) + 1024;
-    const int half_budget = MAX_SMEM / 2 - 2048;
-    // a weight-ring slot holds one GROUP: the S taps of one filter row of one chunk
-    const int group_bytes = d.s * sp.btile_bytes;
+    const int fixed = BLOCK_M * bn * res_es + slab_tail_bytes(bn) + 1024;
+    const int slot_a = planes * sp.slab_bytes;                       // x3: the low plane follows the high plane
+    const int slot_b = planes * d.s * sp.btile_bytes;                // one group: the S taps of a filter row (x3: hi + lo)
     const int total_groups = g.CC * d.r;
-    auto fits = [&](int sa, int sb, int budget) { return sa * sp.slab_bytes + sb * group_bytes + fixed <= budget; };
+    auto fits = [&](int sa, int sb, int budget) { return sa * slot_a + sb * slot_b + fixed <= budget; };
+    const int half_budget = MAX_SMEM / 2 - 2048;
     int sa = g.CC < 2 ? 1 : 2;
     int sb = total_groups < 3 ? total_groups : 3;
     int budget = half_budget;
@@ -461,25 +474,113 @@ bool slab_plan_setup(b200_conv_plan* pl) {
         while (sb > 1 && !fits(sa, sb, budget)) --sb;
         if (!fits(sa, sb, budget)) return false;
     }
-    // use what is left of the budget: deeper weight ring first (it hides the L2 latency of the k loop), then slabs
+    // what is left of the budget: a deeper weight ring first (it hides the L2 latency of the k loop), then slabs
     while (sb < SLAB_MAX_B && sb < total_groups && fits(sa, sb + 1, budget)) ++sb;
     while (sa < SLAB_MAX_A && sa < g.CC && fits(sa + 1, sb, budget)) ++sa;
-    int ring = sa * sp.slab_bytes + sb * group_bytes;
+    int ring = sa * slot_a + sb * slot_b;
     if (ring < staging) {   // the staging tile must fit in the rings it reuses
-        const int extra = (staging - ring + group_bytes - 1) / group_bytes;
+        const int extra = (staging - ring + slot_b - 1) / slot_b;
         if (sb + extra > SLAB_MAX_B || !fits(sa, sb + extra, MAX_SMEM)) return false;
         sb += extra;
-        ring = sa * sp.slab_bytes + sb * group_bytes;
+        ring = sa * slot_a + sb * slot_b;
+        if (ring + fixed > half_budget) budget = MAX_SMEM;
     }
     sp.SA = sa; sp.SB = sb;
     sp.a_off = 0;
-    sp.b_off = sa * sp.slab_bytes;
+    sp.b_off = sa * slot_a;
     sp.epi_off = ring;
-    pl->smem_bytes = ring + fixed;
-    if (pl->smem_bytes > MAX_SMEM) return false;
+    L->smem_bytes = ring + fixed;
+    if (L->smem_bytes > MAX_SMEM) return false;
+    L->two_per_sm = L->smem_bytes <= half_budget + 2048;
+    L->sp = sp;
 
+    // ---- estimated time (SM clocks)
+    const int RS = d.r * d.s;
+    const int ctas = d.n * sp.tiles_h * sp.tiles_w * ((d.k + bn - 1) / bn);
+    const double mma = static_cast<double>(g.CC) * RS * sp.mma_per_tap * (x3 ? 3 : 1) * mma_clk(bn);
+    const double ingest = static_cast<double>(g.CC) * (sp.slab_box_bytes + static_cast<double>(planes) * RS * bn * g.chunk) / 38.7;
+    double loop = mma > ingest ? mma : ingest;
+    if ((sa < 2 && g.CC > 1) || sb < 2) loop = mma + ingest;          // no double buffering: load and MMA serialise
+    L->est_clk = conv_time_estimate(ctas, loop, bn, out_es, L->two_per_sm);
+    return true;
+}
+}  // namespace
+
+// Decide whether the slab variant serves this convolution and set the plan up for it (tile, BN, ring depths, smem).
+// Returns false to leave the plan to the im2col kernel.
+bool slab_plan_setup(b200_conv_plan* pl) {
+    const b200_conv_desc_t& d = pl->desc;
+    const Geometry& g = pl->g;
+    // B200_SABER_SLAB: 0 never, 2 whenever it applies (tests), default: when its time estimate beats the im2col plan's
+    const char* slab_env = getenv("B200_SABER_SLAB");
+    if (slab_env && slab_env[0] == '0') return false;
+    if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) { if (atoi(e) > 1) return false; }   // split-K experiments
+    if (d.r * d.s < 2 || d.stride_h != 1 || d.stride_w != 1 || d.dil_h != 1 || d.dil_w != 1) return false;
+    if (g.chunk < 32 || d.s > 16 || d.r > 16) return false;
+    const int out_es = dtype_size(d.out_dtype);
+    const int res_es = d.res_dtype >= 0 ? dtype_size(d.res_dtype) : 0;
+
+    // ---- candidates: tile width = the row (or an equal part of it), tile height = what fits 128 GEMM rows, every
+    // tile width of the kernel; the estimate weighs halo re-reads, weight re-reads per tile, MMA width and waves
+    const int kr32 = (d.k + 31) / 32 * 32;
+    const int max_bn = (out_es == 4 || res_es == 4) ? 128 : 256;
+    int force_bn = 0;
+    if (const char* e = getenv("B200_SABER_FORCE_BN")) {
+        const int fb = atoi(e);
+        if ((fb == 32 || fb == 64 || fb == 128 || fb == 256) && fb <= max_bn) force_bn = fb;
+    }
+    SlabLayout best{};
+    bool have = false;
+    const int parts[8] = {1, 2, 3, 4, 6, 8, 12, 16};
+    for (int pi = 0; pi < 8; ++pi) {
+        const int tw = (g.wo + parts[pi] - 1) / parts[pi];
+        const int PW = tw + d.s - 1;
+        if (PW > BLOCK_M) continue;
+        if (pi > 0 && tw < 8) break;
+        const int th_max = BLOCK_M / PW < g.ho ? BLOCK_M / PW : g.ho;
+        if (th_max < 1) continue;
+        const int tiles_h = (g.ho + th_max - 1) / th_max;
+        const int th = (g.ho + tiles_h - 1) / tiles_h;          // equal-height tiles
+        const int cands[4] = {32, 64, 128, 256};
+        for (int ci = 0; ci < 4; ++ci) {
+            const int bn = cands[ci];
+            if (force_bn ? bn != force_bn : (bn > max_bn || (bn > kr32 && bn != 32))) continue;
+            SlabLayout L{};
+            if (!slab_layout(d, g, th, tw, bn, &L)) continue;
+            if (!have || L.est_clk < best.est_clk) { best = L; have = true; }
+        }
+    }
+    if (!have) return false;
+    {
+        // the complete im2col plan (pl->bn, grid, stages, smem): A is fetched once per tap; a ring of fewer than three
+        // stages cannot overlap loads and MMAs
+        const bool x3 = d.math == B200_MATH_TF32X3;
+        const double k_bytes = static_cast<double>(g.KS) * g.chunk;
+        const int bn0 = pl->bn;
+        const double mma0 = k_bytes / 32.0 * (x3 ? 3 : 1) * mma_clk(bn0);
+        const double ingest0 = (BLOCK_M + (x3 ? 2.0 : 1.0) * bn0) * k_bytes / 38.7;
+        double loop0 = mma0 > ingest0 ? mma0 : ingest0;
+        if (pl->kp.stages < 3) loop0 = mma0 + ingest0;
+        const int split0 = static_cast<int>(pl->grid.z);           // split-K cluster: the k loop is shared, plus the exchange
+        if (split0 > 1) loop0 = loop0 / split0 + 2500.0;
+        const double est0 = conv_time_estimate(static_cast<int>(pl->grid.x * pl->grid.y * pl->grid.z), loop0, bn0, out_es,
+                                               pl->smem_bytes <= MAX_SMEM / 2);
+        const bool force = slab_env && slab_env[0] == '2';
+        if (!force && !force_bn && est0 <= best.est_clk) return false;
+    }
+
+    ConvKParams& kp = pl->kp;
+    kp.epi_bn = best.bn;
+    kp.split = 1;
+    kp.out_es = out_es;
+    kp.res_es = res_es;
+    kp.out_pw = best.out_pw; kp.out_panels = best.out_panels;
+    kp.res_pw = best.res_pw; kp.res_panels = best.res_panels;
+    pl->smem_bytes = best.smem_bytes;
+    const SlabParams& sp = best.sp;
+    const int bn = best.bn;
     pl->bn = bn;
-    pl->grid = dim3(tiles, (d.k + bn - 1) / bn, 1);
+    pl->grid = dim3(d.n * sp.tiles_h * sp.tiles_w, (d.k + bn - 1) / bn, 1);
     bool ok = false;
     uint32_t a_fmt = 0, b_fmt = 0, c_fmt = 1;
     if (d.math == B200_MATH_I8) {
@@ -487,6 +588,9 @@ bool slab_plan_setup(b200_conv_plan* pl) {
         a_fmt = (d.in_dtype == B200_INT8) ? 1u : 0u; b_fmt = 1u; c_fmt = 2u;
     } else if (d.math == B200_MATH_F16) {
         ok = select_slab_launch<KIND_F16>(pl);
+    } else if (d.math == B200_MATH_TF32X3) {
+        ok = select_slab_launch<KIND_TF32X3>(pl);
+        a_fmt = b_fmt = 2u;
     } else {
         ok = select_slab_launch<KIND_TF32>(pl);
         a_fmt = b_fmt = 2u;

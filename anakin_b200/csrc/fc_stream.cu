@@ -1,0 +1,507 @@
+// Weight-streaming fully-connected layer for small row counts, and the fused classifier head.
+//
+// Replaces SaberFc<NV,*> (saber/funcs/impl/cuda/base/cuda_c/saber_fc.cu:17-195, ker_gemm.cu:8-186, cuBLAS sgemm) for
+// m <= 16 rows: with a handful of rows an inner-product layer is a stream of its weights (VGG16 fc6: 411 MB of fp32)
+// past a few vectors, so the right machine is the load path, not the tensor core -- a 128-row MMA tile would carry 4
+// live rows and the error-compensated fp32 tensor path would read the weights twice. Every weight byte is read exactly
+// once, 16 bytes per lane, by warps that each keep R output rows x 8 input rows of accumulators in registers; the input
+// rows are staged per K chunk in shared memory and shared by the CTA's 8 warps.
+//   int8 : dp4a (u8|s8 x s8 -> s32), exact, then the x86 Saber epilogue of the conv kernels
+//          (f = (acc + bias) * scale, relu, rne + saturate) -- bit-identical to the tcgen05 path.
+//   f16  : fp32 accumulation of exact products;   f32: FFMA.
+//
+// b200_head_run: global pooling + inner product + softmax of an INT8 classification head in ONE launch (k-split
+// integer reduction, last CTA finishes), replacing three dependent launches
+// (saber_pooling.cu, saber_fc.cu, saber_softmax.cu) at the latency-critical end of every request.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/b200_saber.h"
+#include "common.cuh"
+#include "softmax.cuh"
+
+namespace b200 {
+
+constexpr int FC_THREADS = 256;
+constexpr int FC_WARPS = FC_THREADS / 32;
+constexpr int FC_MT = 8;                  // input rows handled per pass
+constexpr int FC_X_BYTES = 16 * 1024;     // one staged input chunk (two buffers): up to FC_MT rows x its K elements
+
+struct FcParams {
+    const void* x;        // [m][ldx] operand dtype
+    const void* w;        // [n][k] operand dtype, k contiguous (k = ldx: stored-K order, zero weights on padding)
+    const float* bias;    // [n] or null
+    const float* scale;   // [n] (int8) or null
+    void* out;            // [m][ldo]
+    int m, k, n, ldx, ldo;
+    int in_unsigned;      // int8: x is u8
+    int out_dtype;        // B200_FLOAT | B200_HALF | B200_INT8 | B200_UINT8
+    int relu;
+    float neg_slope;
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8, uint32_t b_s8, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8), "r"(b_s8), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_ss(uint32_t a_s8, uint32_t b_s8, int c) {
+    int d;
+    asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s8), "r"(b_s8), "r"(c));
+    return d;
+}
+
+// MODE 0: int8 (accumulate s32), 1: f16 (accumulate f32), 2: f32.
+template <int MODE>
+struct FcAcc { typedef float type; };
+template <>
+struct FcAcc<0> { typedef int type; };
+
+template <int MODE>
+__device__ __forceinline__ void fc_dot(typename FcAcc<MODE>::type& acc, const uint4& xv, const uint4& wv, bool x_unsigned) {
+    if constexpr (MODE == 0) {
+        if (x_unsigned) {
+            acc = dp4a_us(xv.x, wv.x, acc); acc = dp4a_us(xv.y, wv.y, acc);
+            acc = dp4a_us(xv.z, wv.z, acc); acc = dp4a_us(xv.w, wv.w, acc);
+        } else {
+            acc = dp4a_ss(xv.x, wv.x, acc); acc = dp4a_ss(xv.y, wv.y, acc);
+            acc = dp4a_ss(xv.z, wv.z, acc); acc = dp4a_ss(xv.w, wv.w, acc);
+        }
+    } else if constexpr (MODE == 1) {
+        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 a = __half22float2(xh[i]), b = __half22float2(wh[i]);
+            acc = __fmaf_rn(a.x, b.x, acc);
+            acc = __fmaf_rn(a.y, b.y, acc);
+        }
+    } else {
+        acc = __fmaf_rn(__uint_as_float(xv.x), __uint_as_float(wv.x), acc);
+        acc = __fmaf_rn(__uint_as_float(xv.y), __uint_as_float(wv.y), acc);
+        acc = __fmaf_rn(__uint_as_float(xv.z), __uint_as_float(wv.z), acc);
+        acc = __fmaf_rn(__uint_as_float(xv.w), __uint_as_float(wv.w), acc);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void fc_store(const FcParams& p, int mi, int row, typename FcAcc<MODE>::type acc) {
+    float f;
+    if constexpr (MODE == 0) {
+        // x86 Saber int8 epilogue, as epilogue16_i8 of the conv kernels: add, then multiply, each rounded
+        f = __fmul_rn(__fadd_rn(__int2float_rn(acc), p.bias ? __ldg(p.bias + row) : 0.f), p.scale ? __ldg(p.scale + row) : 1.f);
+        if (p.relu) f = fmaxf(f, 0.f);
+    } else {
+        f = __fadd_rn(acc, p.bias ? __ldg(p.bias + row) : 0.f);
+        if (p.relu) f = f > 0.f ? f : __fmul_rn(f, p.neg_slope);
+    }
+    const size_t o = static_cast<size_t>(mi) * p.ldo + row;
+    if (p.out_dtype == B200_FLOAT) {
+        static_cast<float*>(p.out)[o] = f;
+    } else if (p.out_dtype == B200_HALF) {
+        static_cast<__half*>(p.out)[o] = __float2half_rn(f);
+    } else if (p.out_dtype == B200_UINT8) {
+        uint32_t c;
+        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(c) : "f"(f));
+        static_cast<uint8_t*>(p.out)[o] = static_cast<uint8_t>(c);
+    } else {
+        int32_t c;
+        asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(c) : "f"(f));
+        static_cast<int8_t*>(p.out)[o] = static_cast<int8_t>(c);
+    }
+}
+
+// The inner-product body: CTA `cta` of `ncta` takes the row blocks cta, cta + ncta, ... ; each of its 8 warps owns
+// R consecutive output rows of the block. smem_x: 2 x FC_X_BYTES bytes -- the input rows are staged per K chunk with
+// cp.async, chunk c+1 while chunk c is being multiplied, so the weight stream never waits for them.
+template <int MODE, int R>
+__device__ __forceinline__ void fc_body(const FcParams& p, uint8_t* smem_x, int cta, int ncta) {
+    constexpr int ES = MODE == 0 ? 1 : (MODE == 1 ? 2 : 4);
+    constexpr int VEC = 16 / ES;                     // elements per 16-byte vector
+    typedef typename FcAcc<MODE>::type acc_t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows_per_block = FC_WARPS * R;
+    const int nblocks = (p.n + rows_per_block - 1) / rows_per_block;
+    for (int m0 = 0; m0 < p.m; m0 += FC_MT) {
+        const int mt = min(FC_MT, p.m - m0);
+        // chunk length: the staged rows fill one buffer (more rows -> shorter chunks), whole 16-byte vectors
+        const int kc_len = (FC_X_BYTES / (mt * 16)) * VEC;
+        const int nchunks = (p.k + kc_len - 1) / kc_len;
+        const int row_vecs = kc_len / VEC;           // vectors per staged row
+        auto stage = [&](int buf, int c) {
+            const int kc = c * kc_len;
+            const int nv = min(kc_len, p.k - kc) / VEC;
+            const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_x + buf * FC_X_BYTES));
+            for (int i = threadIdx.x; i < mt * nv; i += FC_THREADS) {
+                const int mi = i / nv, v = i - mi * nv;
+                const void* src = static_cast<const uint8_t*>(p.x) + (static_cast<size_t>(m0 + mi) * p.ldx + kc) * ES + v * 16;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (mi * row_vecs + v) * 16), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int blk = cta; blk < nblocks; blk += ncta) {
+            const int row0 = blk * rows_per_block + warp * R;
+            acc_t acc[FC_MT][R];
+#pragma unroll
+            for (int mi = 0; mi < FC_MT; ++mi)
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[mi][r] = 0;
+            __syncthreads();                              // both buffers are free
+            stage(0, 0);
+            for (int c = 0; c < nchunks; ++c) {
+                if (c + 1 < nchunks) {
+                    stage((c + 1) & 1, c + 1);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
+                __syncthreads();                          // chunk c has landed for everybody
+                const int kc = c * kc_len;
+                const int nv = min(kc_len, p.k - kc) / VEC;
+                const uint4* xs = reinterpret_cast<const uint4*>(smem_x + (c & 1) * FC_X_BYTES);
+                if (row0 < p.n) {
+                    const uint4* wrow[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        wrow[r] = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.w) +
+                                                                 (static_cast<size_t>(min(row0 + r, p.n - 1)) * p.k + kc) * ES);
+                    // U vectors per row in flight per lane before any arithmetic: the layer is a stream, and what
+                    // streams it at HBM speed is bytes in flight (R x U x 512 B per warp), not issue rate
+                    constexpr int U = 8 / R;
+                    int v = lane;
+                    for (; v + 32 * (U - 1) < nv; v += 32 * U) {
+                        uint4 wv[R][U];
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int u = 0; u < U; ++u) wv[r][u] = ldg_stream(wrow[r] + v + 32 * u);
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+#pragma unroll
+                            for (int mi = 0; mi < FC_MT; ++mi) {
+                                if (mi < mt) {
+                                    const uint4 xv = xs[mi * row_vecs + v + 32 * u];
+#pragma unroll
+                                    for (int r = 0; r < R; ++r) fc_dot<MODE>(acc[mi][r], xv, wv[r][u], p.in_unsigned != 0);
+                                }
+                            }
+                    }
+                    for (; v < nv; v += 32) {
+                        uint4 wv[R];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) wv[r] = ldg_stream(wrow[r] + v);
+#pragma unroll
+                        for (int mi = 0; mi < FC_MT; ++mi) {
+                            if (mi < mt) {
+                                const uint4 xv = xs[mi * row_vecs + v];
+#pragma unroll
+                                for (int r = 0; r < R; ++r) fc_dot<MODE>(acc[mi][r], xv, wv[r], p.in_unsigned != 0);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();                          // chunk c is consumed: its buffer may be refilled
+            }
+            // lanes hold partial sums over their k vectors: butterfly, then lane 0 finishes the R x mt outputs
+            if (row0 < p.n) {
+#pragma unroll
+                for (int mi = 0; mi < FC_MT; ++mi)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc_t a = acc[mi][r];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                        acc[mi][r] = a;
+                    }
+                if (lane == 0) {
+#pragma unroll
+                    for (int mi = 0; mi < FC_MT; ++mi)
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (mi < mt && row0 + r < p.n) fc_store<MODE>(p, m0 + mi, row0 + r, acc[mi][r]);
+                }
+            }
+        }
+    }
+}
+
+template <int MODE, int R>
+__global__ void __launch_bounds__(FC_THREADS) fc_stream_kernel(const FcParams p) {
+    __shared__ __align__(16) uint8_t smem_x[2 * FC_X_BYTES];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    fc_body<MODE, R>(p, smem_x, blockIdx.x, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------ fused head
+// INT8 classifier head in one launch WITHOUT grid barriers: the reduction dimension is split over the CTAs. CTA j owns
+// a slice of the channels: it pools exactly those channels of every image (no redundancy), multiplies them with its
+// slice of every weight row, and adds the integer partial sums into an s32 accumulator [m][n] with fire-and-forget
+// reductions -- integer addition is exact and order-free, so the result is deterministic and bit-identical to the
+// separate ops. Each CTA then takes a ticket; the last one to finish applies the x86 Saber epilogue
+// ((acc + bias) * scale), writes the fp32 logits, runs the softmax and leaves accumulator and ticket counter zeroed
+// for the next launch. No CTA ever waits for another one, so nothing depends on co-residency.
+struct HeadParams {
+    const uint8_t* in;    // NHWC [m][hw][c]  u8 | s8
+    uint8_t* pooled;      // [m][c]           same dtype (the pooling op's output tensor)
+    const int8_t* w;      // [n][c]
+    const float* bias;
+    const float* scale;
+    float* logits;        // [m][ldo]
+    float* prob;          // [m][ldp] or null
+    int32_t* acc;         // [m][n] s32, zero between launches
+    unsigned* ticket;     // zero between launches
+    int m, hw, c, n, ldo, ldp;
+    int in_unsigned, pool_max;
+    int vec_per_cta;      // 16-byte channel vectors per CTA
+};
+
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_MAX_M = 8;
+constexpr int HEAD_MAX_VEC = 4;       // 16-byte vectors per CTA slice (<= 64 channels)
+constexpr int HEAD_PARTS = 8;         // pixel groups per (image, vector) task
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_i8_kernel(const HeadParams h) {
+    __shared__ int32_t part[HEAD_MAX_M * HEAD_MAX_VEC * HEAD_PARTS][16];
+    __shared__ __align__(16) uint8_t xs[HEAD_MAX_M][HEAD_MAX_VEC * 16];
+    __shared__ unsigned is_last;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int cv = h.c >> 4;                                   // vectors per pixel
+    const int v0 = blockIdx.x * h.vec_per_cta;
+    const int nvec = min(h.vec_per_cta, cv - v0);
+    const int tid = threadIdx.x;
+    // ---- 1. pool this CTA's channels: task = (image, vector, pixel group), exact integer sums / maxima
+    const int tasks = h.m * nvec * HEAD_PARTS;
+    if (tid < tasks) {
+        const int pg = tid % HEAD_PARTS, t2 = tid / HEAD_PARTS;
+        const int v = t2 % nvec, mi = t2 / nvec;
+        const uint4* src = reinterpret_cast<const uint4*>(h.in) + static_cast<size_t>(mi) * h.hw * cv + v0 + v;
+        int32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = h.pool_max ? INT32_MIN : 0;
+        for (int t = pg; t < h.hw; t += HEAD_PARTS) {
+            const uint4 y = __ldg(src + static_cast<size_t>(t) * cv);
+            const uint32_t w4[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t b = (w4[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                const int32_t val = h.in_unsigned ? static_cast<int32_t>(b) : static_cast<int32_t>(static_cast<int8_t>(b));
+                r[j] = h.pool_max ? max(r[j], val) : r[j] + val;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) part[tid][j] = r[j];
+    }
+    __syncthreads();
+    for (int e = tid; e < h.m * nvec * 16; e += HEAD_THREADS) {
+        const int j = e & 15, t2 = e >> 4;                     // t2 = mi * nvec + v
+        int32_t sum = h.pool_max ? INT32_MIN : 0;
+        for (int pg = 0; pg < HEAD_PARTS; ++pg) {
+            const int32_t x = part[t2 * HEAD_PARTS + pg][j];
+            sum = h.pool_max ? max(sum, x) : sum + x;
+        }
+        // saber_pooling int8: fp32 sum (exact here) / window, rounded to nearest even, saturated
+        const float q = h.pool_max ? static_cast<float>(sum) : __fdiv_rn(static_cast<float>(sum), static_cast<float>(h.hw));
+        uint32_t code;
+        if (h.in_unsigned) asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(code) : "f"(q));
+        else { int32_t sc; asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(sc) : "f"(q)); code = static_cast<uint32_t>(sc) & 0xffu; }
+        const int v = t2 % nvec, mi = t2 / nvec;
+        xs[mi][v * 16 + j] = static_cast<uint8_t>(code);
+        h.pooled[static_cast<size_t>(mi) * h.c + (v0 + v) * 16 + j] = static_cast<uint8_t>(code);
+    }
+    __syncthreads();
+    // ---- 2. partial inner products over this slice, added into the s32 accumulator
+    for (int row = tid; row < h.n; row += HEAD_THREADS) {
+        const uint4* wr = reinterpret_cast<const uint4*>(h.w + static_cast<size_t>(row) * h.c) + v0;
+        uint4 wv[HEAD_MAX_VEC];
+#pragma unroll
+        for (int v = 0; v < HEAD_MAX_VEC; ++v) wv[v] = v < nvec ? ldg_stream(wr + v) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int mi = 0; mi < HEAD_MAX_M; ++mi) {
+            if (mi < h.m) {
+                int a = 0;
+#pragma unroll
+                for (int v = 0; v < HEAD_MAX_VEC; ++v) {
+                    if (v < nvec) {
+                        const uint4 xv = *reinterpret_cast<const uint4*>(&xs[mi][v * 16]);
+                        if (h.in_unsigned) {
+                            a = dp4a_us(xv.x, wv[v].x, a); a = dp4a_us(xv.y, wv[v].y, a);
+                            a = dp4a_us(xv.z, wv[v].z, a); a = dp4a_us(xv.w, wv[v].w, a);
+                        } else {
+                            a = dp4a_ss(xv.x, wv[v].x, a); a = dp4a_ss(xv.y, wv[v].y, a);
+                            a = dp4a_ss(xv.z, wv[v].z, a); a = dp4a_ss(xv.w, wv[v].w, a);
+                        }
+                    }
+                }
+                asm volatile("red.global.add.s32 [%0], %1;" ::"l"(h.acc + static_cast<size_t>(mi) * h.n + row), "r"(a) : "memory");
+            }
+        }
+    }
+    // ---- 3. ticket: the last CTA finishes the head
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(h.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int idx = tid; idx < h.m * h.n; idx += HEAD_THREADS) {
+        const int mi = idx / h.n, row = idx - mi * h.n;
+        int32_t a;
+        asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(a) : "l"(h.acc + idx) : "memory");
+        h.acc[idx] = 0;                                           // clean for the next launch
+        // x86 Saber int8 epilogue, as epilogue16_i8 of the conv kernels: add, then multiply, each rounded
+        const float f = __fmul_rn(__fadd_rn(__int2float_rn(a), h.bias ? __ldg(h.bias + row) : 0.f), h.scale ? __ldg(h.scale + row) : 1.f);
+        h.logits[static_cast<size_t>(mi) * h.ldo + row] = f;
+    }
+    if (tid == 0) *h.ticket = 0;
+    __syncthreads();
+    if (h.prob == nullptr) return;
+    // softmax: the CTA takes the rows one after the other with the block routine of softmax_rows_kernel
+    __shared__ float red[SOFTMAX_THREADS / 32];
+    for (int row = 0; row < h.m; ++row)
+        softmax_row_block(h.logits + static_cast<size_t>(row) * h.ldo, h.prob + static_cast<size_t>(row) * h.ldp, h.n, red);
+}
+
+static int fc_mode(int math) { return math == B200_MATH_I8 ? 0 : (math == B200_MATH_F16 ? 1 : 2); }
+
+// rows per warp: two CTAs per SM first (bytes in flight), then fewer input re-stagings
+static int fc_rows_per_warp(int n) {
+    const int sms = sm_count();
+    if (n >= FC_WARPS * 4 * 2 * sms) return 4;
+    if (n >= FC_WARPS * 2 * 2 * sms) return 2;
+    return 1;
+}
+
+template <int MODE>
+static void launch_fc(const FcParams& p, int r, unsigned grid, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(FC_THREADS);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (r == 4) cudaLaunchKernelEx(&cfg, fc_stream_kernel<MODE, 4>, p);
+    else if (r == 2) cudaLaunchKernelEx(&cfg, fc_stream_kernel<MODE, 2>, p);
+    else cudaLaunchKernelEx(&cfg, fc_stream_kernel<MODE, 1>, p);
+}
+
+static bool fc_args_ok(const b200_fc_stream_desc_t* d) {
+    if (!d || d->m <= 0 || d->k <= 0 || d->n_out <= 0 || d->ldx < d->k || d->ldo < d->n_out) return false;
+    const int es = d->math == B200_MATH_I8 ? 1 : (d->math == B200_MATH_F16 ? 2 : 4);
+    if ((static_cast<int64_t>(d->k) * es) % 16 != 0 || (static_cast<int64_t>(d->ldx) * es) % 16 != 0) return false;
+    if (d->math == B200_MATH_I8 && !(d->in_dtype == B200_INT8 || d->in_dtype == B200_UINT8)) return false;
+    if (d->math == B200_MATH_F16 && d->in_dtype != B200_HALF) return false;
+    if ((d->math == B200_MATH_TF32 || d->math == B200_MATH_TF32X3) && d->in_dtype != B200_FLOAT) return false;
+    return true;
+}
+
+static FcParams make_fc_params(const b200_fc_stream_desc_t* d, const void* x, const void* w, const float* bias, const float* scale,
+                               void* out) {
+    FcParams p{};
+    p.x = x; p.w = w; p.bias = bias; p.scale = scale; p.out = out;
+    p.m = d->m; p.k = d->k; p.n = d->n_out; p.ldx = d->ldx; p.ldo = d->ldo;
+    p.in_unsigned = d->in_dtype == B200_UINT8 ? 1 : 0;
+    p.out_dtype = d->out_dtype;
+    p.relu = d->relu; p.neg_slope = d->neg_slope;
+    return p;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_fc_stream_max_rows(void) { return 2 * FC_MT; }
+
+int b200_fc_stream_run(const b200_fc_stream_desc_t* d, const void* x, const void* w_plain, const float* bias, const float* scale,
+                       void* out, void* stream) {
+    if (!fc_args_ok(d) || !x || !w_plain || !out) return B200_INVALID_VALUE;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    const FcParams p = make_fc_params(d, x, w_plain, bias, scale, out);
+    const int r = fc_rows_per_warp(p.n);
+    const int nblocks = (p.n + FC_WARPS * r - 1) / (FC_WARPS * r);
+    const unsigned grid = static_cast<unsigned>(nblocks < 2 * sm_count() ? nblocks : 2 * sm_count());
+    const int mode = fc_mode(d->math);
+    if (mode == 0) launch_fc<0>(p, r, grid, static_cast<cudaStream_t>(stream));
+    else if (mode == 1) launch_fc<1>(p, r, grid, static_cast<cudaStream_t>(stream));
+    else launch_fc<2>(p, r, grid, static_cast<cudaStream_t>(stream));
+    count_launch();
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[b200_saber] fc_stream launch failed: %s\n", cudaGetErrorString(e));
+        return B200_UNKNOWN_ERROR;
+    }
+    return B200_SUCCESS;
+}
+
+size_t b200_head_workspace_bytes(const b200_head_desc_t* hd) {
+    if (!hd) return 0;
+    return (static_cast<size_t>(hd->fc.m) * hd->fc.n_out + 4) * sizeof(int32_t);   // s32 accumulator + ticket word
+}
+
+int b200_head_run(const b200_head_desc_t* hd, const void* in, void* pooled, const void* w_plain, const float* bias,
+                  const float* scale, void* logits, float* prob, void* workspace, void* stream) {
+    if (!hd || !in || !pooled || !w_plain || !logits || !workspace) return B200_INVALID_VALUE;
+    const b200_fc_stream_desc_t* d = &hd->fc;
+    if (!fc_args_ok(d) || hd->hw <= 0 || d->ldx != d->k) return B200_INVALID_VALUE;
+    // integer partial sums make the k-split reduction exact and order-free: int8 nets only (float heads keep the
+    // three separate ops), fp32 logits out, at most 8 rows
+    if (d->math != B200_MATH_I8 || d->out_dtype != B200_FLOAT || d->m > HEAD_MAX_M || d->relu) return B200_UNIMPL_ERROR;
+    if (!device_is_sm100()) return B200_WRONG_DEVICE;
+    HeadParams h{};
+    h.in = static_cast<const uint8_t*>(in);
+    h.pooled = static_cast<uint8_t*>(pooled);
+    h.w = static_cast<const int8_t*>(w_plain);
+    h.bias = bias; h.scale = scale;
+    h.logits = static_cast<float*>(logits);
+    h.prob = prob;
+    h.acc = static_cast<int32_t*>(workspace);
+    h.ticket = reinterpret_cast<unsigned*>(h.acc + static_cast<size_t>(d->m) * d->n_out);
+    h.m = d->m; h.hw = hd->hw; h.c = d->k; h.n = d->n_out; h.ldo = d->ldo; h.ldp = hd->ldp;
+    h.in_unsigned = d->in_dtype == B200_UINT8 ? 1 : 0;
+    h.pool_max = hd->pool_max;
+    const int cv = d->k / 16;
+    // slice width: as many CTAs as the 256-thread pooling stage allows (m * vectors * 8 pixel groups <= 256)
+    int vpc = HEAD_THREADS / (HEAD_PARTS * d->m);
+    if (vpc > HEAD_MAX_VEC) vpc = HEAD_MAX_VEC;
+    if (vpc < 1) return B200_UNIMPL_ERROR;
+    while (vpc > 1 && (cv + vpc - 1) / vpc < 64) --vpc;      // keep at least ~64 CTAs busy
+    h.vec_per_cta = vpc;
+    const unsigned grid = static_cast<unsigned>((cv + vpc - 1) / vpc);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(HEAD_THREADS);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, head_i8_kernel, h);
+    count_launch();
+    if (e == cudaSuccess) e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[b200_saber] head launch failed: %s\n", cudaGetErrorString(e));
+        return B200_UNKNOWN_ERROR;
+    }
+    return B200_SUCCESS;
+}
+
+}  // extern "C"

@@ -183,10 +183,48 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
         if (!st) return Status::ANAKINFAIL("Init(" + e.name + "): " + st.info());
         _exec.push_back(e);
     }
+    plan_fused_head();
     // weight uploads and the zero fills above used synchronous copies / this stream: nothing is pending after this
     CUDA_CHECK(cudaStreamSynchronize(_stream));
     CUDA_CHECK(cudaDeviceSynchronize());
     return Status::OK();
+}
+
+// Classifier head: global pooling -> inner product -> softmax, three dependent launches of a few microseconds each at
+// the end of every request (saber_pooling.cu, saber_fc.cu, saber_softmax.cu), run as ONE cooperative launch
+// (b200_head_run). Every edge tensor of the three ops is still written, so the fusion is invisible to readers.
+void NetCore::plan_fused_head() {
+    _head.on = false;
+    // Opt-in (B200_ANAKIN_FUSED_HEAD=1): measured on ResNet-50 INT8 b8 the single launch takes 37 us -- 512 K integer
+    // reductions into 8000 accumulators run at ~27 per ns -- against ~20 us for the three ops it replaces.
+    const char* env = getenv("B200_ANAKIN_FUSED_HEAD");
+    if (!(env && env[0] == '1')) return;
+    for (size_t i = 0; i + 2 < _exec.size(); ++i) {
+        ExecOp &ep = _exec[i], &ef = _exec[i + 1], &es = _exec[i + 2];
+        int is_max = 0, axis = 0;
+        b200_fc_stream_desc_t fd;
+        const void* w; const float *bias, *scale;
+        if (ep.side_join >= 0 || ef.side_join >= 0 || es.side_join >= 0 || ef.wait_side || es.wait_side) continue;
+        if (!ep.op->head_pool_info(&is_max) || !ef.op->head_fc_info(&fd, &w, &bias, &scale) || !es.op->head_softmax_info(&axis)) continue;
+        if (ef.ins.empty() || ef.ins[0] != ep.outs[0] || es.ins.empty() || es.ins[0] != ef.outs[0]) continue;
+        DTensor *in = ep.ins[0], *pooled = ep.outs[0], *logits = ef.outs[0], *prob = es.outs[0];
+        if (in->get_layout() != Layout_NHWC || pooled->get_layout() != Layout_NHWC || in->get_dtype() != pooled->get_dtype()) continue;
+        if (pooled->height() != 1 || pooled->width() != 1 || fd.m > 8 || fd.k != pooled->channel_stored() ||
+            fd.in_dtype != pooled->get_dtype() || fd.out_dtype != B200_FLOAT || logits->get_dtype() != AK_FLOAT ||
+            prob->get_dtype() != AK_FLOAT || axis != 1 || logits->height() != 1 || logits->width() != 1)
+            continue;
+        _head.desc.fc = fd;
+        _head.desc.hw = in->height() * in->width();
+        _head.desc.pool_max = is_max;
+        _head.desc.ldp = prob->channel_stored();
+        _head.w = w; _head.bias = bias; _head.scale = scale;
+        _head.in = in; _head.pooled = pooled; _head.logits = logits; _head.prob = prob;
+        if (fd.math != B200_MATH_I8) continue;                           // float heads keep the three ops
+        if (_head.barrier.re_alloc(b200_head_workspace_bytes(&_head.desc), false) != SaberSuccess) return;   // zero-filled
+        ep.head = 1; ef.head = 2; es.head = 2;
+        _head.on = true;
+        return;
+    }
 }
 
 // Off-chain ops (the reference's ParallScheduler gives such nodes their own lane / stream,
@@ -282,6 +320,14 @@ void NetCore::run_eager() {
     size_t ev = 0;
     for (auto& e : _exec) {
         if (e.wait_side) CUDA_CHECK(cudaStreamWaitEvent(_stream, _join_ev, 0));
+        if (e.head == 2) continue;
+        if (e.head == 1) {
+            SABER_CHECK(static_cast<SaberStatus>(b200_head_run(
+                &_head.desc, _head.in->data(), _head.pooled->mutable_data(), _head.w, _head.bias, _head.scale,
+                _head.logits->mutable_data(), static_cast<float*>(_head.prob->mutable_data()),
+                _head.barrier.ptr, _stream)));
+            continue;
+        }
         if (e.side_join >= 0) {
             (void)ev;
             CUDA_CHECK(cudaEventRecord(_fork_ev, _stream));
@@ -333,7 +379,16 @@ std::vector<float> NetCore::profile_ops(int iters, int reps) {
     for (int it = 0; it < iters + 1; ++it) {  // first pass is a warm-up
         for (size_t i = 0; i < n; ++i) {
             CUDA_CHECK(cudaEventRecord(ev[2 * i], _stream));
-            for (int r = 0; r < reps; ++r) (*_exec[i].op)(_ctx, _exec[i].ins, _exec[i].outs);   // all on one stream here
+            for (int r = 0; r < reps; ++r) {   // all on one stream here
+                if (_exec[i].head == 2) continue;       // covered by the fused head launch timed at the pooling op
+                if (_exec[i].head == 1)
+                    SABER_CHECK(static_cast<SaberStatus>(b200_head_run(
+                        &_head.desc, _head.in->data(), _head.pooled->mutable_data(), _head.w, _head.bias, _head.scale,
+                        _head.logits->mutable_data(), static_cast<float*>(_head.prob->mutable_data()),
+                        _head.barrier.ptr, _stream)));
+                else
+                    (*_exec[i].op)(_ctx, _exec[i].ins, _exec[i].outs);
+            }
             CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], _stream));
         }
         CUDA_CHECK(cudaStreamSynchronize(_stream));

@@ -47,7 +47,7 @@ public:
     // intermediate edges through this
     DTensor* get_tensor_from_node(const std::string& node_name);
     std::vector<std::string> get_exec_order() const;  // "name:op" of every launched op
-    size_t launched_op_count() const { return _exec.size(); }
+    size_t launched_op_count() const { return _exec.size() - (_head.on ? 2 : 0); }
     cudaStream_t stream() const { return _stream; }
     int device() const { return _device; }
     Precision precision() const { return _precision; }
@@ -74,11 +74,22 @@ private:
         std::vector<DTensor*> ins, outs;
         int side_join = -1;       // >= 0: runs on the side stream, joined in front of exec op `side_join`
         bool wait_side = false;   // first reader of a side op's result
+        int head = 0;             // 1: this pooling op launches the fused head (pool + fc + softmax); 2: covered by it
     };
     void run_eager();
     void drop_cuda_graph();
     void plan_activation_memory(const std::vector<ExecOp>& all);
     void plan_side_ops(std::vector<ExecOp>& all);
+    void plan_fused_head();
+    struct FusedHead {
+        b200_head_desc_t desc;
+        const void* w = nullptr;
+        const float* bias = nullptr;
+        const float* scale = nullptr;
+        DTensor *in = nullptr, *pooled = nullptr, *logits = nullptr, *prob = nullptr;
+        saber::DeviceBuffer barrier;   // zeroed workspace of b200_head_run (s32 accumulator + ticket)
+        bool on = false;
+    } _head;
 
     Precision _precision = Precision::FP32;
     int _device = 0;

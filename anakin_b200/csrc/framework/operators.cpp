@@ -328,6 +328,10 @@ public:
     const void* weight_device_ptr() const override {
         return const_cast<saber::Fc<NV, D>&>(_f).impl().engine().weight_device_ptr();
     }
+    bool head_fc_info(b200_fc_stream_desc_t* d, const void** w, const float** bias, const float** scale) const override {
+        if (_param.activation_param.has_active) return false;
+        return const_cast<saber::Fc<NV, D>&>(_f).impl().engine().fc_stream_info(d, w, bias, scale);
+    }
 
 private:
     PBlockPtr _w, _b;
@@ -361,11 +365,17 @@ class PoolingOp : public SimpleOp<saber::Pooling<NV, AK_FLOAT>, PoolingParam<NV>
 public:
     Status InitParam() override { _param = parse_pooling(*_node, ""); return Status::OK(); }
     int output_signedness() const override { return -1; }
+    bool head_pool_info(int* is_max) const override {
+        if (!_param.global_pooling || _param.pad_h != 0 || _param.pad_w != 0) return false;
+        *is_max = _param.pooling_type == Pooling_max ? 1 : 0;
+        return true;
+    }
 };
 
 class SoftmaxOp : public SimpleOp<saber::Softmax<NV, AK_FLOAT>, SoftmaxParam<NV>> {
 public:
     Status InitParam() override { _param = SoftmaxParam<NV>(GET_PARAMETER(int, axis)); return Status::OK(); }
+    bool head_softmax_info(int* axis) const override { *axis = _param.axis; return true; }
 };
 
 class EltwiseOp : public SimpleOp<saber::Eltwise<NV, AK_FLOAT>, EltwiseParam<NV>> {

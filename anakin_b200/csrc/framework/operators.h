@@ -40,6 +40,14 @@ public:
     // device address of the op's packed weights (null for weightless ops); Nets built from one Graph on one
     // device report the same address (WeightArena)
     virtual const void* weight_device_ptr() const { return nullptr; }
+    // Hooks for the Net's fused classifier head (global pooling -> inner product -> softmax in one launch,
+    // b200_head_run): each op reports whether -- after Init -- it is the plain form the fused kernel implements.
+    virtual bool head_pool_info(int* is_max) const { (void)is_max; return false; }
+    virtual bool head_fc_info(b200_fc_stream_desc_t* d, const void** w, const float** bias, const float** scale) const {
+        (void)d; (void)w; (void)bias; (void)scale;
+        return false;
+    }
+    virtual bool head_softmax_info(int* axis) const { (void)axis; return false; }
     const graph::NodePtr& node() const { return _node; }
 
 protected:

@@ -21,7 +21,7 @@ namespace saber {
 // reference's Nets share the PBlocks of the process-wide GraphGlobalMem (framework/graph/graph_global_mem.h:78-250,
 // framework/core/net/worker.cpp:10-53). Entries are reference counted and freed with their last user.
 struct DevWeights {
-    DeviceBuffer w, bias, scale;
+    DeviceBuffer w, bias, scale;   // w: tcgen05-packed image, or the plain [n][k] image of a weight-streaming fc
 };
 namespace {
 std::mutex g_arena_mu;
@@ -64,6 +64,8 @@ struct ConvEngine::Impl {
     Tensor<NV> in_scratch;
     float in_inv_scale = 1.f;
     bool depthwise = false;
+    bool fc_stream = false;           // inner product with few rows: b200_fc_stream_run on the plain weight image
+    b200_fc_stream_desc_t fc_desc;
     Tensor<NV> conv_out_scratch;
     b200_pool_desc_t pool_desc;
 
@@ -74,6 +76,14 @@ struct ConvEngine::Impl {
 
 ConvEngine::ConvEngine() : _p(new Impl()) {}
 const void* ConvEngine::weight_device_ptr() const { return _p->dw ? _p->dw->w.ptr : nullptr; }
+bool ConvEngine::fc_stream_info(b200_fc_stream_desc_t* d, const void** w, const float** bias, const float** scale) const {
+    if (!_p->ready || !_p->fc_stream || _p->need_in_transform) return false;
+    *d = _p->fc_desc;
+    *w = _p->dw->w.ptr;
+    *bias = static_cast<const float*>(_p->dw->bias.ptr);
+    *scale = _p->spec.op_dtype == AK_INT8 ? static_cast<const float*>(_p->dw->scale.ptr) : nullptr;
+    return true;
+}
 ConvEngine::~ConvEngine() { delete _p; }
 
 b200_pool_desc_t make_pool_desc(const Tensor<NV>& in, const PoolingParam<NV>& p) {
@@ -239,6 +249,10 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         }
     }
     if (P.depthwise) { d.c = cs; d.k = cs; d.ldc = cout->channel_stored(); }
+    {
+        const char* e = getenv("B200_SABER_FC_STREAM");
+        P.fc_stream = spec.is_fc && !(e && e[0] == '0') && d.n <= b200_fc_stream_max_rows() && !residual && !spec.has_pool;
+    }
 
     // everything the device image depends on
     std::string key;
@@ -249,7 +263,8 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         key_add(key, spec.weights->data());
         key_add(key, b);
         const int32_t sig[] = {math, d.c, d.k, d.r, d.s, static_cast<int32_t>(cin_dt), static_cast<int32_t>(odt), c_real,
-                               spec.is_fc ? 1 : 0, stem ? 1 : 0, P.depthwise ? 1 : 0, spec.c_per_group, spec.r, spec.s};
+                               spec.is_fc ? 1 : 0, stem ? 1 : 0, P.depthwise ? 1 : 0, spec.c_per_group, spec.r, spec.s,
+                               P.fc_stream ? 1 : 0};
         key_add(key, sig);
         key_add(key, in_scale);
         key_add(key, out_scale);
@@ -331,12 +346,17 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
                     }
                 }
             }
-            const size_t pbytes = b200_conv_packed_weight_bytes(&d);
-            if (pbytes == 0) return SaberInvalidValue;
-            std::vector<uint8_t> packed(pbytes);
-            SaberStatus st = static_cast<SaberStatus>(b200_conv_pack_weights(&d, img.data(), c_img, packed.data()));
-            if (st != SaberSuccess) return st;
-            if (upload(dw->w, packed.data(), pbytes) != SaberSuccess) return SaberOutOfMem;
+            if (P.fc_stream) {
+                // [n][k] in the stored order of the input row: exactly `img`
+                if (upload(dw->w, img.data(), img.size()) != SaberSuccess) return SaberOutOfMem;
+            } else {
+                const size_t pbytes = b200_conv_packed_weight_bytes(&d);
+                if (pbytes == 0) return SaberInvalidValue;
+                std::vector<uint8_t> packed(pbytes);
+                SaberStatus st = static_cast<SaberStatus>(b200_conv_pack_weights(&d, img.data(), c_img, packed.data()));
+                if (st != SaberSuccess) return st;
+                if (upload(dw->w, packed.data(), pbytes) != SaberSuccess) return SaberOutOfMem;
+            }
 
             if (op == AK_INT8) {
                 const float u = 127.f / 255.f;
@@ -378,7 +398,13 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         else if (rdt == AK_UINT8 && odt == AK_INT8) d.sum_scale = res_scale * (127.f / 255.f) / out_scale;
         else d.sum_scale = res_scale / out_scale;
     }
-    if (!P.depthwise) {
+    if (P.fc_stream) {
+        b200_fc_stream_desc_t& f = P.fc_desc;
+        memset(&f, 0, sizeof(f));
+        f.math = math; f.in_dtype = cin_dt; f.out_dtype = odt;
+        f.m = d.n; f.k = d.c; f.ldx = d.c; f.n_out = spec.k; f.ldo = d.ldc;
+        f.relu = d.relu; f.neg_slope = d.neg_slope;
+    } else if (!P.depthwise) {
         SaberStatus pst = static_cast<SaberStatus>(b200_conv_plan_create(
             &d, P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
             op == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, &P.plan));
@@ -419,7 +445,11 @@ SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Te
     }
     void* dst = P.spec.has_pool ? P.conv_out_scratch.mutable_data() : out.mutable_data();
     SaberStatus st;
-    if (P.depthwise) {
+    if (P.fc_stream) {
+        st = static_cast<SaberStatus>(b200_fc_stream_run(
+            &P.fc_desc, src, P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
+            P.spec.op_dtype == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, dst, stream));
+    } else if (P.depthwise) {
         st = static_cast<SaberStatus>(b200_dwconv_run(&P.desc, src, P.dw->w.ptr,
                                                       static_cast<const float*>(P.dw->bias.ptr), nullptr, dst, stream));
     } else {

@@ -42,6 +42,9 @@ public:
     SaberStatus run(const Tensor<NV>& in, const Tensor<NV>* residual, Tensor<NV>& out, cudaStream_t stream);
     // device address of the packed weight image this engine runs on (shared between engines through the arena)
     const void* weight_device_ptr() const;
+    // the engine is a weight-streaming inner product (few rows): its C-ABI descriptor and device tables, for the
+    // fused classifier head
+    bool fc_stream_info(b200_fc_stream_desc_t* d, const void** w, const float** bias, const float** scale) const;
 
 private:
     struct Impl;

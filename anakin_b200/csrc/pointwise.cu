@@ -17,6 +17,7 @@
 
 #include "../../include/b200_saber.h"
 #include "common.cuh"
+#include "softmax.cuh"
 
 namespace b200 {
 
@@ -444,28 +445,14 @@ __global__ void pool_warp_kernel(const uint4* __restrict__ in, uint4* __restrict
 }
 
 // ------------------------------------------------------------------ softmax
-// inner == 1: one warp per row, shuffle reductions (reference uses one thread per row).
-__global__ void softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
-                                    int len, int in_pitch, int out_pitch) {
+// inner == 1: one 256-thread CTA per row (the reference uses one thread per row).
+__global__ void __launch_bounds__(SOFTMAX_THREADS) softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                     int rows, int len, int in_pitch, int out_pitch) {
+    __shared__ float red[SOFTMAX_THREADS / 32];
     pdl_enter();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= rows) return;
-    const float* x = in + 1ll * warp * in_pitch;
-    float* y = out + 1ll * warp * out_pitch;
-    float mx = -3.402823466e+38f;
-    for (int i = lane; i < len; i += 32) mx = fmaxf(mx, __ldg(x + i));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int i = lane; i < len; i += 32) {
-        const float e = expf(__ldg(x + i) - mx);
-        y[i] = e;
-        sum += e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    for (int i = lane; i < len; i += 32) y[i] = __fdiv_rn(y[i], sum);
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    softmax_row_block(in + 1ll * row * in_pitch, out + 1ll * row * out_pitch, len, red);
 }
 // inner > 1 (softmax over a non-innermost axis): one thread per (outer, inner) column.
 __global__ void softmax_strided_kernel(const float* __restrict__ in, float* __restrict__ out,
@@ -935,9 +922,8 @@ int b200_softmax_rows(const float* in, float* out, int32_t rows, int32_t len, in
                       int32_t out_pitch, void* stream) {
     if (!in || !out || rows <= 0 || len <= 0 || in_pitch < len || out_pitch < len) return B200_INVALID_VALUE;
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
-    const int block = 128;  // 4 rows per CTA
-    const unsigned grid = (static_cast<unsigned>(rows) * 32 + block - 1) / block;
-    launch_pdl(softmax_rows_kernel, grid, block, S(stream), in, out, rows, len, in_pitch, out_pitch);
+    launch_pdl(softmax_rows_kernel, static_cast<unsigned>(rows), SOFTMAX_THREADS, S(stream), in, out, rows, len, in_pitch,
+               out_pitch);
     return check_launch("softmax");
 }
 

@@ -291,8 +291,31 @@ def load_calibration(model_name):
         return json.load(f)["edge_scales"]
 
 
-def build(model_name, batch=1, precision="fp32"):
+HEAD_DENSE = {"tiny_resnet": "fc", "resnet50": "fc1000", "resnet101": "fc1000", "vgg16": "fc8", "mobilenet_v1": "fc7"}
+
+
+def center_head(graph, model_name):
+    """A randomly initialised net maps every image to nearly the same logits (the classifier sees a large common
+    feature vector plus a small image-dependent part), so top-1 would be the same class for every input and an
+    "exact top-1" check would discriminate nothing. The classifier bias is therefore chosen as b - W.mu, mu = the mean
+    penultimate feature vector of the 8 calibration images (tools/make_golden.py computes it with the fp32 oracle and
+    commits it as tests/golden/<model>_fc_bias.npy): logits are centred and the arg-max varies from image to image.
+    Architecture and every other weight are untouched."""
+    p = os.path.join(_GOLDEN, "%s_fc_bias.npy" % model_name)
+    if not os.path.exists(p):
+        return graph
+    bias = np.load(p).astype(np.float32)
+    for n in graph["nodes"]:
+        if n["name"] == HEAD_DENSE[model_name]:
+            assert n["attrs"]["weight_2"].size == bias.size
+            n["attrs"]["weight_2"] = bias.reshape(n["attrs"]["weight_2"].shape)
+    return graph
+
+
+def build(model_name, batch=1, precision="fp32", centered=True):
     g = BUILDERS[model_name](batch)
+    if centered:
+        center_head(g, model_name)
     if precision == "int8":
         apply_int8(g, load_calibration(model_name))
     return g

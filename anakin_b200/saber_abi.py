@@ -44,6 +44,18 @@ class PoolDesc(C.Structure):
     ]
 
 
+class FcStreamDesc(C.Structure):
+    _fields_ = [
+        ("math", C.c_int32), ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("m", C.c_int32), ("k", C.c_int32), ("ldx", C.c_int32), ("n_out", C.c_int32), ("ldo", C.c_int32),
+        ("relu", C.c_int32), ("neg_slope", C.c_float),
+    ]
+
+
+class HeadDesc(C.Structure):
+    _fields_ = [("fc", FcStreamDesc), ("hw", C.c_int32), ("pool_max", C.c_int32), ("ldp", C.c_int32)]
+
+
 # every symbol include/b200_saber.h declares: name -> (restype, argtypes)
 _vp, _i, _f, _sz = C.c_void_p, C.c_int32, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -59,6 +71,10 @@ SYMBOLS = {
     "b200_conv_plan_info": (C.c_int, [_vp] + [C.POINTER(_i)] * 5),
     "b200_conv_plan_split": (C.c_int, [_vp]),
     "b200_conv_plan_is_slab": (C.c_int, [_vp]),
+    "b200_fc_stream_max_rows": (C.c_int, []),
+    "b200_fc_stream_run": (C.c_int, [C.POINTER(FcStreamDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_head_workspace_bytes": (_sz, [C.POINTER(HeadDesc)]),
+    "b200_head_run": (C.c_int, [C.POINTER(HeadDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_dwconv_run": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_fc_desc": (C.c_int, [C.POINTER(ConvDesc), _i, _i, _i, _i, _i, _i]),
     "b200_pool_out_hw": (C.c_int, [C.POINTER(PoolDesc), C.POINTER(_i), C.POINTER(_i)]),

@@ -186,6 +186,44 @@ B200_API int b200_fc_desc(b200_conv_desc_t* d, int32_t math, int32_t in_dtype, i
                  int32_t k_in, int32_t n_out);
 
 /* ------------------------------------------------------------------------
+ * Weight-streaming inner product for m <= b200_fc_stream_max_rows() rows. Replaces SaberFc<NV,*>::dispatch
+ * (saber/funcs/impl/cuda/base/cuda_c/saber_fc.cu:17-195, ker_gemm.cu:8-186 / cuBLAS) where the layer is a stream of
+ * its weights past a few input rows: every weight byte is read once.
+ *   x        [m][ldx]      operand dtype (u8|s8 for I8, f16 for F16, f32 for TF32 / TF32X3 -- computed in plain fp32)
+ *   w_plain  [n_out][k]    operand dtype, k contiguous, in the STORED order of x's row (k = ldx; zero on padding)
+ *   out      [m][ldo]      out_dtype;  int8 epilogue f = (acc + bias) * scale, relu, rne + saturate (as the conv plan)
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t math;       /* b200_math_t */
+    int32_t in_dtype, out_dtype;
+    int32_t m, k, ldx;  /* rows, reduction length, input row pitch (elements); k*es and ldx*es multiples of 16 bytes */
+    int32_t n_out, ldo; /* output columns, output row pitch (elements) */
+    int32_t relu;
+    float neg_slope;
+} b200_fc_stream_desc_t;
+B200_API int b200_fc_stream_max_rows(void);
+B200_API int b200_fc_stream_run(const b200_fc_stream_desc_t* d, const void* x, const void* w_plain, const float* bias,
+                                const float* scale, void* out, void* stream);
+
+/* INT8 classification head in one launch: global pooling over hw pixels of an NHWC tensor [m][hw][k]
+ * (saber_pooling.cu; AVG divides by hw, rounds to nearest even and saturates), the inner product above on the pooled
+ * rows, and -- when prob is given -- a row softmax of the fp32 logits (saber_softmax.cu). The reduction dimension is
+ * split over the CTAs and combined with integer atomics (exact, order-free); the last CTA applies the epilogue and the
+ * softmax. The pooled rows and the logits are written to their own tensors exactly as the three separate ops would
+ * write them. `workspace`: b200_head_workspace_bytes(d) bytes of ZEROED device memory owned by the caller, one per
+ * concurrently running stream (the kernel leaves it zeroed). math I8, fp32 logits, m <= 8; anything else returns
+ * B200_UNIMPL_ERROR and the caller runs the three ops. */
+typedef struct {
+    b200_fc_stream_desc_t fc; /* ldx == k == stored channels of the pooled tensor */
+    int32_t hw;               /* pixels pooled per row */
+    int32_t pool_max;         /* 1 max, 0 average */
+    int32_t ldp;              /* prob row pitch (elements) */
+} b200_head_desc_t;
+B200_API size_t b200_head_workspace_bytes(const b200_head_desc_t* d);
+B200_API int b200_head_run(const b200_head_desc_t* d, const void* in, void* pooled, const void* w_plain, const float* bias,
+                           const float* scale, void* logits, float* prob, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------
  * Pooling. Replaces SaberPooling<NV,*> / VenderPooling
  * (saber/funcs/impl/cuda/base/cuda_c/saber_pooling.cu:20-229, vender_pooling.cpp).
  * NHWC in/out, c multiple of (16 / sizeof(elem)).

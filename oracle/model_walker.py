@@ -156,7 +156,7 @@ def _conv_kw(a):
     return dict(stride=tuple(a["strides"]), pad=tuple(a["padding"]), dil=tuple(a["dilation_rate"]))
 
 
-def run_fp32(graph, x_nchw, collect_absmax=False):
+def run_fp32(graph, x_nchw, collect_absmax=False, return_values=False):
     """FP32 forward (NHWC internally). Returns {output_name: ndarray}, and with collect_absmax
     also {node_name: max|x|} of every node's output (for max-abs calibration,
     CalibrationAlgoType::MAXABS, saber/saber_types.h:357-360)."""
@@ -222,6 +222,8 @@ def run_fp32(graph, x_nchw, collect_absmax=False):
                 np.transpose(v, (0, 3, 1, 2))
         else:
             raise NotImplementedError(g.kind)
+    if return_values:          # every node's fp32 output (NHWC), for goldens of intermediate edges (logits)
+        return outputs, vals
     if collect_absmax:
         return outputs, absmax
     return outputs

@@ -38,6 +38,32 @@ def _run(G, precision, x, graph=True, keep_edges=True):
     return net
 
 
+def _check_fp32_logits(oracle, want, got, what):
+    """BASELINE.md section 3 on the LOGITS (probabilities of a 1000-way softmax are ~1e-3 and would pass anything):
+    the reference metric tensor_cmp_host (tensor_op.cpp:580-599) at 1e-3 as the reference applies it, AND a
+    per-element relative bound |a-b| / max(|a|, |b|, eps) <= 1e-3. eps is 1e-3 of the largest |logit|: summing the
+    same fp32 products in another order already moves logits that happen to sit near zero by more than 1e-3 of
+    themselves, so a scale-free eps can be met by no second implementation; the share of elements that also meet
+    eps = 1e-6 is asserted to stay above 97 %."""
+    want = np.asarray(want, np.float32)
+    got = np.asarray(got, np.float32)
+    assert want.shape == got.shape, (want.shape, got.shape)
+    mr, md = oracle.tensor_cmp(want, got)
+    assert md < 1e-3 or mr <= 1e-3, (what, mr, md)
+    scale = float(np.abs(want).max())
+    diff = np.abs(want - got)
+    rel = diff / np.maximum(np.maximum(np.abs(want), np.abs(got)), 1e-3 * scale)
+    assert rel.max() <= 1e-3, (what, float(rel.max()), float(diff.max()), scale)
+    strict = diff / np.maximum(np.maximum(np.abs(want), np.abs(got)), 1e-6)
+    assert (strict <= 1e-3).mean() > 0.97, (what, float((strict <= 1e-3).mean()))
+    return float(diff.max()), float(rel.max())
+
+
+def _logits(net, node, batch):
+    arr, info = net.read_tensor(node)
+    return _valid(arr, info).reshape(batch, -1)
+
+
 def _valid(arr, info):
     c = info["dims"][1]
     return arr[..., :c] if info["layout"] == 9 else arr
@@ -97,15 +123,20 @@ def test_tiny_resnet_int8_bit_exact(batch, oracle):
 def test_tiny_resnet_golden_fixture():
     """Committed oracle outputs (tools/make_golden.py) -- does not need /root/reference."""
     from anakin_b200 import modelzoo
+    from oracle import pyoracle as O
     gold = np.load(os.path.join(GOLD, "tiny_resnet_golden.npz"))
-    g, G = _build("tiny_resnet", 4, "int8")
-    net = _run(G, "int8", modelzoo.synthetic_input(4, 32))
+    nb = gold["top1_int8"].shape[0]
+    assert len(set(gold["top1_fp32"].tolist())) >= 3      # the fixture discriminates: several classes win
+    g, G = _build("tiny_resnet", nb, "int8")
+    net = _run(G, "int8", modelzoo.synthetic_input(nb, 32))
     got = net.get_output()
     assert (got.argmax(1) == gold["top1_int8"]).all()
+    np.testing.assert_array_equal(_logits(net, "fc", nb), gold["logits_int8"])
     np.testing.assert_allclose(got, gold["prob_int8"], rtol=1e-4, atol=1e-6)
-    g, G = _build("tiny_resnet", 4, "fp32")
-    net = _run(G, "fp32", modelzoo.synthetic_input(4, 32))
-    np.testing.assert_allclose(net.get_output(), gold["prob_fp32"], rtol=2e-3, atol=1e-5)
+    g, G = _build("tiny_resnet", nb, "fp32")
+    net = _run(G, "fp32", modelzoo.synthetic_input(nb, 32))
+    _check_fp32_logits(O, gold["logits_fp32"], _logits(net, "fc", nb), "tiny_resnet fp32")
+    assert (net.get_output().argmax(1) == gold["top1_fp32"]).all()
 
 
 def test_resnet50_int8_golden_and_oracle(oracle):
@@ -141,8 +172,10 @@ def test_resnet50_int8_full_batch_matches_golden_and_is_batch_invariant(batch):
     net = _run(G, "int8", x)
     logits, info = net.read_tensor("fc1000")
     logits = _valid(logits, info).reshape(batch, -1)
-    np.testing.assert_array_equal(logits[:4], gold["logits_int8"])
-    assert (net.get_output().argmax(1)[:4] == gold["top1_int8"]).all()
+    # every image of the batch against the committed oracle logits (32 goldens: 16 different winning classes)
+    np.testing.assert_array_equal(logits, gold["logits_int8"][:batch])
+    assert (net.get_output().argmax(1) == gold["top1_int8"][:batch]).all()
+    assert len(set(gold["top1_int8"][:batch].tolist())) >= 4
     _, G4 = _build("resnet50", 4, "int8")
     net4 = _run(G4, "int8", x[4:8])
     l4, i4 = net4.read_tensor("fc1000")
@@ -156,16 +189,19 @@ def test_resnet50_int8_full_batch_matches_golden_and_is_batch_invariant(batch):
     np.testing.assert_allclose(prob.sum(1), 1.0, rtol=1e-5)
 
 
-def test_resnet50_fp32_golden():
+@pytest.mark.parametrize("batch", [1, 8])
+def test_resnet50_fp32_golden(batch):
+    """C1 (batch 1) and a full batch: fp32 logits of every image against the fp32 oracle's."""
     from anakin_b200 import modelzoo
-    gold = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
-    g, G = _build("resnet50", 1, "fp32")
-    net = _run(G, "fp32", modelzoo.synthetic_input(1))
-    got = net.get_output()
     from oracle import pyoracle as O
-    mr, md = O.tensor_cmp(gold["prob_fp32"][:1], got)
+    gold = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
+    g, G = _build("resnet50", batch, "fp32")
+    net = _run(G, "fp32", modelzoo.synthetic_input(batch))
+    _check_fp32_logits(O, gold["logits_fp32"][:batch], _logits(net, "fc1000", batch), "resnet50 fp32 b%d" % batch)
+    got = net.get_output()
+    mr, md = O.tensor_cmp(gold["prob_fp32"][:batch], got)
     assert md < 1e-3 or mr <= 1e-3, (mr, md)
-    assert got.argmax(1)[0] == gold["top1_fp32"][0]
+    assert (got.argmax(1) == gold["top1_fp32"][:batch]).all()
 
 
 def test_graph_save_reload_runs_identically():
@@ -203,9 +239,9 @@ def test_resnet101_int8_golden():
     g, G = _build("resnet101", 4, "int8")
     net = _run(G, "int8", modelzoo.synthetic_input(4))
     got = net.get_output()
-    assert (got.argmax(1) == gold["top1_int8"]).all()
+    assert (got.argmax(1) == gold["top1_int8"][:4]).all()
     logits, info = net.read_tensor("fc1000")
-    np.testing.assert_array_equal(_valid(logits, info).reshape(4, -1), gold["logits_int8"])
+    np.testing.assert_array_equal(_valid(logits, info).reshape(4, -1), gold["logits_int8"][:4])
 
 
 def test_vgg16_fp32_golden():
@@ -213,12 +249,14 @@ def test_vgg16_fp32_golden():
     from anakin_b200 import modelzoo
     from oracle import pyoracle as O
     gold = np.load(os.path.join(GOLD, "vgg16_golden.npz"))
-    g, G = _build("vgg16", 2, "fp32")
-    net = _run(G, "fp32", modelzoo.synthetic_input(2))
+    batch = 4                                   # the batch size C3 names
+    g, G = _build("vgg16", batch, "fp32")
+    net = _run(G, "fp32", modelzoo.synthetic_input(batch))
+    _check_fp32_logits(O, gold["logits_fp32"], _logits(net, "fc8", batch), "vgg16 fp32 b4")
     got = net.get_output()
     mr, md = O.tensor_cmp(gold["prob_fp32"], got)
     assert md < 1e-3 or mr <= 1e-3, (mr, md)
-    assert (got.argmax(1) == gold["top1_fp32"]).all()
+    assert (got.argmax(1) == gold["top1_fp32"]).all() and len(set(gold["top1_fp32"].tolist())) >= 3
 
 
 def test_mobilenet_v1_fp16_vs_fp32_oracle():
@@ -228,17 +266,26 @@ def test_mobilenet_v1_fp16_vs_fp32_oracle():
     from anakin_b200 import modelzoo
     from oracle import pyoracle as O
     gold = np.load(os.path.join(GOLD, "mobilenet_v1_golden.npz"))
-    x = modelzoo.synthetic_input(4)
-    g, G = _build("mobilenet_v1", 4, "fp32")
-    got32 = _run(G, "fp32", x).get_output()
-    mr, md = O.tensor_cmp(gold["prob_fp32"], got32)
-    assert md < 1e-3 or mr <= 1e-3, (mr, md)
-    g, G = _build("mobilenet_v1", 4, "fp16")
-    got16 = _run(G, "fp16", x).get_output()
+    batch = 16                                  # the batch size C5 names
+    x = modelzoo.synthetic_input(batch)
+    g, G = _build("mobilenet_v1", batch, "fp32")
+    net32 = _run(G, "fp32", x)
+    _check_fp32_logits(O, gold["logits_fp32"], _logits(net32, "fc7", batch), "mobilenet fp32 b16")
+    g, G = _build("mobilenet_v1", batch, "fp16")
+    net16 = _run(G, "fp16", x)
+    got16 = net16.get_output()
     assert np.isfinite(got16).all()
-    rel = np.abs(got16 - gold["prob_fp32"]).max() / gold["prob_fp32"].max()
-    assert rel < 5e-2, rel
-    assert (got16.argmax(1) == gold["top1_fp32"]).all()
+    # FP16 storage between the 28 layers: every edge tensor is rounded to 11 significant bits (relative 2^-11 each).
+    # Derived bound on a logit, errors taken as independent over the L = 28 roundings in series:
+    #   |dlogit| <= 4 * sqrt(L) * 2^-11 * max|logit|   (4 sigma), i.e. 1.04e-2 of the logit scale
+    l16, l32 = _logits(net16, "fc7", batch).astype(np.float32), gold["logits_fp32"]
+    bound = 4.0 * np.sqrt(28.0) * 2.0 ** -11 * float(np.abs(l32).max())
+    assert np.abs(l16 - l32).max() <= bound, (float(np.abs(l16 - l32).max()), bound)
+    # top-1 must agree wherever the fp32 margin is larger than twice that bound
+    srt = np.sort(l32, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 2 * bound
+    assert clear.sum() >= batch // 2, int(clear.sum())
+    assert (got16.argmax(1)[clear] == gold["top1_fp32"][clear]).all()
 
 
 def test_cpp_example_program_runs():
@@ -267,7 +314,7 @@ def test_worker_sync_prediction_two_threads():
         x = modelzoo.synthetic_input(4, 32)
         for _ in range(6):
             out = w.sync_prediction(x, 4 * 12).reshape(4, 12)[:, :10]
-            np.testing.assert_allclose(out, gold["prob_int8"], rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose(out, gold["prob_int8"][:4], rtol=1e-4, atol=1e-6)
         del w
 
 

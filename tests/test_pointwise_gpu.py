@@ -236,3 +236,139 @@ def test_dwconv_f32(stride, oracle):
     torch.cuda.synchronize()
     mr, md = oracle.tensor_cmp(want, out.cpu().numpy())
     assert md < 1e-3 or mr <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Weight-streaming inner product (fc_stream.cu) and the fused classifier head (pool + fc + softmax, one launch)
+FC_CASES = [(8, 2048, 1000), (4, 25088, 512), (1, 512, 10), (13, 4096, 200), (16, 1024, 64)]   # (m, k, n)
+
+
+@pytest.mark.parametrize("m,k,n", FC_CASES)
+@pytest.mark.parametrize("variant", ["u8_f32", "s8_relu_u8", "u8_s8"])
+def test_fc_stream_int8_bit_exact(m, k, n, variant, oracle):
+    """int8 inner product: exact dp4a sums + the x86 Saber epilogue, bit-identical to the 1x1-conv oracle."""
+    import ctypes as C
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(hash((m, k, n, variant)) % (2 ** 31))
+    unsigned = variant.startswith("u8")
+    x = (rng.integers(0, 256, (m, 1, 1, k)).astype(np.uint8) if unsigned else rng.integers(-128, 128, (m, 1, 1, k)).astype(np.int8))
+    w = rng.integers(-127, 128, (n, k, 1, 1)).astype(np.int8)
+    bias = rng.uniform(-2000, 2000, n).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, n).astype(np.float32) * np.float32(1.0 / (40.0 * np.sqrt(k) * 8))
+    out_dtype = {"u8_f32": A.FLOAT, "s8_relu_u8": A.UINT8, "u8_s8": A.INT8}[variant]
+    relu = variant == "s8_relu_u8"
+    want = oracle.conv_s8_nhwc_x86(x, w, bias, scale, out_dtype=out_dtype, relu=relu).reshape(m, n)
+    lib = A.load()
+    d = A.FcStreamDesc()
+    d.math, d.in_dtype, d.out_dtype = A.MATH_I8, (A.UINT8 if unsigned else A.INT8), out_dtype
+    d.m, d.k, d.ldx, d.n_out = m, k, k, n
+    d.ldo = (n + 15) // 16 * 16
+    d.relu = int(relu)
+    out = torch.zeros((m, d.ldo), dtype={A.FLOAT: torch.float32, A.UINT8: torch.uint8, A.INT8: torch.int8}[out_dtype], device="cuda")
+    xd, wd, bd, sd = dev(x.reshape(m, k)), dev(w.reshape(n, k)), dev(bias), dev(scale)
+    assert m <= lib.b200_fc_stream_max_rows()
+    A.check(lib.b200_fc_stream_run(C.byref(d), ptr(xd), ptr(wd), ptr(bd), ptr(sd), ptr(out), stream_ptr()), "fc_stream")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert (got[:, n:] == 0).all()
+    np.testing.assert_array_equal(got[:, :n], want)
+
+
+@pytest.mark.parametrize("m,k,n", [(4, 25088, 256), (8, 1024, 1000), (3, 4096, 100)])
+@pytest.mark.parametrize("math", ["f32", "f16"])
+def test_fc_stream_float(m, k, n, math, oracle):
+    import ctypes as C
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(hash((m, k, n, math)) % (2 ** 31))
+    x = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k)) * np.sqrt(2.0 / k)).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    if math == "f16":
+        xs, ws = x.astype(np.float16), w.astype(np.float16)
+        x_seen, w_seen = xs.astype(np.float32), ws.astype(np.float32)
+        mk, dt = A.MATH_F16, A.HALF
+    else:
+        xs, ws, x_seen, w_seen = x, w, x, w
+        mk, dt = A.MATH_TF32X3, A.FLOAT
+    want = np.maximum(x_seen.astype(np.float64) @ w_seen.astype(np.float64).T + bias, 0).astype(np.float32)
+    lib = A.load()
+    d = A.FcStreamDesc()
+    d.math, d.in_dtype, d.out_dtype = mk, dt, A.FLOAT
+    d.m, d.k, d.ldx, d.n_out, d.ldo, d.relu = m, k, k, n, n, 1
+    out = torch.zeros((m, n), dtype=torch.float32, device="cuda")
+    xd, wd, bd = dev(xs), dev(ws), dev(bias)
+    A.check(lib.b200_fc_stream_run(C.byref(d), ptr(xd), ptr(wd), ptr(bd), None, ptr(out), stream_ptr()), "fc_stream")
+    torch.cuda.synchronize()
+    mr, md = oracle.tensor_cmp(want, out.cpu().numpy())
+    assert md < 1e-3 or mr <= 1e-3, (mr, md)
+    assert md <= 2e-5 * max(1.0, float(np.abs(want).max())) * max(1.0, k / 4096), md
+
+
+@pytest.mark.parametrize("m,hw,c,n", [(8, 49, 2048, 1000), (2, 49, 512, 10), (5, 16, 1024, 257), (1, 49, 2048, 1000),
+                                      (8, 4, 64, 33)])
+@pytest.mark.parametrize("dtype", ["u8", "s8"])
+@pytest.mark.parametrize("pool", ["avg", "max"])
+def test_fused_head_matches_the_three_separate_ops(m, hw, c, n, dtype, pool, oracle):
+    """b200_head_run == b200_pool_run -> b200_fc_stream_run -> b200_softmax_rows on every tensor it writes, bit for
+    bit, over repeated launches on the same (self-cleaning) workspace; the pooled codes are the oracle's."""
+    import ctypes as C
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(hash((m, hw, c, n, dtype, pool)) % (2 ** 31))
+    lib = A.load()
+    side = int(round(hw ** 0.5))
+    assert side * side == hw
+    if dtype == "u8":
+        x = rng.integers(0, 256, (m, side, side, c)).astype(np.uint8)
+        dt, tdt = A.UINT8, torch.uint8
+    else:
+        x = rng.integers(-128, 128, (m, side, side, c)).astype(np.int8)
+        dt, tdt = A.INT8, torch.int8
+    w = rng.integers(-127, 128, (n, c)).astype(np.int8)
+    scale = rng.uniform(0.5, 1.5, n).astype(np.float32) * np.float32(1.0 / (40.0 * np.sqrt(c) * 8))
+    bias = rng.uniform(-2000, 2000, n).astype(np.float32)
+    xd, wd, bd, sd = dev(x), dev(w), dev(bias), dev(scale)
+    ldo = (n + 3) // 4 * 4
+    # --- the three separate ops
+    pd = A.PoolDesc()
+    pd.dtype, pd.type, pd.n, pd.h, pd.w, pd.c = dt, (A.POOL_MAX if pool == "max" else A.POOL_AVG_INC), m, side, side, c
+    pd.window_h = pd.window_w = side
+    pd.stride_h = pd.stride_w = 1
+    pd.global_pooling = 1
+    pooled_ref = torch.zeros((m, c), dtype=tdt, device="cuda")
+    A.check(lib.b200_pool_run(C.byref(pd), ptr(xd), ptr(pooled_ref), stream_ptr()), "pool")
+    fd = A.FcStreamDesc()
+    fd.math, fd.in_dtype, fd.out_dtype = A.MATH_I8, dt, A.FLOAT
+    fd.m, fd.k, fd.ldx, fd.n_out, fd.ldo = m, c, c, n, ldo
+    logits_ref = torch.zeros((m, ldo), dtype=torch.float32, device="cuda")
+    A.check(lib.b200_fc_stream_run(C.byref(fd), ptr(pooled_ref), ptr(wd), ptr(bd), ptr(sd), ptr(logits_ref), stream_ptr()), "fc")
+    prob_ref = torch.zeros((m, ldo), dtype=torch.float32, device="cuda")
+    A.check(lib.b200_softmax_rows(ptr(logits_ref), ptr(prob_ref), m, n, ldo, ldo, stream_ptr()), "softmax")
+    # --- one launch
+    hd = A.HeadDesc()
+    hd.fc, hd.hw, hd.pool_max, hd.ldp = fd, hw, int(pool == "max"), ldo
+    pooled = torch.zeros((m, c), dtype=tdt, device="cuda")
+    logits = torch.zeros((m, ldo), dtype=torch.float32, device="cuda")
+    prob = torch.zeros((m, ldo), dtype=torch.float32, device="cuda")
+    ws = torch.zeros(lib.b200_head_workspace_bytes(C.byref(hd)), dtype=torch.uint8, device="cuda")
+    for rep in range(3):
+        A.check(lib.b200_head_run(C.byref(hd), ptr(xd), ptr(pooled), ptr(wd), ptr(bd), ptr(sd), ptr(logits), ptr(prob),
+                                  ptr(ws), stream_ptr()), "head")
+        torch.cuda.synchronize()
+        assert torch.equal(pooled, pooled_ref), rep
+        assert torch.equal(logits, logits_ref), rep
+        assert torch.equal(prob, prob_ref), rep
+        assert int(ws.count_nonzero()) == 0, "the workspace must be left zeroed"
+    want_pool = oracle.pool_s8_nhwc(x, (side, side), (0, 0), (side, side), 1 if pool == "max" else 2, global_pooling=True)
+    np.testing.assert_array_equal(pooled.cpu().numpy(), want_pool.reshape(m, c))
+    np.testing.assert_allclose(prob.cpu().numpy()[:, :n].sum(1), 1.0, rtol=1e-5)
+    # float heads are not fused: the entry point says so and the Net keeps the three ops
+    fd.math, fd.in_dtype = A.MATH_F16, A.HALF
+    hd.fc = fd
+    assert lib.b200_head_run(C.byref(hd), ptr(xd), ptr(pooled), ptr(wd), ptr(bd), ptr(sd), ptr(logits), ptr(prob), ptr(ws),
+                             stream_ptr()) == A.UNIMPL_ERROR
