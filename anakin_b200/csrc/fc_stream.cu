@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -437,7 +438,8 @@ int b200_fc_stream_run(const b200_fc_stream_desc_t* d, const void* x, const void
     const FcParams p = make_fc_params(d, x, w_plain, bias, scale, out);
     const int r = fc_rows_per_warp(p.n);
     const int nblocks = (p.n + FC_WARPS * r - 1) / (FC_WARPS * r);
-    const unsigned grid = static_cast<unsigned>(nblocks < 2 * sm_count() ? nblocks : 2 * sm_count());
+    static const int grid_mult = [] { const char* e = getenv("B200_FC_GRID_MULT"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+    const unsigned grid = static_cast<unsigned>(nblocks < grid_mult * sm_count() ? nblocks : grid_mult * sm_count());
     const int mode = fc_mode(d->math);
     if (mode == 0) launch_fc<0>(p, r, grid, static_cast<cudaStream_t>(stream));
     else if (mode == 1) launch_fc<1>(p, r, grid, static_cast<cudaStream_t>(stream));

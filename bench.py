@@ -145,6 +145,73 @@ def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, 
             "ms_per_step": dt / steps * 1e3, "images_per_step": n_img}
 
 
+LOGIT_NODE = {"tiny_resnet": "fc", "resnet50": "fc1000", "resnet101": "fc1000", "vgg16": "fc8", "mobilenet_v1": "fc7"}
+
+
+def check_parity(net, model, prec, batch, rank):
+    """Every rank compares what it just computed with the committed oracle goldens (tests/golden, made by
+    tools/make_golden.py from the pinned CPU oracle): image i of rank r is golden image r*batch + i.
+    INT8: logits bit-exact and top-1 equal; FP32: reference criterion on the logits and top-1 equal where the
+    oracle's margin is clear. A mismatch aborts the benchmark: a fast wrong answer is not a result."""
+    path = os.path.join(ROOT, "tests", "golden", "%s_golden.npz" % model)
+    if not os.path.exists(path) or prec == "fp16":
+        return {"checked_images": 0, "note": "no golden for this model / precision"}
+    gold = np.load(path)
+    key = "logits_int8" if prec == "int8" else "logits_fp32"
+    if key not in gold:
+        return {"checked_images": 0, "note": "no %s golden" % key}
+    lo = rank * batch
+    n = max(0, min(batch, gold[key].shape[0] - lo))
+    if n == 0:
+        return {"checked_images": 0, "note": "rank beyond the golden set"}
+    arr, info = net.read_tensor(LOGIT_NODE[model])
+    c = info["dims"][1]
+    got = (arr[..., :c] if info["layout"] == 9 else arr).reshape(batch, -1)[:n]
+    want = gold[key][lo:lo + n]
+    top1 = net.get_output().argmax(1)[:n]
+    if prec == "int8":
+        ok = bool(np.array_equal(got, want)) and bool((top1 == gold["top1_int8"][lo:lo + n]).all())
+        res = {"checked_images": int(n), "int8_logits_bit_exact": ok, "max_abs_diff": float(np.abs(got - want).max())}
+    else:
+        off = gold["logit_offset"]
+        scale = float(np.abs(want + off).max())
+        md = float(np.abs(got - want).max())
+        srt = np.sort(want, axis=1)
+        clear = (srt[:, -1] - srt[:, -2]) > 4 * md
+        ok = md <= 2.5e-4 * scale and bool((top1[clear] == gold["top1_fp32"][lo:lo + n][clear]).all())
+        res = {"checked_images": int(n), "fp32_logits_within_2.5e-4_of_scale": ok, "max_abs_diff": md, "logit_scale": scale}
+    if not ok:
+        raise SystemExit("bench.py: rank %d results differ from the oracle goldens: %s" % (rank, res))
+    return res
+
+
+def time_net(model, prec, batch, local_rank, steps, flush):
+    """Device-timed ms per prediction() of another (model, batch) on this rank: CUDA-graph replay, L2 flushed."""
+    import torch
+    from anakin_b200 import anakin_bin, api, modelzoo
+    G = api.Graph.from_bytes(anakin_bin.dumps(modelzoo.build(model, batch=batch, precision=prec if prec == "int8" else "fp32")))
+    G.ResetBatchSize("input_0", batch)
+    G.Optimize()
+    net = api.Net(G, prec, device=local_rank)
+    net.set_input("input_0", modelzoo.synthetic_input(batch, 224))
+    for _ in range(5):
+        net.prediction()
+    net.sync()
+    stream = torch.cuda.ExternalStream(net.stream, device=torch.device("cuda", local_rank))
+    ms = 0.0
+    with torch.cuda.stream(stream):
+        for _ in range(steps):
+            if flush is not None:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            net.prediction()
+            b.record(stream)
+            b.synchronize()
+            ms += a.elapsed_time(b)
+    return ms / steps
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -216,6 +283,7 @@ def main():
     net.prediction()   # captures the CUDA graph
     net.sync()
     top1 = net.get_output().argmax(1)
+    parity = check_parity(net, model, prec, batch, rank)
 
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -321,6 +389,43 @@ def main():
         del W
     clocks_e2e = sampler2.stop() if (rank == 0 and sampler2.proc) else None
 
+    # ---- N > 1 extras: BASELINE config C4 (ResNet-101 INT8, GLOBAL batch 32 split over the GPUs: strong scaling),
+    # and the in-process flavour of the replicas (one Worker, one thread per GPU) exercised once from rank 0
+    c4 = None
+    multi_worker = None
+    if world > 1 and model == "resnet50" and prec == "int8" and 32 % world == 0:
+        per_gpu = 32 // world
+        barrier()
+        c4_ms = time_net("resnet101", "int8", per_gpu, local_rank, max(10, K // 5), flush)
+        t = torch.tensor([c4_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c4 = {"model": "resnet101", "precision": "int8", "global_batch": 32, "batch_per_gpu": per_gpu,
+              "ms_per_step": float(t.item()), "images_per_s": 32.0 / (float(t.item()) / 1e3), "scaling": "strong"}
+        barrier()
+        if rank == 0:
+            W2 = api.Worker(mpath if T > 0 else None, prec, threads=world, devices=list(range(world)), batch=batch) if T > 0 else None
+            if W2 is not None:
+                W2.wait_ready()
+                nreq = 8 * world
+                ins = [torch.from_numpy(x).pin_memory() for _ in range(2 * world)]
+                outs = [torch.empty(out_info["bytes"] // 4, dtype=torch.float32).pin_memory() for _ in range(2 * world)]
+                for phase in range(2):
+                    t0 = time.perf_counter()
+                    inflight = 0
+                    for i in range(nreq):
+                        if inflight == 2 * world:
+                            W2.async_get_result(); inflight -= 1
+                        j = i % (2 * world)
+                        W2.async_prediction_ptr(ins[j].data_ptr(), ins[j].numel(), outs[j].data_ptr(), outs[j].numel())
+                        inflight += 1
+                    while inflight:
+                        W2.async_get_result(); inflight -= 1
+                    dt = time.perf_counter() - t0
+                multi_worker = {"api": "one Worker, %d threads, thread i on GPU i (in-process replicas)" % world,
+                                "images_per_s": nreq * batch / dt, "requests": nreq}
+                del W2
+        barrier()
+
     # ---- per-op device times (eager, event pair per op) -> roofline of the dominant kernel
     prof = net.profile_ops(5, 20)
     conv_ms = sum(ms for _, op, ms in prof if op.startswith("Conv") or op == "Dense")
@@ -341,6 +446,11 @@ def main():
     value = images / (total_ms / 1e3)
     gop_step = GOP_PER_IMAGE.get(model, 0.0) * batch
     conv_launches = sum(1 for _, op, _ in prof if op.startswith("Conv") or op == "Dense")
+    # the roofline is computed from the TIMED region: the conv / fc kernels' share of a step (from the per-op profile)
+    # applied to the device-timed graph-replay step
+    share = conv_ms / all_ms if all_ms else 0.0
+    conv_ms_eager = conv_ms
+    conv_ms = (total_ms / K) * share
     # tensor roof: kind::i8 runs at twice the bf16 rate; the measured bf16 GEMM peak x2 is the denominator
     mult = 2.0 if prec == "int8" else (1.0 if prec == "fp16" else 0.5)
     peak_tops = P["bf16_tflops"] * mult
@@ -372,12 +482,16 @@ def main():
                "top1_first": worker_top1, "serial": serial}
     else:
         e2e = dict(serial, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h)
-    # DRAM bytes per conv launch from the committed `ncu --set full` capture of this same workload (profiles/)
+    # DRAM / L2 bytes per conv launch: from this round's `ncu --set full` capture of this same workload
+    # (profiles/r02_conv_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep; a bench run cannot profile itself)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    traffic_l2 = None
+    tpath = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
     if model == "resnet50" and prec == "int8" and batch == 8 and os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_l2 = tj.get("lts_bytes_per_launch")
     line = {
         "metric": "%s %s images/sec" % (MODEL_NAMES.get(model, model), prec.upper()),
         "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
@@ -394,13 +508,14 @@ def main():
         "ms_per_step_p50": float(np.median(per_step)), "ms_per_step_p99": float(np.percentile(per_step, 99)),
         "e2e": e2e,
         "roofline": {"bound": "hbm" if hbm_bound else "tensor",
-                     "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % conv_launches,
+                     "kernel": "conv_igemm_kernel / conv_slab_kernel (tcgen05 implicit GEMM, %d launches/step)" % conv_launches,
                      "achieved": achieved_gbs if hbm_bound else achieved_tops,
                      "peak": P["hbm_gbs"] if hbm_bound else peak_tops,
                      "unit": "GB/s" if hbm_bound else ("TOP/s" if prec == "int8" else "TFLOP/s"),
                      "frac": (achieved_gbs / P["hbm_gbs"]) if hbm_bound else (achieved_tops / peak_tops if peak_tops else None),
                      "traffic": traffic,
-                     "traffic_unit": "DRAM bytes per launch, mean over the step's conv launches (cold-cache ncu capture)",
+                     "traffic_l2": traffic_l2,
+                     "traffic_unit": "DRAM (and L2) bytes per launch, mean over the step's conv launches (this round's cold-cache ncu capture)",
                      "algorithmic_bytes_per_launch": alg_bytes / conv_launches if conv_launches else None,
                      "algorithmic_gop_per_step": gop_step,
                      "lower_bound_us": {"tensor": t_tensor_us, "hbm": t_hbm_us},
@@ -409,13 +524,19 @@ def main():
                                 "peak_source": "%s bf16 dense x%.1f" % (P["src"], mult)},
                      "hbm": {"achieved": achieved_gbs, "peak": P["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved_gbs / P["hbm_gbs"], "peak_source": "%s device copy" % P["src"]},
-                     "kernel_ms_per_step": conv_ms, "all_ops_ms_per_step_eager": all_ms,
-                     "kernel_share_of_step": conv_ms / all_ms if all_ms else None},
+                     "kernel_ms_per_step": conv_ms, "kernel_ms_per_step_eager_profile": conv_ms_eager,
+                     "all_ops_ms_per_step_eager": all_ms,
+                     "kernel_share_of_step": share},
         "clocks": clocks,
         "clocks_e2e": clocks_e2e,
         "top1_first": [int(v) for v in top1[:4]],
+        "parity": parity,
         "cuda_graph": net.cuda_graph_active(),
     }
+    if c4 is not None:
+        line["strong_scaling_c4"] = c4
+    if multi_worker is not None:
+        line["worker_in_process_multi_gpu"] = multi_worker
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_oracle_images_per_s(model, prec, batch)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -61,6 +61,8 @@ def main(models):
         out["prob_fp32"] = fp32["prob_out"].astype(np.float32)
         out["top1_fp32"] = fp32["prob_out"].argmax(1).astype(np.int32)
         out["logits_fp32"] = vals[LOGITS[name]].reshape(nb, -1).astype(np.float32)
+        # what centring took away: logits + logit_offset are the logits of the net with its drawn bias
+        out["logit_offset"] = (b - centred).astype(np.float32)
         if name in INT8_MODELS:
             scales = W.calibrate(g, cal_x)
             with open(os.path.join(GOLD, "%s_calib.json" % name), "w") as f:
