@@ -359,6 +359,9 @@ struct b200_conv_plan {
     const void* map_out_ptr;
     const void* map_res_ptr;
     void (*launch)(b200_conv_plan*, void* stream);
+    // persistent tile-pipelined variant (conv_persistent.cu): grid.x x grid.y tiles walked by persistent_ctas CTAs
+    bool persistent = false;
+    int persistent_ctas = 0;
     // slab-staged variant (conv_slab.cu): 4-D tiled maps, its own tiling
     bool slab = false;
     b200::SlabParams sp;

@@ -71,6 +71,7 @@ SYMBOLS = {
     "b200_conv_plan_info": (C.c_int, [_vp] + [C.POINTER(_i)] * 5),
     "b200_conv_plan_split": (C.c_int, [_vp]),
     "b200_conv_plan_is_slab": (C.c_int, [_vp]),
+    "b200_conv_plan_is_persistent": (C.c_int, [_vp]),
     "b200_fc_stream_max_rows": (C.c_int, []),
     "b200_fc_stream_run": (C.c_int, [C.POINTER(FcStreamDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_head_workspace_bytes": (_sz, [C.POINTER(HeadDesc)]),

@@ -167,6 +167,9 @@ B200_API int b200_conv_plan_split(const b200_conv_plan_t* plan);
 /* 1 when the plan runs the slab-staged stride-1 R x S kernel (the input rectangle of a tile is staged once per
  * channel chunk and the filter taps are row-shifted views of it) instead of the TMA-im2col kernel. */
 B200_API int b200_conv_plan_is_slab(const b200_conv_plan_t* plan);
+/* 1 when the plan runs the persistent tile-pipelined kernel (one CTA per SM walks the tile list, two TMEM accumulators:
+ * the epilogue of a tile overlaps the main loop of the next) -- chosen for grids of more than two tiles per SM. */
+B200_API int b200_conv_plan_is_persistent(const b200_conv_plan_t* plan);
 
 /* ------------------------------------------------------------------------
  * Depthwise convolution (MobileNet). Replaces SaberDepthWiseConv

@@ -75,6 +75,7 @@ class ConvRunner:
         d = dict(zip(("block_n", "grid_x", "grid_y", "k_steps", "smem"), [x.value for x in v]))
         d["split"] = self.lib.b200_conv_plan_split(self.plan)
         d["slab"] = bool(self.lib.b200_conv_plan_is_slab(self.plan))
+        d["persistent"] = bool(self.lib.b200_conv_plan_is_persistent(self.plan))
         return d
 
     def run(self, x_dev, res_dev=None, out_dev=None):

@@ -336,3 +336,61 @@ def test_conv_slab_float(case, math, with_res, oracle, monkeypatch):
         scale_ref = float(np.abs(want).max())
         steps = max(1.0, c * r * s / 1152.0)
         assert max_diff <= 2e-5 * max(1.0, scale_ref) * steps, (max_diff, scale_ref, steps)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Persistent tile-pipelined kernel (conv_persistent.cu): one CTA per SM walks the tile list with two TMEM accumulators.
+# Forced on (B200_SABER_PERSISTENT=2) so that small grids exercise it too: CTAs with 1, 2 and many tiles, several
+# n-tiles (bias / scale tables reloaded mid-walk), residual buffer hand-back, ragged last m-tile, strided and 3x3 im2col.
+# (n, h, w, c, k, r, stride, pad)
+PERSISTENT_CASES = [
+    (8, 56, 56, 64, 256, 1, 1, 0),      # 196 tiles on 148 CTAs
+    (32, 56, 56, 64, 64, 1, 1, 0),      # 784 tiles: 5-6 per CTA
+    (4, 28, 28, 128, 512, 1, 1, 0),     # several n-tiles per CTA walk
+    (6, 30, 30, 32, 72, 3, 2, 1),       # strided 3x3, ragged channels and rows
+    (2, 9, 9, 256, 40, 1, 1, 0),        # fewer tiles than SMs
+    (16, 28, 28, 256, 128, 1, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", PERSISTENT_CASES)
+@pytest.mark.parametrize("variant", ["s8_relu_u8", "u8_res_s8", "s8_f32"])
+def test_conv_persistent_int8_bit_exact(case, variant, oracle, monkeypatch):
+    monkeypatch.setenv("B200_SABER_PERSISTENT", "2")
+    monkeypatch.setenv("B200_SABER_SLAB", "0")
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev, pad_channels
+    rng = np.random.default_rng(hash((case, variant)) % (2 ** 31))
+    n, h, w, c, k, r, stride, pad = case
+    in_unsigned = variant == "u8_res_s8"
+    x, wq, bias, scale = _slab_io(rng, (n, h, w, c, k, r, r, pad, pad), in_unsigned)
+    out_dtype = {"s8_relu_u8": A.UINT8, "u8_res_s8": A.INT8, "s8_f32": A.FLOAT}[variant]
+    kw = dict(stride=(stride, stride), pad=(pad, pad), dil=(1, 1), relu=variant != "s8_f32")
+    res, sum_scale = None, 1.0
+    oh = oracle.conv_out_size(h, pad, 1, r, stride)
+    ow = oracle.conv_out_size(w, pad, 1, r, stride)
+    if variant == "u8_res_s8":
+        res = rng.integers(0, 256, (n, oh, ow, k)).astype(np.uint8)
+        sum_scale = 0.37
+    want = oracle.conv_s8_nhwc_x86(x, wq, bias, scale, residual=res, sum_scale=sum_scale, out_dtype=out_dtype, **kw)
+    ldc = (k + 15) // 16 * 16 if out_dtype != A.FLOAT else (k + 3) // 4 * 4
+    run = ConvRunner(A.MATH_I8, x.shape, A.UINT8 if in_unsigned else A.INT8, wq, bias, scale,
+                     out_dtype, res_dtype=(A.UINT8 if res is not None else -1), sum_scale=sum_scale, ldc=ldc, **kw)
+    info = run.info()
+    assert info["persistent"] and not info["slab"], info
+    for rep in range(2):
+        got = run.run(dev(x), dev(pad_channels(res, ldc)) if res is not None else None)
+        torch.cuda.synchronize()
+        got = got.cpu().numpy()
+        assert (got[..., k:] == 0).all(), "padding channels must stay untouched"
+        bad = np.argwhere(got[..., :k] != want)
+        assert bad.shape[0] == 0, "%d mismatches, first %s (info %s)" % (bad.shape[0], bad[:5], info)
+
+
+@pytest.mark.parametrize("math", ["f16", "tf32"])
+def test_conv_persistent_float(math, oracle, monkeypatch):
+    monkeypatch.setenv("B200_SABER_PERSISTENT", "2")
+    monkeypatch.setenv("B200_SABER_SLAB", "0")
+    test_conv_float((2, 28, 28, 128, 128, 3, 1, 1, 1), math, True, oracle)
+    test_conv_float((2, 24, 24, 64, 64, 1, 1, 0, 1), math, False, oracle)
