@@ -273,7 +273,7 @@ def test_model_walker_reproduces_golden(model, oracle):
     gold = np.load(os.path.join(GOLD, "%s_golden.npz" % model))
     hw = 32 if model == "tiny_resnet" else 224
     n = 2
-    g = modelzoo.BUILDERS[model](batch=1)
+    g = modelzoo.build(model, batch=1)
     x = modelzoo.synthetic_input(n, hw)
     np.testing.assert_array_equal(W.run_fp32(g, x)["prob_out"], gold["prob_fp32"][:n])
     scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration(model).items()}
