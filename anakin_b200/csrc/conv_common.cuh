@@ -62,6 +62,15 @@ struct SlabParams {
     int32_t btile_bytes;           // BN * chunk
     int32_t mma_per_tap;           // chunk / 32
     int32_t a_off, b_off, epi_off; // smem carve-up: slab ring, weight ring (staging reuses the front), residual tile
+    int32_t step_h, step_w;        // conv-output distance between neighbouring tiles (= th, tw unless pooling is fused)
+    int32_t org_h, org_w;          // conv-output origin of tile (0, 0): 0, or -pool_pad with a padded pooling window
+    // fused MAX pooling (b200_conv_desc_t::fuse_pool): the CTA's th x tw conv rectangle is what a ph x pw tile of pooled
+    // pixels needs (neighbouring rectangles overlap when the window exceeds the stride); the pooled pixels are written
+    // straight from the staging tile, 16 bytes per thread
+    int32_t pool, pk, ps, pp;      // fused pooling: window, stride, padding (square)
+    int32_t ph, pw, PHo, PWo;      // pooled tile of a CTA, pooled size
+    int32_t out_ld_bytes;          // pooled tensor: bytes per pixel row pitch
+    void* out_ptr;                 // pooled tensor (bound per run)
 };
 
 // Shared memory carve-up (1024-B aligned base):

@@ -678,6 +678,27 @@ int b200_conv_out_hw(const b200_conv_desc_t* d, int32_t* ho, int32_t* wo) {
     return B200_SUCCESS;
 }
 
+int b200_conv_pooled_hw(const b200_conv_desc_t* d, int32_t* ho, int32_t* wo) {
+    if (!d) return B200_INVALID_VALUE;
+    Geometry g = make_geometry(d);
+    if (!g.ok) return B200_INVALID_VALUE;
+    int32_t oh = g.ho, ow = g.wo;
+    if (d->fuse_pool) {
+        b200_pool_desc_t pd;
+        memset(&pd, 0, sizeof(pd));
+        pd.dtype = d->out_dtype; pd.type = B200_POOL_MAX; pd.n = d->n; pd.h = g.ho; pd.w = g.wo; pd.c = d->k;
+        pd.window_h = pd.window_w = d->fuse_pool;
+        pd.stride_h = pd.stride_w = d->pool_stride > 0 ? d->pool_stride : 2;
+        pd.pad_h = pd.pad_w = d->pool_pad;
+        pd.floor_as_conv = d->pool_floor_as_conv;
+        int st = b200_pool_out_hw(&pd, &oh, &ow);
+        if (st != B200_SUCCESS) return st;
+    }
+    if (ho) *ho = oh;
+    if (wo) *wo = ow;
+    return B200_SUCCESS;
+}
+
 size_t b200_conv_packed_weight_bytes(const b200_conv_desc_t* d) {
     if (!d) return 0;
     Geometry g = make_geometry(d);
@@ -727,7 +748,11 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     if (d->math != B200_MATH_I8 && d->math != B200_MATH_F16 && d->math != B200_MATH_TF32 &&
         d->math != B200_MATH_TF32X3)
         return B200_UNIMPL_ERROR;
-    if (d->fuse_pool != 0) return B200_UNIMPL_ERROR;
+    if (d->fuse_pool < 0 || d->pool_stride < 0 || d->pool_pad < 0) return B200_INVALID_VALUE;
+    // fused pooling lives in the slab kernel's epilogue (a CTA owns a rectangle of the output): stride-1 r x s filters
+    if (d->fuse_pool != 0 && (d->res_dtype >= 0 || d->r * d->s < 2 || d->stride_h != 1 || d->stride_w != 1 ||
+                              d->dil_h != 1 || d->dil_w != 1 || (d->k * dtype_size(d->out_dtype)) % 16 != 0))
+        return B200_UNIMPL_ERROR;
     load_driver_entry_points();
     if (!g_encode_tiled || !g_encode_im2col) return B200_NOT_INITIALIZED;
     Geometry g = make_geometry(d);
@@ -907,6 +932,7 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
         *plan_out = pl;
         return B200_SUCCESS;
     }
+    if (d->fuse_pool != 0) { delete pl; return B200_UNIMPL_ERROR; }   // no rectangle tiling holds this window
     const bool persistent = persistent_plan_setup(pl);
     if (verbose && persistent)
         fprintf(stderr, "[b200_saber] plan persistent: %u x %u tiles on %d CTAs, stages %d smem %d\n", pl->grid.x, pl->grid.y,

@@ -87,7 +87,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int tj = t % sp.tiles_w; t /= sp.tiles_w;
     const int ti = t % sp.tiles_h;
     const int n_img = t / sp.tiles_h;
-    const int p0 = ti * sp.th, q0 = tj * sp.tw;
+    const int p0 = ti * sp.step_h + sp.org_h, q0 = tj * sp.step_w + sp.org_w;
     const int n0 = blockIdx.y * BN;
     const int own_groups = max(0, min(BN, p.K - n0) + 15) >> 4;
 
@@ -316,7 +316,54 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_fence_before();
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-        if (warp_idx == 2 && lane == 0) {
+        if (sp.pool) {
+            // fused MAX pooling: (pooled pixel, 16-byte channel group) items over the 256 epilogue threads; windows are
+            // clipped to the conv output, so padding cells and the garbage rows of the rectangle never take part
+            const int es = p.out_es;
+            const int cpp = min(BN, p.K - n0) * es / 16;
+            const int lgo = lg2(p.out_pw);
+            const uint32_t stage_sa = smem_u32(out_tile);
+            uint8_t* outp = static_cast<uint8_t*>(sp.out_ptr);
+            for (int it = threadIdx.x - 64; it < sp.ph * sp.pw * cpp; it += EPI_THREADS) {
+                const int c16 = it % cpp;
+                const int e = it / cpp;
+                const int oj = e % sp.pw, oi = e / sp.pw;
+                const int gi = ti * sp.ph + oi, gj = tj * sp.pw + oj;
+                if (gi >= sp.PHo || gj >= sp.PWo) continue;
+                const int hs = max(gi * sp.ps - sp.pp, 0), he = min(gi * sp.ps - sp.pp + sp.pk, sp.Ho);
+                const int ws = max(gj * sp.ps - sp.pp, 0), we = min(gj * sp.ps - sp.pp + sp.pk, sp.Wo);
+                uint4 acc = make_uint4(0, 0, 0, 0);
+                bool first = true;
+                for (int y = hs; y < he; ++y) {
+                    for (int x = ws; x < we; ++x) {
+                        const uint4 v = lds128(panel_addr(make_panel_row(stage_sa, lgo, (y - p0) * sp.tw + (x - q0)), c16 * 16));
+                        if (first) { acc = v; first = false; continue; }
+                        if (p.out_dtype == B200_UINT8) {
+                            acc.x = __vmaxu4(acc.x, v.x); acc.y = __vmaxu4(acc.y, v.y); acc.z = __vmaxu4(acc.z, v.z); acc.w = __vmaxu4(acc.w, v.w);
+                        } else if (p.out_dtype == B200_INT8) {
+                            acc.x = __vmaxs4(acc.x, v.x); acc.y = __vmaxs4(acc.y, v.y); acc.z = __vmaxs4(acc.z, v.z); acc.w = __vmaxs4(acc.w, v.w);
+                        } else if (p.out_dtype == B200_HALF) {
+                            uint32_t* a = &acc.x; const uint32_t* b = &v.x;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const __half2 ha = *reinterpret_cast<const __half2*>(a + q), hb = *reinterpret_cast<const __half2*>(b + q);
+                                const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+                                const __half2 r = __halves2half2(fa.x >= fb.x ? __low2half(ha) : __low2half(hb),
+                                                                 fa.y >= fb.y ? __high2half(ha) : __high2half(hb));
+                                a[q] = *reinterpret_cast<const uint32_t*>(&r);
+                            }
+                        } else {
+                            float* a = reinterpret_cast<float*>(&acc.x); const float* b = reinterpret_cast<const float*>(&v.x);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) a[q] = a[q] >= b[q] ? a[q] : b[q];
+                        }
+                    }
+                }
+                const size_t o = ((static_cast<size_t>(n_img) * sp.PHo + gi) * sp.PWo + gj) * sp.out_ld_bytes +
+                                 static_cast<size_t>(n0) * es + c16 * 16;
+                *reinterpret_cast<uint4*>(outp + o) = acc;
+            }
+        } else if (warp_idx == 2 && lane == 0) {
             TL(6);
             const int cols_per_panel = p.out_pw / p.out_es;
             for (int jp = 0; jp < p.out_panels; ++jp) {
@@ -436,7 +483,10 @@ struct SlabLayout {
 };
 
 // Shared-memory layout of one (tile, BN) candidate; false when it cannot fit.
-bool slab_layout(const b200_conv_desc_t& d, const Geometry& g, int th, int tw, int bn, SlabLayout* L) {
+struct PoolTiling { int pk, ps, pp, ph, pw, PHo, PWo; };   // fused pooling: th x tw is the rectangle a ph x pw pooled tile needs
+
+bool slab_layout(const b200_conv_desc_t& d, const Geometry& g, int th, int tw, int bn, SlabLayout* L,
+                 const PoolTiling* pool = nullptr) {
     const bool x3 = d.math == B200_MATH_TF32X3;
     const int planes = x3 ? 2 : 1;
     const int out_es = dtype_size(d.out_dtype);
@@ -447,6 +497,16 @@ bool slab_layout(const b200_conv_desc_t& d, const Geometry& g, int th, int tw, i
     if (sp.th * sp.PW > BLOCK_M || sp.th + d.r - 1 > 256 || sp.PW > 256) return false;
     sp.tiles_h = (g.ho + th - 1) / th;
     sp.tiles_w = (g.wo + tw - 1) / tw;
+    sp.step_h = th; sp.step_w = tw; sp.org_h = 0; sp.org_w = 0;
+    if (pool) {
+        sp.pool = 1; sp.pk = pool->pk; sp.ps = pool->ps; sp.pp = pool->pp;
+        sp.ph = pool->ph; sp.pw = pool->pw; sp.PHo = pool->PHo; sp.PWo = pool->PWo;
+        sp.tiles_h = (pool->PHo + pool->ph - 1) / pool->ph;
+        sp.tiles_w = (pool->PWo + pool->pw - 1) / pool->pw;
+        sp.step_h = pool->ph * pool->ps; sp.step_w = pool->pw * pool->ps;
+        sp.org_h = sp.org_w = -pool->pp;
+        sp.out_ld_bytes = d.ldc * dtype_size(d.out_dtype);
+    }
     const int rows_alloc = ((BLOCK_M + (d.r - 1) * sp.PW + (d.s - 1)) + 7) & ~7;
     sp.slab_bytes = (rows_alloc * g.chunk + 1023) & ~1023;   // rows of `chunk` bytes; 8 rows = one swizzle period
     sp.slab_box_bytes = (th + d.r - 1) * sp.PW * g.chunk;
@@ -513,8 +573,10 @@ bool slab_plan_setup(b200_conv_plan* pl) {
     const Geometry& g = pl->g;
     // B200_SABER_SLAB: 0 never, 2 whenever it applies (tests), default: when its time estimate beats the im2col plan's
     const char* slab_env = getenv("B200_SABER_SLAB");
-    if (slab_env && slab_env[0] == '0') return false;
-    if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) { if (atoi(e) > 1) return false; }   // split-K experiments
+    if (!d.fuse_pool) {   // (a fused pooling has no other kernel to fall back to)
+        if (slab_env && slab_env[0] == '0') return false;
+        if (const char* e = getenv("B200_SABER_FORCE_SPLIT")) { if (atoi(e) > 1) return false; }   // split-K experiments
+    }
     if (d.r * d.s < 2 || d.stride_h != 1 || d.stride_w != 1 || d.dil_h != 1 || d.dil_w != 1) return false;
     if (g.chunk < 32 || d.s > 16 || d.r > 16) return false;
     const int out_es = dtype_size(d.out_dtype);
@@ -532,7 +594,39 @@ bool slab_plan_setup(b200_conv_plan* pl) {
     SlabLayout best{};
     bool have = false;
     const int parts[8] = {1, 2, 3, 4, 6, 8, 12, 16};
-    for (int pi = 0; pi < 8; ++pi) {
+    if (d.fuse_pool) {
+        // pooled tilings: a ph x pw tile of pooled pixels, its conv rectangle th x tw = ((ph-1)*ps + pk) x ((pw-1)*ps + pk)
+        PoolTiling pt{};
+        pt.pk = d.fuse_pool; pt.ps = d.pool_stride > 0 ? d.pool_stride : 2; pt.pp = d.pool_pad;
+        int32_t pho = 0, pwo = 0;
+        if (b200_conv_pooled_hw(&d, &pho, &pwo) != B200_SUCCESS) return false;
+        pt.PHo = pho; pt.PWo = pwo;
+        for (int pi = 0; pi < 8; ++pi) {
+            const int pw = (pwo + parts[pi] - 1) / parts[pi];
+            const int tw = (pw - 1) * pt.ps + pt.pk;
+            const int PW = tw + d.s - 1;
+            if (PW > BLOCK_M) continue;
+            if (pi > 0 && pw < 2) break;
+            const int rows = BLOCK_M / PW;                    // conv rows that fit
+            if (rows < pt.pk) continue;
+            int ph_max = (rows - pt.pk) / pt.ps + 1;
+            if (ph_max > pho) ph_max = pho;
+            const int tiles_h = (pho + ph_max - 1) / ph_max;
+            pt.ph = (pho + tiles_h - 1) / tiles_h;
+            pt.pw = pw;
+            const int th = (pt.ph - 1) * pt.ps + pt.pk;
+            const int cands[4] = {32, 64, 128, 256};
+            for (int ci = 0; ci < 4; ++ci) {
+                const int bn = cands[ci];
+                if (force_bn ? bn != force_bn : (bn > max_bn || (bn > kr32 && bn != 32))) continue;
+                SlabLayout L{};
+                if (!slab_layout(d, g, th, tw, bn, &L, &pt)) continue;
+                if (!have || L.est_clk < best.est_clk) { best = L; have = true; }
+            }
+        }
+        if (!have) return false;
+    }
+    for (int pi = 0; pi < 8 && !d.fuse_pool; ++pi) {
         const int tw = (g.wo + parts[pi] - 1) / parts[pi];
         const int PW = tw + d.s - 1;
         if (PW > BLOCK_M) continue;
@@ -551,7 +645,7 @@ bool slab_plan_setup(b200_conv_plan* pl) {
         }
     }
     if (!have) return false;
-    {
+    if (!d.fuse_pool) {
         // the complete im2col plan (pl->bn, grid, stages, smem): A is fetched once per tap; a ring of fewer than three
         // stages cannot overlap loads and MMAs
         const bool x3 = d.math == B200_MATH_TF32X3;
@@ -615,7 +709,10 @@ int slab_bind_maps(b200_conv_plan* pl, void* encode_tiled_fn, const void* in, co
         if (st != B200_SUCCESS) return st;
         pl->map_a_ptr = in;
     }
-    if (out != pl->map_out_ptr) {
+    if (sp.pool) {
+        pl->sp.out_ptr = out;       // the pooled pixels are written with plain 16-byte stores
+        if (pl->map_out_ptr == nullptr) { pl->map_out = pl->map_a; pl->map_out_ptr = out; }   // placeholder, never used
+    } else if (out != pl->map_out_ptr) {
         int st = encode_nhwc_map(encode_tiled_fn, &pl->map_out, out, d.out_dtype, d.k, d.ldc, g.wo, g.ho, d.n,
                                  pl->kp.out_pw / pl->kp.out_es, sp.tw, sp.th, pl->kp.out_pw);
         if (st != B200_SUCCESS) return st;

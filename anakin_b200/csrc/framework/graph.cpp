@@ -5,6 +5,8 @@
 //   Optimize     reference framework/graph/graph.cpp:350-472,588-804
 #include "graph.h"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <fstream>
 #include <functional>
@@ -693,8 +695,13 @@ void GraphCore::fuse_in_order_patterns() {
             if (!_nodes.count(head_name)) continue;
             NodePtr head = _nodes[head_name];
             if (head->op != pat.chain[0].second) continue;
-            // Conv*Pool fusions are skipped for NV-INT8 (graph.cpp:378-386)
-            if (has_pool && head->bit_type == saber::AK_INT8) continue;
+            // Conv*Pool fusions: the reference skips them for NV-INT8 (graph.cpp:378-386) -- its INT8 conv has no fused
+            // pooling kernel. Here an INT8 conv absorbs a following MAX pooling (the stem kernel runs both in one launch;
+            // int8 pooling passes its input scale through, saber_pooling.cpp:583-584, so the fused node's output simply
+            // carries the conv's output scale). B200_ANAKIN_INT8_CONV_POOL=0 restores the reference behaviour.
+            const bool int8_head = head->bit_type == saber::AK_INT8;
+            static const bool int8_pool_fusion = [] { const char* e = getenv("B200_ANAKIN_INT8_CONV_POOL"); return !(e && e[0] == '0'); }();
+            if (has_pool && int8_head && !int8_pool_fusion) continue;
             std::vector<NodePtr> chain = {head};
             bool ok = true;
             for (size_t i = 1; i < pat.chain.size(); ++i) {
@@ -705,6 +712,11 @@ void GraphCore::fuse_in_order_patterns() {
                 chain.push_back(nxt);
             }
             if (!ok) continue;
+            if (has_pool && int8_head) {
+                const NodePtr& pool = chain.back();
+                if (pool->get_attr_or<std::string>("method", "") != "MAX" || pool->get_attr_or<bool>("global_pooling", false))
+                    continue;
+            }
             // merge attrs of the followers into the head with prefix "<patternNode>_" (graph.cpp:588-762)
             for (size_t i = 1; i < chain.size(); ++i) {
                 const std::string prefix = std::string(pat.chain[i].first) + "_";
@@ -715,6 +727,10 @@ void GraphCore::fuse_in_order_patterns() {
             for (auto& t : last->outs) {
                 Edge e; e.bottom = head->name; e.top = t;
                 e.scale = edge_scale(last->name, t);
+                if (has_pool && int8_head) {   // the tensor the fused node writes is requantised with the conv's output scale
+                    std::vector<float> s_in = edge_scale(chain[chain.size() - 2]->name, last->name);
+                    if (!s_in.empty()) e.scale = s_in;
+                }
                 _edges[e.name()] = e;
                 for (auto& b : _nodes[t]->ins) if (b == last->name) b = head->name;
             }

@@ -39,7 +39,7 @@ bool op_supports_int8(const std::string& op) {
     // who gets an INT8 kernel at all (ANAKIN_REGISTER_OP_HELPER(..., INT8))
     static const std::set<std::string> s = {
         "Convolution", "ConvRelu", "ConvBatchnorm", "ConvBatchnormScale", "ConvBatchnormScaleRelu", "ConvScale",
-        "ConvScaleRelu", "ConvEltwise", "Dense", "Pooling", "Eltwise", "EltwiseRelu", "Split", "Gather", "Input"};
+        "ConvScaleRelu", "ConvEltwise", "ConvReluPool", "ConvBatchnormScaleReluPool", "Dense", "Pooling", "Eltwise", "EltwiseRelu", "Split", "Gather", "Input"};
     return s.count(op) != 0;
 }
 

@@ -61,6 +61,10 @@ struct ConvEngine::Impl {
     bool need_in_transform = false;
     bool stem = false;       // input transform = stem pack (R x S conv over RGB -> R x 1 conv over X2)
     int stem_taps = 0;
+    bool stem_fused = false; // graph-input conv (+ max pool) in one launch straight from the fp32 NCHW tensor (conv_stem.cu)
+    bool stem_pool_fused = false;
+    bool pool_fused = false;  // NHWC conv whose plan runs the following MAX pooling in its epilogue (fuse_pool)
+    b200_stem_desc_t stem_desc;
     Tensor<NV> in_scratch;
     float in_inv_scale = 1.f;
     bool depthwise = false;
@@ -146,14 +150,59 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         static const bool stem_enabled = [] { const char* e = getenv("B200_SABER_STEM_PACK"); return !(e && e[0] == '0'); }();
         P.stem = stem_enabled && !spec.is_fc && spec.group == 1 && in.channel() <= 4 && spec.s > 1 && spec.s <= 8 &&
                  spec.dil_w == 1 && spec.dil_h == 1;
-        if (P.stem) {
+        // ... and when the output is a plain 16-byte-multiple NHWC pixel, the whole layer (quantise, conv, epilogue and a
+        // following MAX pooling) is one launch that reads the fp32 NCHW tensor itself (b200_stem_conv_run)
+        static const bool stem_fused_enabled = [] { const char* e = getenv("B200_SABER_STEM_FUSED"); return !(e && e[0] == '0'); }();
+        P.stem_fused = false;
+        if (P.stem && stem_fused_enabled && !residual) {
+            b200_stem_desc_t& sd = P.stem_desc;
+            memset(&sd, 0, sizeof(sd));
+            sd.math = math;
+            sd.n = in.num(); sd.c = in.channel(); sd.h = in.height(); sd.w = in.width();
+            sd.k = spec.k;
+            sd.r = spec.r; sd.s = spec.s; sd.stride_h = spec.stride_h; sd.stride_w = spec.stride_w;
+            sd.pad_h = spec.pad_h; sd.pad_w = spec.pad_w;
+            sd.relu = spec.relu ? 1 : 0; sd.neg_slope = spec.neg_slope;
+            sd.in_inv_scale = 1.f;
+            if (op == AK_INT8) {
+                if (in.get_scale().empty()) return SaberInvalidValue;
+                sd.in_inv_scale = 1.f / in.get_scale()[0];
+            }
+            sd.out_dtype = out.get_dtype();
+            sd.ldc = out.channel_stored();
+            P.stem_pool_fused = false;
+            if (spec.has_pool && spec.pool.pooling_type == Pooling_max && !spec.pool.global_pooling) {
+                sd.fuse_pool = 1; sd.pool_type = B200_POOL_MAX;
+                sd.pool_window_h = spec.pool.window_h; sd.pool_window_w = spec.pool.window_w;
+                sd.pool_pad_h = spec.pool.pad_h; sd.pool_pad_w = spec.pool.pad_w;
+                sd.pool_stride_h = spec.pool.stride_h; sd.pool_stride_w = spec.pool.stride_w;
+                sd.pool_floor_as_conv = spec.pool.cmp_out_shape_floor_as_conv ? 1 : 0;
+                P.stem_pool_fused = true;
+            }
+            int32_t oh = 0, ow = 0;
+            int st = b200_stem_conv_out_hw(&sd, &oh, &ow);
+            if (st != B200_SUCCESS && P.stem_pool_fused) {     // this pooling does not fuse: conv here, pooling after it
+                sd.fuse_pool = 0;
+                P.stem_pool_fused = false;
+                st = b200_stem_conv_out_hw(&sd, &oh, &ow);
+            }
+            const bool direct = !spec.has_pool || P.stem_pool_fused;
+            P.stem_fused = st == B200_SUCCESS && (!direct || (oh == out.height() && ow == out.width())) &&
+                           (out.get_layout() == Layout_NHWC || (out.height() == 1 && out.width() == 1));
+        }
+        if (P.stem_fused) {
+            P.in_inv_scale = P.stem_desc.in_inv_scale;
+            s = Shape({1, 4, 1, 1}, Layout_NHWC);        // no packed tensor exists; the dtype bookkeeping below stays
+        } else if (P.stem) {
             P.stem_taps = spec.s <= 4 ? 4 : 8;
             const int wo = conv_out_size(in.width(), spec.pad_w, 1, spec.s, spec.stride_w);
             s = Shape({in.num(), P.stem_taps * 4, in.height() + 2 * spec.pad_h, wo}, Layout_NHWC);
         }
         if (P.in_scratch.re_alloc(s, sdt) != SaberSuccess) return SaberOutOfMem;
         CUDA_CHECK(cudaMemsetAsync(P.in_scratch.mutable_data(), 0, P.in_scratch.storage_bytes(), ctx.get_compute_stream()));
-        if (op == AK_INT8) {
+        if (P.stem_fused) {
+            if (op == AK_INT8) P.in_scratch.set_scale(in.get_scale());
+        } else if (op == AK_INT8) {
             if (in.get_scale().empty()) return SaberInvalidValue;
             P.in_inv_scale = 1.f / in.get_scale()[0];
             P.in_scratch.set_scale(in.get_scale());
@@ -191,6 +240,16 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         for (int y = 0; y < H; ++y)
             for (int x = 0; x < W; ++x)
                 for (int c = 0; c < C; ++c) col_map[(y * W + x) * cs + c] = (c * H + y) * W + x;
+    } else if (P.need_in_transform && P.stem_fused) {
+        // bookkeeping in the X2 view (8 taps x 4 channels per output column): the weight image is the same
+        d.n = in.num(); d.h = in.height() + 2 * spec.pad_h;
+        d.w = conv_out_size(in.width(), spec.pad_w, 1, spec.s, spec.stride_w);
+        d.c = 32;
+        d.r = spec.r; d.s = 1;
+        d.pad_h = 0; d.pad_w = 0;
+        d.stride_h = spec.stride_h; d.stride_w = 1;
+        d.dil_h = 1; d.dil_w = 1;
+        c_real = 32;
     } else if (P.need_in_transform && P.stem) {
         d.n = cin->num(); d.h = cin->height(); d.w = cin->width(); d.c = cs;   // X2: c = taps*4
         d.r = spec.r; d.s = 1;
@@ -215,7 +274,27 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
 
     // ---- 3. where the conv writes
     Tensor<NV>* cout = &out;
-    if (spec.has_pool) {
+    // conv + MAX pooling in one launch (the conv plan's fuse_pool) when the window is square; the plan decides
+    static const bool pool_fusion_enabled = [] { const char* e = getenv("B200_SABER_FUSE_POOL"); return !(e && e[0] == '0'); }();
+    P.pool_fused = pool_fusion_enabled && spec.has_pool && !P.need_in_transform && !spec.is_fc && !residual &&
+                   spec.group == 1 && spec.pool.pooling_type == Pooling_max && !spec.pool.global_pooling &&
+                   spec.pool.window_h == spec.pool.window_w && spec.pool.stride_h == spec.pool.stride_w &&
+                   spec.pool.pad_h == spec.pool.pad_w && out.get_layout() == Layout_NHWC;
+    auto setup_pool_scratch = [&]() -> SaberStatus {
+        Shape s({d.n, spec.k, conv_out_size(d.h, d.pad_h, d.dil_h, d.r, d.stride_h),
+                 conv_out_size(d.w, d.pad_w, d.dil_w, d.s, d.stride_w)}, Layout_NHWC);
+        if (P.conv_out_scratch.re_alloc(s, out.get_dtype()) != SaberSuccess) return SaberOutOfMem;
+        CUDA_CHECK(cudaMemsetAsync(P.conv_out_scratch.mutable_data(), 0, P.conv_out_scratch.storage_bytes(), ctx.get_compute_stream()));
+        P.conv_out_scratch.set_scale(out.get_scale());
+        P.pool_desc = make_pool_desc(P.conv_out_scratch, spec.pool);
+        return SaberSuccess;
+    };
+    if (P.pool_fused) {
+        d.fuse_pool = spec.pool.window_h;
+        d.pool_stride = spec.pool.stride_h;
+        d.pool_pad = spec.pool.pad_h;
+        d.pool_floor_as_conv = spec.pool.cmp_out_shape_floor_as_conv ? 1 : 0;
+    } else if (spec.has_pool && !(P.stem_fused && P.stem_pool_fused)) {
         Shape s({d.n, spec.k, conv_out_size(d.h, d.pad_h, d.dil_h, d.r, d.stride_h),
                  conv_out_size(d.w, d.pad_w, d.dil_w, d.s, d.stride_w)}, Layout_NHWC);
         if (P.conv_out_scratch.re_alloc(s, out.get_dtype()) != SaberSuccess) return SaberOutOfMem;
@@ -404,10 +483,22 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         f.math = math; f.in_dtype = cin_dt; f.out_dtype = odt;
         f.m = d.n; f.k = d.c; f.ldx = d.c; f.n_out = spec.k; f.ldo = d.ldc;
         f.relu = d.relu; f.neg_slope = d.neg_slope;
-    } else if (!P.depthwise) {
+    } else if (!P.depthwise && !P.stem_fused) {
         SaberStatus pst = static_cast<SaberStatus>(b200_conv_plan_create(
             &d, P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
             op == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, &P.plan));
+        if (pst == SaberUnImplError && P.pool_fused) {
+            // this pooling does not fuse into this conv: conv into a scratch tensor, pooling after it
+            P.pool_fused = false;
+            d.fuse_pool = 0; d.pool_stride = 0; d.pool_pad = 0; d.pool_floor_as_conv = 0;
+            SaberStatus sst = setup_pool_scratch();
+            if (sst != SaberSuccess) return sst;
+            d.out_dtype = P.conv_out_scratch.get_dtype();
+            d.ldc = P.conv_out_scratch.channel_stored();
+            pst = static_cast<SaberStatus>(b200_conv_plan_create(
+                &d, P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
+                op == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, &P.plan));
+        }
         if (pst != SaberSuccess) return pst;
     }
 
@@ -429,6 +520,17 @@ SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Te
     Impl& P = *_p;
     if (!P.ready) return SaberNotInitialized;
     const void* src = in.data();
+    if (P.need_in_transform && P.stem_fused) {
+        const bool pool_after = P.spec.has_pool && !P.stem_pool_fused;
+        void* dst = pool_after ? P.conv_out_scratch.mutable_data() : out.mutable_data();
+        SaberStatus st = static_cast<SaberStatus>(b200_stem_conv_run(
+            &P.stem_desc, static_cast<const float*>(in.data()), P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
+            P.spec.op_dtype == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, dst, stream));
+        if (st != SaberSuccess) return st;
+        if (pool_after)
+            st = static_cast<SaberStatus>(b200_pool_run(&P.pool_desc, P.conv_out_scratch.data(), out.mutable_data(), stream));
+        return st;
+    }
     if (P.need_in_transform && P.stem) {
         SaberStatus st = static_cast<SaberStatus>(b200_stem_pack(
             static_cast<const float*>(in.data()), P.in_scratch.mutable_data(), P.in_scratch.get_dtype(), in.num(),
@@ -443,7 +545,8 @@ SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Te
         if (st != SaberSuccess) return st;
         src = P.in_scratch.data();
     }
-    void* dst = P.spec.has_pool ? P.conv_out_scratch.mutable_data() : out.mutable_data();
+    const bool pool_after = P.spec.has_pool && !P.pool_fused;
+    void* dst = pool_after ? P.conv_out_scratch.mutable_data() : out.mutable_data();
     SaberStatus st;
     if (P.fc_stream) {
         st = static_cast<SaberStatus>(b200_fc_stream_run(
@@ -456,7 +559,7 @@ SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Te
         st = static_cast<SaberStatus>(b200_conv_plan_run(P.plan, src, residual ? residual->data() : nullptr, dst, stream));
     }
     if (st != SaberSuccess) return st;
-    if (P.spec.has_pool)
+    if (pool_after)
         st = static_cast<SaberStatus>(b200_pool_run(&P.pool_desc, P.conv_out_scratch.data(), out.mutable_data(), stream));
     return st;
 }

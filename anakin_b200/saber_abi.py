@@ -31,7 +31,8 @@ class ConvDesc(C.Structure):
         ("ldc", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
         ("pad_h", C.c_int32), ("pad_w", C.c_int32), ("stride_h", C.c_int32), ("stride_w", C.c_int32),
         ("dil_h", C.c_int32), ("dil_w", C.c_int32), ("relu", C.c_int32), ("neg_slope", C.c_float),
-        ("sum_scale", C.c_float), ("fuse_pool", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("sum_scale", C.c_float), ("fuse_pool", C.c_int32), ("pool_stride", C.c_int32), ("pool_pad", C.c_int32),
+        ("pool_floor_as_conv", C.c_int32),
     ]
 
 
@@ -41,6 +42,19 @@ class PoolDesc(C.Structure):
         ("c", C.c_int32), ("window_h", C.c_int32), ("window_w", C.c_int32), ("pad_h", C.c_int32),
         ("pad_w", C.c_int32), ("stride_h", C.c_int32), ("stride_w", C.c_int32),
         ("global_pooling", C.c_int32), ("floor_as_conv", C.c_int32), ("reserved", C.c_int32 * 2),
+    ]
+
+
+class StemDesc(C.Structure):
+    _fields_ = [
+        ("math", C.c_int32), ("out_dtype", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("h", C.c_int32),
+        ("w", C.c_int32), ("k", C.c_int32), ("ldc", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
+        ("stride_h", C.c_int32), ("stride_w", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+        ("relu", C.c_int32), ("neg_slope", C.c_float), ("in_inv_scale", C.c_float), ("fuse_pool", C.c_int32),
+        ("pool_type", C.c_int32), ("pool_window_h", C.c_int32), ("pool_window_w", C.c_int32),
+        ("pool_pad_h", C.c_int32), ("pool_pad_w", C.c_int32), ("pool_stride_h", C.c_int32),
+        ("pool_stride_w", C.c_int32), ("pool_global", C.c_int32), ("pool_floor_as_conv", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -63,6 +77,7 @@ SYMBOLS = {
     "b200_abi_version": (C.c_int, []),
     "b200_device_ok": (C.c_int, [C.c_int]),
     "b200_conv_out_hw": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_i), C.POINTER(_i)]),
+    "b200_conv_pooled_hw": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_i), C.POINTER(_i)]),
     "b200_conv_packed_weight_bytes": (_sz, [C.POINTER(ConvDesc)]),
     "b200_conv_pack_weights": (C.c_int, [C.POINTER(ConvDesc), _vp, _i, _vp]),
     "b200_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, C.POINTER(_vp)]),
@@ -88,6 +103,11 @@ SYMBOLS = {
     "b200_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "b200_stem_pack": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "b200_nhwc_to_nchw": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "b200_stem_conv_out_hw": (C.c_int, [C.POINTER(StemDesc), C.POINTER(_i), C.POINTER(_i)]),
+    "b200_stem_packed_weight_bytes": (_sz, [C.POINTER(StemDesc)]),
+    "b200_stem_pack_weights": (C.c_int, [C.POINTER(StemDesc), _vp, _vp]),
+    "b200_stem_conv_info": (C.c_int, [C.POINTER(StemDesc)] + [C.POINTER(_i)] * 5),
+    "b200_stem_conv_run": (C.c_int, [C.POINTER(StemDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_launch_count": (C.c_uint64, []),
 }
 

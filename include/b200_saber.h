@@ -134,14 +134,21 @@ typedef struct {
     int32_t relu;      /* 0/1 */
     float neg_slope;   /* float paths only */
     float sum_scale;   /* I8: residual multiplier; float: beta */
-    int32_t fuse_pool; /* 0, or 2 = fused 2x2/s2 max pool after relu (ConvPooling) */
-    int32_t reserved[3];
+    int32_t fuse_pool;  /* 0, or the window w of a w x w MAX pooling fused behind the activation (ConvPooling,
+                           saber_conv_pooling.cpp:36-130): `out` is then the POOLED tensor [n, ph, pw, ldc]
+                           (b200_conv_pooled_hw). Stride-1 r x s convolutions with r*s > 1, no residual,
+                           k * sizeof(out) a 16-byte multiple; anything else: B200_UNIMPL_ERROR from plan_create */
+    int32_t pool_stride; /* fused pooling: stride (0 = 2), padding, PoolingParam::cmp_out_shape_floor_as_conv */
+    int32_t pool_pad;
+    int32_t pool_floor_as_conv;
 } b200_conv_desc_t;
 
 typedef struct b200_conv_plan b200_conv_plan_t;
 
 /* Output spatial size per saber/funcs/funcs_utils.h:41-51. */
 B200_API int b200_conv_out_hw(const b200_conv_desc_t* d, int32_t* ho, int32_t* wo);
+/* Size of what the plan stores: the pooled size (saber/funcs/pooling.h:69-132) when d->fuse_pool, else the conv size. */
+B200_API int b200_conv_pooled_hw(const b200_conv_desc_t* d, int32_t* ho, int32_t* wo);
 
 /* Bytes of the packed (tcgen05 K-major, k-step ordered) weight image. */
 B200_API size_t b200_conv_packed_weight_bytes(const b200_conv_desc_t* d);
@@ -296,6 +303,45 @@ B200_API int b200_stem_pack(const float* in, void* out, int32_t out_dtype, int32
                    float inv_scale, void* stream);
 B200_API int b200_nhwc_to_nchw(const void* in, int32_t in_dtype, float* out, int32_t n, int32_t c, int32_t h,
                       int32_t w, int32_t c_pad, float scale, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Stem convolution: the graph-input conv (fp32 NCHW input with c <= 4 channels, filter width <= 8, dilation 1),
+ * its bias / scale / relu epilogue and -- with fuse_pool = 1 -- the MAX pooling that follows it, in one launch.
+ * Replaces SaberConv2DPooling<NV,*>::{create,dispatch} (saber/funcs/impl/cuda/saber_conv_pooling.cpp:36-130; the SASS
+ * winograd_conv_relu_pooling / direct_conv_bias_relu_maxpool2k2s0p_* entry points, sass_funcs.h:54-427) and the input
+ * quantisation the reference's conv runs on its own input (saber_conv.cpp:341-381) for that layer: the input is
+ * quantised (INT8: clamp(roundf(x * in_inv_scale)), x86_utils.h:318-347) / converted in shared memory, never in HBM.
+ *   in   fp32 NCHW [n, c, h, w]
+ *   out  NHWC [n, oh, ow, ldc] out_dtype, first k channels written; (oh, ow) = the pooled size when fuse_pool,
+ *        else the conv size (b200_stem_conv_out_hw)
+ *   weights: b200_stem_pack_weights of the operand-typed KCRS image ([k][c][r][s] int8 / fp16 bits / fp32)
+ * Epilogue numerics are the conv plan's (see above); pooling is applied to the requantised values, so the result is
+ * bit-identical to conv plan -> b200_pool_run. Pooling other than MAX, or k * sizeof(out) not a 16-byte multiple,
+ * returns B200_UNIMPL_ERROR (the caller runs the separate ops).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t math;      /* b200_math_t */
+    int32_t out_dtype;
+    int32_t n, c, h, w;
+    int32_t k, ldc;
+    int32_t r, s, stride_h, stride_w, pad_h, pad_w;
+    int32_t relu;
+    float neg_slope;
+    float in_inv_scale; /* INT8: 1 / input scale */
+    int32_t fuse_pool;  /* 0 | 1 */
+    int32_t pool_type;  /* a b200_pool_t value: B200_POOL_MAX is what fuses */
+    int32_t pool_window_h, pool_window_w, pool_pad_h, pool_pad_w, pool_stride_h, pool_stride_w;
+    int32_t pool_global, pool_floor_as_conv;
+    int32_t reserved[2];
+} b200_stem_desc_t;
+B200_API int b200_stem_conv_out_hw(const b200_stem_desc_t* d, int32_t* oh, int32_t* ow);
+B200_API size_t b200_stem_packed_weight_bytes(const b200_stem_desc_t* d);
+B200_API int b200_stem_pack_weights(const b200_stem_desc_t* d, const void* src_kcrs, void* dst_packed);
+/* tile the kernel chose: conv rectangle per CTA, output channels per CTA, CTA count, shared memory */
+B200_API int b200_stem_conv_info(const b200_stem_desc_t* d, int32_t* tile_h, int32_t* tile_w, int32_t* block_n,
+                                 int32_t* ctas, int32_t* smem_bytes);
+B200_API int b200_stem_conv_run(const b200_stem_desc_t* d, const float* in_nchw, const void* packed_weights_dev,
+                                const float* bias_dev, const float* scale_dev, void* out, void* stream);
 
 /* Kernel-launch counter (every launch made through this library). */
 B200_API uint64_t b200_launch_count(void);

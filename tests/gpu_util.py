@@ -38,7 +38,7 @@ class ConvRunner:
 
     def __init__(self, math, x_shape_nhwc, in_dtype, w_kcrs, bias_f, scale, out_dtype, res_dtype=-1,
                  stride=(1, 1), pad=(0, 0), dil=(1, 1), relu=False, neg_slope=0.0, sum_scale=1.0,
-                 ldc=None):
+                 ldc=None, fuse_pool=0, pool_stride=0, pool_pad=0, pool_floor_as_conv=False):
         lib = A.load()
         n, h, w, c = x_shape_nhwc
         k, c_real, r, s = w_kcrs.shape
@@ -51,9 +51,11 @@ class ConvRunner:
         d.stride_h, d.stride_w = stride
         d.dil_h, d.dil_w = dil
         d.relu, d.neg_slope, d.sum_scale = int(relu), neg_slope, sum_scale
+        d.fuse_pool, d.pool_stride, d.pool_pad, d.pool_floor_as_conv = fuse_pool, pool_stride, pool_pad, int(pool_floor_as_conv)
         self.d = d
         ho, wo = C.c_int32(), C.c_int32()
-        A.check(lib.b200_conv_out_hw(C.byref(d), C.byref(ho), C.byref(wo)), "conv_out_hw")
+        # (the size of what the plan stores: the pooled size with a fused pooling)
+        A.check(lib.b200_conv_pooled_hw(C.byref(d), C.byref(ho), C.byref(wo)), "conv_pooled_hw")
         self.ho, self.wo = ho.value, wo.value
         nbytes = lib.b200_conv_packed_weight_bytes(C.byref(d))
         packed = np.zeros(nbytes, np.uint8)

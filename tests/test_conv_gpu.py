@@ -394,3 +394,82 @@ def test_conv_persistent_float(math, oracle, monkeypatch):
     monkeypatch.setenv("B200_SABER_SLAB", "0")
     test_conv_float((2, 28, 28, 128, 128, 3, 1, 1, 1), math, True, oracle)
     test_conv_float((2, 24, 24, 64, 64, 1, 1, 0, 1), math, False, oracle)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fused MAX pooling in the conv plan's epilogue (b200_conv_desc_t::fuse_pool; SaberConv2DPooling,
+# saber_conv_pooling.cpp:36-130): bit-exact against conv -> pool of the oracle (int8), reference criterion (float).
+# (n, h, w, c, k, r, pad, pool window, pool stride, pool pad)
+POOL_CASES = [
+    (2, 56, 56, 64, 64, 3, 1, 2, 2, 0),       # VGG-style 3x3 + 2x2/s2
+    (1, 224, 224, 64, 64, 3, 1, 2, 2, 0),     # VGG16 conv1_2 + pool1 at full size
+    (2, 28, 28, 128, 256, 3, 1, 2, 2, 0),     # several n-tiles
+    (1, 30, 26, 32, 48, 3, 1, 3, 2, 0),       # overlapping window (3x3/s2), ceil-mode ragged edge, k = 48
+    (1, 14, 14, 512, 512, 3, 1, 2, 2, 0),     # VGG16 conv5_3 + pool5
+    (2, 17, 19, 64, 32, 5, 2, 3, 2, 1),       # 5x5 filter, padded pooling window
+    (1, 12, 12, 64, 64, 3, 0, 2, 1, 0),       # stride-1 pooling
+]
+
+
+@pytest.mark.parametrize("case", POOL_CASES)
+@pytest.mark.parametrize("variant", ["u8", "s8"])
+def test_conv_fused_pool_int8_bit_exact(case, variant, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev
+    rng = np.random.default_rng(abs(hash((case, variant))) % (2 ** 31))
+    n, h, w, c, k, r, pad, pk, ps, pp = case
+    x = rng.integers(0, 256, (n, h, w, c)).astype(np.uint8)
+    wq = rng.integers(-127, 128, (k, c, r, r)).astype(np.int8)
+    bias = rng.uniform(-2000, 2000, k).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, k).astype(np.float32) * np.float32(1.0 / (40.0 * np.sqrt(c * r * r) * 8))
+    out_dtype = A.UINT8 if variant == "u8" else A.INT8
+    relu = variant == "u8"
+    conv = oracle.conv_s8_nhwc_x86(x, wq, bias, scale, out_dtype=out_dtype, pad=(pad, pad), relu=relu)
+    want = oracle.pool_s8_nhwc(conv, (pk, pk), (pp, pp), (ps, ps), A.POOL_MAX)
+    ldc = (k + 15) // 16 * 16
+    run = ConvRunner(A.MATH_I8, x.shape, A.UINT8, wq, bias, scale, out_dtype, pad=(pad, pad), relu=relu, ldc=ldc,
+                     fuse_pool=pk, pool_stride=ps, pool_pad=pp)
+    assert run.info()["slab"]
+    got = run.run(dev(x))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert (got[..., k:] == 0).all()
+    assert got[..., :k].shape == want.shape, (got.shape, want.shape)
+    np.testing.assert_array_equal(got[..., :k], want)
+
+
+@pytest.mark.parametrize("case", [POOL_CASES[0], POOL_CASES[3], POOL_CASES[4]])
+@pytest.mark.parametrize("math", ["f16", "tf32x3"])
+def test_conv_fused_pool_float(case, math, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner, dev
+    rng = np.random.default_rng(abs(hash((case, math))) % (2 ** 31))
+    n, h, w, c, k, r, pad, pk, ps, pp = case
+    x = rng.uniform(-1, 1, (n, h, w, c)).astype(np.float32)
+    wt = (rng.standard_normal((k, c, r, r)) * np.sqrt(2.0 / (c * r * r))).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, k).astype(np.float32)
+    if math == "f16":
+        xs, ws = x.astype(np.float16), wt.astype(np.float16)
+        x_seen, w_seen, mk, dt = xs.astype(np.float32), ws.astype(np.float32), A.MATH_F16, A.HALF
+    else:
+        xs, ws, x_seen, w_seen, mk, dt = x, wt, x, wt, A.MATH_TF32X3, A.FLOAT
+    conv = oracle.conv_f32_nhwc(x_seen, w_seen, bias, pad=(pad, pad), relu=True, neg_slope=0.1)
+    want = oracle.pool_f32(conv, (pk, pk), (pp, pp), (ps, ps), A.POOL_MAX, nhwc=True)
+    run = ConvRunner(mk, xs.shape, dt, ws, bias, None, A.FLOAT, pad=(pad, pad), relu=True, neg_slope=0.1,
+                     fuse_pool=pk, pool_stride=ps, pool_pad=pp)
+    got = run.run(dev(xs))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    max_ratio, max_diff = oracle.tensor_cmp(want, got)
+    assert max_diff < 1e-3 or max_ratio <= 1e-3, (max_ratio, max_diff, run.info())
+
+
+def test_conv_fused_pool_rejects_what_it_cannot_fuse():
+    from anakin_b200 import saber_abi as A
+    from gpu_util import ConvRunner
+    wq = np.ones((64, 64, 1, 1), np.int8)
+    with pytest.raises(A.SaberError):     # 1x1 conv: no rectangle tiling -> UNIMPL, the caller pools separately
+        ConvRunner(A.MATH_I8, (1, 8, 8, 64), A.UINT8, wq, None, None, A.UINT8, fuse_pool=2, pool_stride=2)

@@ -106,19 +106,28 @@ def test_cpp_parser_fusion_and_save_match_the_walker():
     desc = {n: (op, ins, outs) for n, op, ins, outs in G.describe()}
     groups = W.plan(g)
     head_of = {m["name"]: gr.head["name"] for gr in groups for m in gr.nodes}
+    absorbed = 0
     for gr in groups:
         head = gr.head["name"]
+        if gr.kind == "pool" and head not in desc:
+            # a MAX pooling behind an INT8 conv + relu is absorbed by the conv (the stem kernel runs both in one launch;
+            # a deliberate divergence from graph.cpp:378-386, as ConvEltwise for INT8 is)
+            producer = head_of[gr.inputs[0]]
+            assert desc[producer][0].endswith("Pool") and gr.head["attrs"]["method"] == "MAX", (head, desc[producer][0])
+            absorbed += 1
+            continue
         assert head in desc, head
         op = desc[head][0]
         if gr.kind == "conv":
             want = "ConvEltwise" if gr.elt is not None else (
                 "Conv" + ("Batchnorm" if gr.bn else "") + ("Scale" if gr.scale else "") + ("Relu" if gr.relu else ""))
             want = "Convolution" if want == "Conv" else want
-            assert op == want, (head, op, want)
+            assert op in (want, want + "Pool"), (head, op, want)
             if gr.elt is not None:
                 assert desc[head][1][1] == head_of[gr.residual]   # residual is the second input
-    assert len(desc) == len(groups)
-    # INT8 graphs keep Conv*Pool unfused (graph.cpp:378-386); an fp32 graph fuses the stem pool
+    assert len(desc) == len(groups) - absorbed and absorbed == 1
+    # B200_ANAKIN_INT8_CONV_POOL=0 keeps INT8 Conv*Pool unfused as the reference does (graph.cpp:378-386); an fp32 graph
+    # always fuses the stem pool
     Gf = api.Graph.from_bytes(anakin_bin.dumps(modelzoo.tiny_resnet(2)))
     Gf.Optimize()
     assert dict((n, op) for n, op, _, _ in Gf.describe())["conv1"] == "ConvBatchnormScaleReluPool"

@@ -106,7 +106,8 @@ def test_tiny_resnet_int8_bit_exact(batch, oracle):
         if name not in trace:
             continue
         arr, info = net.read_tensor(name)
-        w_arr, w_dt, w_scale = trace[name]
+        # a conv that absorbed its MAX pooling (INT8 too: one launch of the stem kernel) holds the pooled tensor
+        w_arr, w_dt, w_scale = trace["pool1" if op.endswith("Pool") else name]
         assert info["dtype"] == w_dt, (name, op, info, w_dt)
         got = _valid(arr, info)
         if w_arr.ndim == 4 and got.shape != w_arr.shape:
@@ -159,9 +160,12 @@ def test_resnet50_int8_golden_and_oracle(oracle):
     # full-depth bit-exactness of a late int8 edge against a fresh oracle run
     scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration("resnet50").items()}
     want, trace = W.run_int8(g, x, scales, return_intermediate=True)
-    for node in ("conv1", "res2a_branch2c", "res3d_branch2c", "res5c_branch2c", "pool5"):
+    # (conv1 absorbs pool1 -- one launch of the stem kernel -- so the tensor of node conv1 is the oracle's pool1)
+    for node, oracle_node in (("conv1", "pool1"), ("res2a_branch2c",) * 2, ("res3d_branch2c",) * 2, ("res5c_branch2c",) * 2,
+                              ("pool5",) * 2):
         arr, info = net.read_tensor(node)
-        np.testing.assert_array_equal(_valid(arr, info).reshape(trace[node][0].shape), trace[node][0], err_msg=node)
+        want_t = trace[oracle_node][0]
+        np.testing.assert_array_equal(_valid(arr, info).reshape(want_t.shape), want_t, err_msg=node)
     assert net.launched_ops() <= 60
 
 
