@@ -38,6 +38,13 @@ constexpr int STEM_THREADS = 160;   // warps 0..3: one GEMM row each in the epil
 constexpr int STEM_TAPS = 8;
 constexpr int STEM_TMEM_COLS = 64;
 
+// n / d for small non-negative n by one multiply-high (m = ceil(2^32 / d); exact for n * d < 2^32)
+struct FastDiv {
+    uint32_t m, d;
+    __host__ void set(uint32_t div) { d = div; m = div <= 1 ? 0u : static_cast<uint32_t>(0xFFFFFFFFu / div) + 1u; }
+    __device__ __forceinline__ uint32_t quot(uint32_t n) const { return d <= 1 ? n : __umulhi(n, m); }
+};
+
 struct StemParams {
     const float* in;      // [n][c][h][w] fp32
     const uint8_t* w;     // packed [k][R][ROWB] (X3: the low image follows the high image)
@@ -56,7 +63,10 @@ struct StemParams {
     int32_t qrows, qcols; // line buffer extent (input rows / columns of the patch)
     int32_t krows;        // rows (k) per plane that carry data = ch + (R-1)/stride_h
     int32_t plane_bytes, wt_stride;
-    int32_t off_planes, off_qbuf, off_tail;
+    int32_t off_planes, off_stage, off_tail;
+    int32_t tiles_img, tiles_total;      // tiles per image, tiles in all (walked by gridDim.x persistent CTAs)
+    int32_t cpp, store_tw, store_items;  // store phase: 16-byte chunks per pixel, tile width, items per tile
+    FastDiv div_bn, div_tiles_img, div_tiles_w, div_qcols, div_sh, div_sw, div_cpp, div_tw;
     float inv_scale;
     ConvKParams kp;       // epilogue parameters (relu, dtypes, tables)
 };
@@ -81,10 +91,9 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
     using E = StemElem<MK>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* wt = smem;                           // [PL][R][wt_stride]
+    uint8_t* wt = smem;                           // [PL][R][wt_stride], loaded once per CTA
     uint8_t* planes = smem + p.off_planes;        // [stride_h][PL][plane_bytes]
-    uint8_t* qbuf = smem + p.off_qbuf;            // [qrows][qcols] pixels
-    uint8_t* stage = smem;                        // the operand region, dead once the MMAs have retired
+    uint8_t* stage = smem + p.off_stage;          // epilogue staging tile [128][bn * out_es]
     float* bias_s = reinterpret_cast<float*>(smem + p.off_tail);
     float* scale_s = bias_s + 64;
     uint64_t* mma_bar = reinterpret_cast<uint64_t*>(scale_s + 64);
@@ -92,15 +101,7 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
 
     const int tid = threadIdx.x;
     const int warp_idx = tid >> 5;
-    int t = blockIdx.x;
-    const int tj = t % p.tiles_w; t /= p.tiles_w;
-    const int ti = t % p.tiles_h;
-    const int n_img = t / p.tiles_h;
     const int n0 = blockIdx.y * p.bn;
-    // conv-output origin of this CTA's rectangle (negative rows / columns exist with a padded pooling window: they are
-    // computed from zero input and never read)
-    const int i0 = p.pool ? ti * p.ph * p.ps_h - p.pp_h : ti * p.ch;
-    const int j0 = p.pool ? tj * p.pw * p.ps_w - p.pp_w : tj * p.cw;
 
     if (tid == 0) {
         mbar_init(mma_bar, 1);
@@ -108,18 +109,17 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
     }
     if (warp_idx == 4) tmem_alloc<STEM_TMEM_COLS>(tmem_ptr_smem);
 
-    // ---- weights (independent of the previous kernel): packed [k][R][ROWB] -> R swizzled [bn][ROWB] tiles, as
-    // asynchronous 16-byte copies that land while the input patch is read and converted
+    // ---- weights (independent of the previous kernel), once per CTA: packed [k][R][ROWB] -> R swizzled [bn][ROWB] tiles
+    // as asynchronous 16-byte copies that land while the first input patch is read and converted
     {
         const int per_plane = p.R * p.bn * E::C16;
         for (int i = tid; i < PL * per_plane; i += STEM_THREADS) {
-            const int pl = i / per_plane;
-            int e = i - pl * per_plane;
-            const int c16 = e % E::C16; e /= E::C16;
-            const int oc = e % p.bn;
-            const int r = e / p.bn;
+            const int pl = i >= per_plane ? 1 : 0;
+            uint32_t e = i - pl * per_plane;
+            const uint32_t c16 = e % E::C16; e /= E::C16;      // compile-time divisor
+            const uint32_t r = p.div_bn.quot(e), oc = e - r * p.bn;
             const uint32_t dst = smem_u32(wt + (pl * p.R + r) * p.wt_stride + oc * E::ROWB + ((c16 ^ swz16(oc, E::LG)) << 4));
-            if (n0 + oc < p.k) {
+            if (n0 + static_cast<int>(oc) < p.k) {
                 const uint8_t* src = p.w + (static_cast<size_t>(pl) * p.k + n0 + oc) * p.R * E::ROWB +
                                      static_cast<size_t>(r) * E::ROWB + c16 * 16;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -137,203 +137,226 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
     pdl_launch_dependents();
     pdl_wait_prior_grid();
 
-    // ---- 1. input patch -> line buffer of quantised / converted 4-channel pixels
-    {
-        const int h0 = i0 * p.stride_h - p.pad_h, w0 = j0 * p.stride_w - p.pad_w;
-        const int npx = p.qrows * p.qcols;
-        const size_t plane = static_cast<size_t>(p.h) * p.w_in;
-        const float* img = p.in + static_cast<size_t>(n_img) * p.c * plane;
-        // batches of STEM_PXB pixels per thread: all their loads are in flight before the first conversion
-        constexpr int STEM_PXB = 6;
-        for (int base = tid; base < npx; base += STEM_PXB * STEM_THREADS) {
-        float vv[STEM_PXB][4];
-#pragma unroll
-        for (int u = 0; u < STEM_PXB; ++u) {
-            const int i = base + u * STEM_THREADS;
-            const int qr = i / p.qcols, qc = i - qr * p.qcols;
-            const int y = h0 + qr, x = w0 + qc;
-            const bool ok = i < npx && y >= 0 && y < p.h && x >= 0 && x < p.w_in;
-            const float* px = img + static_cast<size_t>(ok ? y : 0) * p.w_in + (ok ? x : 0);
-#pragma unroll
-            for (int cch = 0; cch < 4; ++cch) vv[u][cch] = (ok && cch < p.c) ? __ldg(px + cch * plane) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < STEM_PXB; ++u) {
-            const int i = base + u * STEM_THREADS;
-            if (i >= npx) break;
-            const float* v = vv[u];
-            if constexpr (MK == KIND_I8) {
-                uint32_t wd = 0;
-#pragma unroll
-                for (int cch = 0; cch < 4; ++cch) {
-                    // secur_cast2char(x * inv): roundf + clamp (reference x86_utils.h:318-347)
-                    float f = roundf(__fmul_rn(v[cch], p.inv_scale));
-                    f = fminf(fmaxf(f, -128.f), 127.f);
-                    wd |= (static_cast<uint32_t>(static_cast<int>(f)) & 0xffu) << (8 * cch);
-                }
-                reinterpret_cast<uint32_t*>(qbuf)[i] = wd;
-            } else if constexpr (MK == KIND_F16) {
-                __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
-                reinterpret_cast<uint2*>(qbuf)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-            } else {
-                reinterpret_cast<float4*>(qbuf)[i] = make_float4(v[0], v[1], v[2], v[3]);
-            }
-        }
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's weight copies have landed
-    __syncthreads();
-
-    // ---- 2. operand planes: row (k, j) of plane `par` = line-buffer pixels [k*stride_h + par][j*stride_w .. +7]
-    {
-        const int per_plane = p.krows * p.cw * E::C16;
-        const uint32_t* q32 = reinterpret_cast<const uint32_t*>(qbuf);
-        for (int i = tid; i < p.stride_h * per_plane; i += STEM_THREADS) {
-            const int par = i / per_plane;
-            int e = i - par * per_plane;
-            const int c16 = e % E::C16; e /= E::C16;
-            const int j = e % p.cw;
-            const int k = e / p.cw;
-            const int qr = k * p.stride_h + par;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (qr < p.qrows) {
-                const uint32_t* s = q32 + (static_cast<size_t>(qr) * p.qcols + j * p.stride_w) * (E::PXB / 4) + c16 * 4;
-                v = make_uint4(s[0], s[1], s[2], s[3]);
-            }
-            const int row = k * p.cw + j;
-            uint8_t* dst = planes + par * PL * p.plane_bytes + row * E::ROWB + ((c16 ^ swz16(row, E::LG)) << 4);
-            if constexpr (X3) {
-                // x = hi + lo, hi = top 19 bits (exact split); the low plane follows the high plane
-                uint4 hq, lq;
-                hq.x = v.x & 0xFFFFE000u; hq.y = v.y & 0xFFFFE000u; hq.z = v.z & 0xFFFFE000u; hq.w = v.w & 0xFFFFE000u;
-                lq.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(hq.x)));
-                lq.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(hq.y)));
-                lq.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(hq.z)));
-                lq.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(hq.w)));
-                *reinterpret_cast<uint4*>(dst) = hq;
-                *reinterpret_cast<uint4*>(dst + p.plane_bytes) = lq;
-            } else {
-                *reinterpret_cast<uint4*>(dst) = v;
-            }
-        }
-    }
-    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-
-    // ---- 3. R filter rows x (ROWB / 32) K slices into one TMEM accumulator
-    if (warp_idx == 4) {
-        if (elect_one()) {
-            const uint32_t lt = layout_type_for_chunk(E::ROWB);
-            const uint32_t hi = ((8u * E::ROWB) >> 4) | (1u << 14) | (lt << 29);   // SBO = 8 rows, version 1, swizzle
-            const uint32_t lbo = 1u << 16;
-            const uint32_t planes16 = smem_u32(planes) >> 4, wt16 = smem_u32(wt) >> 4;
-            const uint32_t plane16 = static_cast<uint32_t>(p.plane_bytes) >> 4, wts16 = static_cast<uint32_t>(p.wt_stride) >> 4;
-            const uint32_t shift16 = static_cast<uint32_t>(p.cw * E::ROWB) >> 4;   // one conv row of the rectangle
-            uint32_t accum = 0;
-#pragma unroll 1
-            for (int r = 0; r < p.R; ++r) {
-                const int par = r % p.stride_h, a = r / p.stride_h;
-                const uint32_t a_hi_pl = (planes16 + par * PL * plane16 + a * shift16) | lbo;
-                const uint32_t b_hi_pl = (wt16 + r * wts16) | lbo;
-#pragma unroll
-                for (uint32_t q = 0; q < 2u * (E::ROWB / 32); q += 2) {
-                    tc_mma_lohi<MK>(tmem_base, a_hi_pl + q, hi, b_hi_pl + q, hi, idesc, accum);
-                    accum = 1;
-                    if (X3) {
-                        tc_mma_lohi<MK>(tmem_base, a_hi_pl + plane16 + q, hi, b_hi_pl + q, hi, idesc, 1);
-                        tc_mma_lohi<MK>(tmem_base, a_hi_pl + q, hi, b_hi_pl + p.R * wts16 + q, hi, idesc, 1);
-                    }
-                }
-            }
-            tc_commit(mma_bar);
-        }
-        __syncwarp();
-    }
-
-    // ---- 4. fused epilogue into the staging tile (GEMM row m = i*cw + j <-> one thread)
     auto lg2 = [](int pw) { return pw == 128 ? 7 : (pw == 64 ? 6 : (pw == 32 ? 5 : 4)); };
     const int lg_out = lg2(p.kp.out_pw);
-    if (warp_idx < 4) {
-        mbar_wait(mma_bar, 0);
-        tc_fence_after();
-        const int m = tid;
-        const PanelRow out_row = make_panel_row(smem_u32(stage), lg_out, m);
-        const PanelRow res_row = out_row;   // no residual
-        const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.bn; c0 += 16) {
-            if (n0 + c0 >= p.k) break;
-            uint32_t v0[16];
-            tmem_ld_32x32b_x16(t_row + c0, v0);
-            tmem_ld_wait();
-            epilogue16<MK>(p.kp, v0, c0, bias_sa, scale_sa, res_row, out_row);
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
+    const uint32_t stage_sa = smem_u32(stage);
+    const uint32_t planes_sa = smem_u32(planes);
+    const size_t plane = static_cast<size_t>(p.h) * p.w_in;
+    const int npx = p.qrows * p.qcols;
+    uint32_t mma_phase = 0;
+    bool first_tile = true;
+    uint32_t tmem_base = 0;
 
-    // ---- 5. (max pool +) store: 16 bytes per thread and item, NHWC
-    {
-        const int es = p.kp.out_es;
-        const int kc = min(p.bn, p.k - n0);                 // channels this CTA stores
-        const int cpp = kc * es / 16;                       // 16-byte chunks per pixel
-        const int out_dt = p.kp.out_dtype;
-        uint8_t* out = static_cast<uint8_t*>(p.out);
-        const int th = p.pool ? p.ph : p.ch, tw = p.pool ? p.pw : p.cw;
-        const int oi0 = p.pool ? ti * p.ph : i0, oj0 = p.pool ? tj * p.pw : j0;
-        for (int it = tid; it < th * tw * cpp; it += STEM_THREADS) {
-            const int c16 = it % cpp;
-            int e = it / cpp;
-            const int oj = e % tw, oi = e / tw;
-            const int gi = oi0 + oi, gj = oj0 + oj;
-            if (gi >= p.OH || gj >= p.OW) continue;
-            const int byte = c16 * 16;
-            uint4 acc;
-            if (!p.pool) {
-                acc = lds128(panel_addr(make_panel_row(smem_u32(stage), lg_out, oi * p.cw + oj), byte));
-            } else {
-                // window in conv coordinates, clipped to the conv output (padding cells never take part)
-                const int hs = max(gi * p.ps_h - p.pp_h, 0), he = min(gi * p.ps_h - p.pp_h + p.pk_h, p.Ho);
-                const int ws = max(gj * p.ps_w - p.pp_w, 0), we = min(gj * p.ps_w - p.pp_w + p.pk_w, p.Wo);
-                bool first = true;
-                acc = make_uint4(0, 0, 0, 0);
-                for (int y = hs; y < he; ++y) {
-                    for (int x = ws; x < we; ++x) {
-                        const uint4 v = lds128(panel_addr(make_panel_row(smem_u32(stage), lg_out, (y - i0) * p.cw + (x - j0)), byte));
-                        if (first) { acc = v; first = false; continue; }
-                        if (out_dt == B200_UINT8) {
-                            acc.x = __vmaxu4(acc.x, v.x); acc.y = __vmaxu4(acc.y, v.y); acc.z = __vmaxu4(acc.z, v.z); acc.w = __vmaxu4(acc.w, v.w);
-                        } else if (out_dt == B200_INT8) {
-                            acc.x = __vmaxs4(acc.x, v.x); acc.y = __vmaxs4(acc.y, v.y); acc.z = __vmaxs4(acc.z, v.z); acc.w = __vmaxs4(acc.w, v.w);
-                        } else if (out_dt == B200_HALF) {
-                            // r >= x ? r : x on every lane, as the stand-alone pooling kernel
-                            uint32_t* a = &acc.x; const uint32_t* b = &v.x;
+    // ---- persistent walk over the CTA's tiles (tile = one ch x cw conv rectangle of one image)
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        const uint32_t n_img = p.div_tiles_img.quot(tile);
+        const uint32_t t_in = tile - n_img * p.tiles_img;
+        const uint32_t ti = p.div_tiles_w.quot(t_in), tj = t_in - ti * p.tiles_w;
+        // conv-output origin of the rectangle (negative rows / columns exist with a padded pooling window: they are
+        // computed from zero input and never read)
+        const int i0 = p.pool ? static_cast<int>(ti) * p.ph * p.ps_h - p.pp_h : static_cast<int>(ti) * p.ch;
+        const int j0 = p.pool ? static_cast<int>(tj) * p.pw * p.ps_w - p.pp_w : static_cast<int>(tj) * p.cw;
+
+        // ---- 1. input patch -> operand planes. Pixel (qr, qc) of the patch is input (h0 + qr, w0 + qc); quantised /
+        // converted once, it is stored at every (output column j, tap t) with j * stride_w + t == qc of row
+        // k = qr / stride_h of plane qr % stride_h -- a 4 / 8 / 16-byte store into the swizzled K-major row (k, j).
+        {
+            const int h0 = i0 * p.stride_h - p.pad_h, w0 = j0 * p.stride_w - p.pad_w;
+            const float* img = p.in + static_cast<size_t>(n_img) * p.c * plane;
+            constexpr int STEM_PXB = 5;     // pixels in flight per thread: all their loads are issued before the first use
+            for (int base = tid; base < npx; base += STEM_PXB * STEM_THREADS) {
+                float vv[STEM_PXB][3];
+                float v3[STEM_PXB];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const __half2 ha = *reinterpret_cast<const __half2*>(a + q), hb = *reinterpret_cast<const __half2*>(b + q);
-                                const float2 fa = __half22float2(ha), fb = __half22float2(hb);
-                                const __half2 r = __halves2half2(fa.x >= fb.x ? __low2half(ha) : __low2half(hb),
-                                                                 fa.y >= fb.y ? __high2half(ha) : __high2half(hb));
-                                a[q] = *reinterpret_cast<const uint32_t*>(&r);
-                            }
+                for (int u = 0; u < STEM_PXB; ++u) {
+                    const int i = base + u * STEM_THREADS;
+                    const uint32_t qr = p.div_qcols.quot(i), qc = i - qr * p.qcols;
+                    const int y = h0 + static_cast<int>(qr), x = w0 + static_cast<int>(qc);
+                    const bool ok = i < npx && y >= 0 && y < p.h && x >= 0 && x < p.w_in;
+                    const float* px = img + static_cast<size_t>(ok ? y : 0) * p.w_in + (ok ? x : 0);
+#pragma unroll
+                    for (int cch = 0; cch < 3; ++cch) vv[u][cch] = (ok && cch < p.c) ? __ldg(px + cch * plane) : 0.f;
+                    v3[u] = (ok && p.c > 3) ? __ldg(px + 3 * plane) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < STEM_PXB; ++u) {
+                    const int i = base + u * STEM_THREADS;
+                    if (i >= npx) break;
+                    const uint32_t qr = p.div_qcols.quot(i), qc = i - qr * p.qcols;
+                    const uint32_t k = p.div_sh.quot(qr), par = qr - k * p.stride_h;
+                    uint32_t t = 0, j = qc;                     // stride_w == 1: every tap of column j = qc - t
+                    if (p.stride_w > 1) { j = p.div_sw.quot(qc); t = qc - j * p.stride_w; }
+                    // the pixel in operand precision
+                    uint32_t w0q = 0, w1q = 0, w2q = 0, w3q = 0;      // hi (or the only) plane: 4 | 8 | 16 bytes
+                    uint32_t l0q = 0, l1q = 0, l2q = 0, l3q = 0;      // X3: the low plane
+                    if constexpr (MK == KIND_I8) {
+#pragma unroll
+                        for (int cch = 0; cch < 4; ++cch) {
+                            // secur_cast2char(x * inv): roundf + clamp (reference x86_utils.h:318-347)
+                            float f = roundf(__fmul_rn(cch < 3 ? vv[u][cch] : v3[u], p.inv_scale));
+                            f = fminf(fmaxf(f, -128.f), 127.f);
+                            w0q |= (static_cast<uint32_t>(static_cast<int>(f)) & 0xffu) << (8 * cch);
+                        }
+                    } else if constexpr (MK == KIND_F16) {
+                        __half2 a = __floats2half2_rn(vv[u][0], vv[u][1]), b = __floats2half2_rn(vv[u][2], v3[u]);
+                        w0q = *reinterpret_cast<uint32_t*>(&a); w1q = *reinterpret_cast<uint32_t*>(&b);
+                    } else {
+                        w0q = __float_as_uint(vv[u][0]); w1q = __float_as_uint(vv[u][1]);
+                        w2q = __float_as_uint(vv[u][2]); w3q = __float_as_uint(v3[u]);
+                        if constexpr (X3) {   // x = hi + lo, hi = top 19 bits (exact split)
+                            const uint32_t h0q = w0q & 0xFFFFE000u, h1q = w1q & 0xFFFFE000u, h2q = w2q & 0xFFFFE000u, h3q = w3q & 0xFFFFE000u;
+                            l0q = __float_as_uint(__fsub_rn(__uint_as_float(w0q), __uint_as_float(h0q)));
+                            l1q = __float_as_uint(__fsub_rn(__uint_as_float(w1q), __uint_as_float(h1q)));
+                            l2q = __float_as_uint(__fsub_rn(__uint_as_float(w2q), __uint_as_float(h2q)));
+                            l3q = __float_as_uint(__fsub_rn(__uint_as_float(w3q), __uint_as_float(h3q)));
+                            w0q = h0q; w1q = h1q; w2q = h2q; w3q = h3q;
+                        }
+                    }
+                    const uint32_t plane_sa = planes_sa + par * PL * p.plane_bytes;
+                    int jj = static_cast<int>(j);
+#pragma unroll 1
+                    for (; t < STEM_TAPS && jj >= 0; t += p.stride_w, --jj) {
+                        if (jj >= p.cw) continue;
+                        const uint32_t row = k * p.cw + jj;
+                        const uint32_t boff = t * E::PXB;
+                        const uint32_t a = plane_sa + row * E::ROWB + ((((boff >> 4) ^ swz16(row, E::LG))) << 4) + (boff & 15u);
+                        if constexpr (MK == KIND_I8) {
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(w0q) : "memory");
+                        } else if constexpr (MK == KIND_F16) {
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(w0q), "r"(w1q) : "memory");
                         } else {
-                            float* a = reinterpret_cast<float*>(&acc.x); const float* b = reinterpret_cast<const float*>(&v.x);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) a[q] = a[q] >= b[q] ? a[q] : b[q];
+                            sts128(a, make_uint4(w0q, w1q, w2q, w3q));
+                            if constexpr (X3) sts128(a + p.plane_bytes, make_uint4(l0q, l1q, l2q, l3q));
                         }
                     }
                 }
             }
-            const size_t o = ((static_cast<size_t>(n_img) * p.OH + gi) * p.OW + gj) * p.ldc * es + static_cast<size_t>(n0) * es + byte;
-            *reinterpret_cast<uint4*>(out + o) = acc;
         }
+        if (first_tile) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's weight copies have landed
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (first_tile) { tmem_base = *tmem_ptr_smem; first_tile = false; }
+
+        // ---- 2. R filter rows x (ROWB / 32) K slices into the TMEM accumulator
+        if (warp_idx == 4) {
+            if (elect_one()) {
+                const uint32_t lt = layout_type_for_chunk(E::ROWB);
+                const uint32_t hi = ((8u * E::ROWB) >> 4) | (1u << 14) | (lt << 29);   // SBO = 8 rows, version 1, swizzle
+                const uint32_t lbo = 1u << 16;
+                const uint32_t planes16 = planes_sa >> 4, wt16 = smem_u32(wt) >> 4;
+                const uint32_t plane16 = static_cast<uint32_t>(p.plane_bytes) >> 4, wts16 = static_cast<uint32_t>(p.wt_stride) >> 4;
+                const uint32_t shift16 = static_cast<uint32_t>(p.cw * E::ROWB) >> 4;   // one conv row of the rectangle
+                uint32_t accum = 0;
+                int par = 0, a = 0;
+#pragma unroll 1
+                for (int r = 0; r < p.R; ++r) {
+                    const uint32_t a_hi_pl = (planes16 + par * PL * plane16 + a * shift16) | lbo;
+                    const uint32_t b_hi_pl = (wt16 + r * wts16) | lbo;
+#pragma unroll
+                    for (uint32_t q = 0; q < 2u * (E::ROWB / 32); q += 2) {
+                        tc_mma_lohi<MK>(tmem_base, a_hi_pl + q, hi, b_hi_pl + q, hi, idesc, accum);
+                        accum = 1;
+                        if (X3) {
+                            tc_mma_lohi<MK>(tmem_base, a_hi_pl + plane16 + q, hi, b_hi_pl + q, hi, idesc, 1);
+                            tc_mma_lohi<MK>(tmem_base, a_hi_pl + q, hi, b_hi_pl + p.R * wts16 + q, hi, idesc, 1);
+                        }
+                    }
+                    if (++par == p.stride_h) { par = 0; ++a; }
+                }
+                tc_commit(mma_bar);
+            }
+            __syncwarp();
+        }
+
+        // ---- 3. fused epilogue into the staging tile (GEMM row m = i*cw + j <-> one thread)
+        if (warp_idx < 4) {
+            mbar_wait(mma_bar, mma_phase);
+            tc_fence_after();
+            const PanelRow out_row = make_panel_row(stage_sa, lg_out, tid);
+            const PanelRow res_row = out_row;   // no residual
+            const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                if (n0 + c0 >= p.k) break;
+                uint32_t v0[16];
+                tmem_ld_32x32b_x16(t_row + c0, v0);
+                tmem_ld_wait();
+                epilogue16<MK>(p.kp, v0, c0, bias_sa, scale_sa, res_row, out_row);
+            }
+            tc_fence_before();
+        }
+        mma_phase ^= 1;
+        __syncthreads();
+
+        // ---- 4. (max pool +) store: 16 bytes per thread and item, NHWC
+        {
+            const int es = p.kp.out_es;
+            const int out_dt = p.kp.out_dtype;
+            uint8_t* out = static_cast<uint8_t*>(p.out);
+            const int oi0 = p.pool ? static_cast<int>(ti) * p.ph : i0, oj0 = p.pool ? static_cast<int>(tj) * p.pw : j0;
+            for (int it = tid; it < p.store_items; it += STEM_THREADS) {
+                const uint32_t e = p.div_cpp.quot(it), c16 = it - e * p.cpp;
+                const uint32_t oi = p.div_tw.quot(e), oj = e - oi * p.store_tw;
+                const int gi = oi0 + static_cast<int>(oi), gj = oj0 + static_cast<int>(oj);
+                const int byte = c16 * 16;
+                if (gi >= p.OH || gj >= p.OW || n0 * es + byte + 16 > p.k * es) continue;   // (ragged last n-tile)
+                uint4 acc;
+                if (!p.pool) {
+                    acc = lds128(panel_addr(make_panel_row(stage_sa, lg_out, oi * p.cw + oj), byte));
+                } else {
+                    // window in conv coordinates, clipped to the conv output (padding cells never take part)
+                    const int hs = max(gi * p.ps_h - p.pp_h, 0), he = min(gi * p.ps_h - p.pp_h + p.pk_h, p.Ho);
+                    const int ws = max(gj * p.ps_w - p.pp_w, 0), we = min(gj * p.ps_w - p.pp_w + p.pk_w, p.Wo);
+                    bool first = true;
+                    acc = make_uint4(0, 0, 0, 0);
+                    for (int y = hs; y < he; ++y) {
+                        int m = (y - i0) * p.cw + (ws - j0);
+                        for (int x = ws; x < we; ++x, ++m) {
+                            const uint4 v = lds128(panel_addr(make_panel_row(stage_sa, lg_out, m), byte));
+                            if (first) { acc = v; first = false; continue; }
+                            if (out_dt == B200_UINT8) {
+                                acc.x = __vmaxu4(acc.x, v.x); acc.y = __vmaxu4(acc.y, v.y); acc.z = __vmaxu4(acc.z, v.z); acc.w = __vmaxu4(acc.w, v.w);
+                            } else if (out_dt == B200_INT8) {
+                                acc.x = __vmaxs4(acc.x, v.x); acc.y = __vmaxs4(acc.y, v.y); acc.z = __vmaxs4(acc.z, v.z); acc.w = __vmaxs4(acc.w, v.w);
+                            } else if (out_dt == B200_HALF) {
+                                // r >= x ? r : x on every lane, as the stand-alone pooling kernel
+                                uint32_t* a = &acc.x; const uint32_t* b = &v.x;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const __half2 ha = *reinterpret_cast<const __half2*>(a + q), hb = *reinterpret_cast<const __half2*>(b + q);
+                                    const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+                                    const __half2 r = __halves2half2(fa.x >= fb.x ? __low2half(ha) : __low2half(hb),
+                                                                     fa.y >= fb.y ? __high2half(ha) : __high2half(hb));
+                                    a[q] = *reinterpret_cast<const uint32_t*>(&r);
+                                }
+                            } else {
+                                float* a = reinterpret_cast<float*>(&acc.x); const float* b = reinterpret_cast<const float*>(&v.x);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) a[q] = a[q] >= b[q] ? a[q] : b[q];
+                            }
+                        }
+                    }
+                }
+                const size_t o = ((static_cast<size_t>(n_img) * p.OH + gi) * p.OW + gj) * p.ldc * es + static_cast<size_t>(n0) * es + byte;
+                *reinterpret_cast<uint4*>(out + o) = acc;
+            }
+        }
+        // the next tile rewrites the planes and the staging tile, and its MMAs the accumulator
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
     }
 
-    __syncthreads();
+    if (first_tile) {   // a CTA without a tile still owns a TMEM allocation
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = *tmem_ptr_smem;
+    }
     if (warp_idx == 4) {
         tc_fence_after();
         tmem_dealloc<STEM_TMEM_COLS>(tmem_base);
@@ -434,16 +457,20 @@ int stem_plan(const b200_stem_desc_t* d, StemPlan* P) {
     for (int bn = kr; bn >= 16; bn >>= 1) {
         p.bn = bn;
         p.wt_stride = (bn * rowb + 1023) & ~1023;
-        const int operands = planes_n * p.R * p.wt_stride + p.stride_h * planes_n * p.plane_bytes;
         p.off_planes = planes_n * p.R * p.wt_stride;
-        const int stage = BLOCK_M * bn * out_es;
-        int front = operands > stage ? operands : stage;
-        p.off_qbuf = (front + 15) & ~15;
-        p.off_tail = (p.off_qbuf + p.qrows * p.qcols * 4 * es + 15) & ~15;
+        p.off_stage = p.off_planes + p.stride_h * planes_n * p.plane_bytes;      // (1024-aligned: every part is)
+        p.off_tail = p.off_stage + BLOCK_M * bn * out_es;
         P->smem_bytes = p.off_tail + 2 * 64 * 4 + 16 + 1024;
         if (P->smem_bytes <= MAX_SMEM) break;
         if (bn == 16) return B200_OUT_OF_MEM;
     }
+    p.tiles_img = p.tiles_h * p.tiles_w;
+    p.tiles_total = d->n * p.tiles_img;
+    p.cpp = (d->k < p.bn ? d->k : p.bn) * out_es / 16;   // (a ragged last n-tile stores fewer: guarded by the kernel)
+    p.store_tw = p.pool ? p.pw : p.cw;
+    p.store_items = (p.pool ? p.ph * p.pw : p.ch * p.cw) * p.cpp;
+    p.div_bn.set(p.bn); p.div_tiles_img.set(p.tiles_img); p.div_tiles_w.set(p.tiles_w); p.div_qcols.set(p.qcols);
+    p.div_sh.set(p.stride_h); p.div_sw.set(p.stride_w); p.div_cpp.set(p.cpp); p.div_tw.set(p.store_tw);
     ConvKParams& kp = p.kp;
     kp.K = d->k;
     kp.relu = d->relu; kp.neg_slope = d->neg_slope; kp.sum_scale = 1.f;
@@ -458,7 +485,18 @@ int stem_plan(const b200_stem_desc_t* d, StemPlan* P) {
     if (d->math == B200_MATH_I8) { a_fmt = 1u; b_fmt = 1u; c_fmt = 2u; }       // the graph input quantises to s8
     else if (d->math != B200_MATH_F16) { a_fmt = b_fmt = 2u; }
     P->idesc = make_idesc(c_fmt, a_fmt, b_fmt, BLOCK_M, p.bn);
-    P->grid = dim3(d->n * p.tiles_h * p.tiles_w, (d->k + p.bn - 1) / p.bn, 1);
+    // persistent CTAs: a few per SM (they hide each other's serial phases), each walking its share of the tiles with the
+    // weights, tables, barrier and TMEM allocation set up once
+    {
+        const int n_tiles_n = (d->k + p.bn - 1) / p.bn;
+        int per_sm = (MAX_SMEM + 1024) / (P->smem_bytes + 1024);
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        int ctas = sm_count() * per_sm / n_tiles_n;
+        if (ctas < 1) ctas = 1;
+        if (ctas > p.tiles_total) ctas = p.tiles_total;
+        P->grid = dim3(ctas, n_tiles_n, 1);
+    }
     P->kind = d->math == B200_MATH_I8 ? KIND_I8 : (d->math == B200_MATH_F16 ? KIND_F16 : (x3 ? KIND_TF32X3 : KIND_TF32));
     return B200_SUCCESS;
 }

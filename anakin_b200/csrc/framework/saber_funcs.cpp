@@ -319,7 +319,7 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
     const float* b = has_bias ? static_cast<const float*>(spec.bias->data()) : nullptr;
     const DataType odt = cout->get_dtype();
     float in_scale = 1.f, out_scale = 1.f;
-    if (op == AK_INT8 && !P.depthwise) {
+    if (op == AK_INT8) {
         if (cin->get_scale().empty()) return SaberInvalidValue;
         in_scale = cin->get_scale()[0];
         if (odt != AK_FLOAT) {
@@ -358,8 +358,51 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
     if (!P.dw) {
         std::shared_ptr<DevWeights> dw = std::make_shared<DevWeights>();
         std::vector<float> bias_f(spec.k, 0.f), scale_f;
-        if (P.depthwise) {
-            if (op == AK_INT8) return SaberUnImplError;
+        // INT8 epilogue tables from the per-output-channel weight scales (jit_avx512_core_x8s8s32x_conv.cpp:55-62,226-255)
+        auto int8_tables = [&](const std::vector<float>& w_scale, int count) {
+            const float u = 127.f / 255.f;
+            scale_f.assign(count, 1.f);
+            bias_f.assign(count, 0.f);
+            for (int i = 0; i < spec.k; ++i) {
+                float sc;
+                if (cin_dt == AK_INT8 && odt == AK_INT8) sc = (w_scale[i] * in_scale) / out_scale;
+                else if (cin_dt == AK_UINT8 && odt == AK_UINT8) sc = (w_scale[i] * in_scale * u) / (out_scale * u);
+                else if (cin_dt == AK_UINT8 && odt == AK_INT8) sc = (w_scale[i] * in_scale * u) / out_scale;
+                else if (cin_dt == AK_UINT8 && odt == AK_FLOAT) sc = w_scale[i] * in_scale * u;
+                else if (cin_dt == AK_INT8 && odt == AK_UINT8) sc = (w_scale[i] * in_scale) / (out_scale * u);
+                else sc = w_scale[i] * in_scale;
+                scale_f[i] = sc;
+                const float inv = (cin_dt == AK_UINT8) ? (1.f / (w_scale[i] * in_scale * u))
+                                                       : (1.f / (w_scale[i] * in_scale));
+                bias_f[i] = b ? b[i] * inv : 0.f;
+            }
+        };
+        if (P.depthwise && op == AK_INT8) {
+            // weights [c][1][r][s] -> int8 [r][s][c_stored], one scale per channel (x86_utils.h:293-323: max|w|/127,
+            // truncating cast); SaberDepthWiseConv's INT8 arm (saber_depthwiseconv_act.cu:84-295)
+            if (odt != AK_INT8 && odt != AK_UINT8) return SaberUnImplError;
+            const int RS = spec.r * spec.s;
+            std::vector<int8_t> ww(static_cast<size_t>(RS) * cs, 0);
+            std::vector<float> w_scale(spec.k, 1.f);
+            for (int c = 0; c < spec.k; ++c) {
+                float sw = 1.f;
+                if (wq8) {
+                    sw = wq_scale_of(c);
+                } else {
+                    float mx = 0.f;
+                    for (int i = 0; i < RS; ++i) { const float a = fabsf(w[c * RS + i]); mx = a > mx ? a : mx; }
+                    sw = mx / 127.f;
+                    if (sw == 0.f) sw = 1.f;
+                }
+                w_scale[c] = sw;
+                for (int i = 0; i < RS; ++i)
+                    ww[static_cast<size_t>(i) * cs + c] = wq8 ? wq[c * RS + i] : static_cast<int8_t>(w[c * RS + i] / sw);
+            }
+            if (upload(dw->w, ww.data(), ww.size()) != SaberSuccess) return SaberOutOfMem;
+            int8_tables(w_scale, cs);
+            if (upload(dw->scale, scale_f.data(), scale_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+            if (upload(dw->bias, bias_f.data(), bias_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
+        } else if (P.depthwise) {
             // weights [c][1][r][s] -> [r][s][c_stored]
             const int RS = spec.r * spec.s;
             auto wv = [&](int c, int i) { return wq8 ? wq[c * RS + i] * wq_scale_of(c) : w[c * RS + i]; };
@@ -438,21 +481,7 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
             }
 
             if (op == AK_INT8) {
-                const float u = 127.f / 255.f;
-                scale_f.assign(spec.k, 1.f);
-                for (int i = 0; i < spec.k; ++i) {
-                    float s;
-                    if (cin_dt == AK_INT8 && odt == AK_INT8) s = (w_scale[i] * in_scale) / out_scale;
-                    else if (cin_dt == AK_UINT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale * u) / (out_scale * u);
-                    else if (cin_dt == AK_UINT8 && odt == AK_INT8) s = (w_scale[i] * in_scale * u) / out_scale;
-                    else if (cin_dt == AK_UINT8 && odt == AK_FLOAT) s = w_scale[i] * in_scale * u;
-                    else if (cin_dt == AK_INT8 && odt == AK_UINT8) s = (w_scale[i] * in_scale) / (out_scale * u);
-                    else s = w_scale[i] * in_scale;
-                    scale_f[i] = s;
-                    const float inv = (cin_dt == AK_UINT8) ? (1.f / (w_scale[i] * in_scale * u))
-                                                           : (1.f / (w_scale[i] * in_scale));
-                    bias_f[i] = b ? b[i] * inv : 0.f;
-                }
+                int8_tables(w_scale, spec.k);
                 if (upload(dw->scale, scale_f.data(), scale_f.size() * sizeof(float)) != SaberSuccess) return SaberOutOfMem;
             } else {
                 for (int i = 0; i < spec.k; ++i) bias_f[i] = b ? b[i] : 0.f;
@@ -553,8 +582,9 @@ SaberStatus ConvEngine::run(const Tensor<NV>& in, const Tensor<NV>* residual, Te
             &P.fc_desc, src, P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
             P.spec.op_dtype == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, dst, stream));
     } else if (P.depthwise) {
-        st = static_cast<SaberStatus>(b200_dwconv_run(&P.desc, src, P.dw->w.ptr,
-                                                      static_cast<const float*>(P.dw->bias.ptr), nullptr, dst, stream));
+        st = static_cast<SaberStatus>(b200_dwconv_run(
+            &P.desc, src, P.dw->w.ptr, static_cast<const float*>(P.dw->bias.ptr),
+            P.spec.op_dtype == AK_INT8 ? static_cast<const float*>(P.dw->scale.ptr) : nullptr, dst, stream));
     } else {
         st = static_cast<SaberStatus>(b200_conv_plan_run(P.plan, src, residual ? residual->data() : nullptr, dst, stream));
     }

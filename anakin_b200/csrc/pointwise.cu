@@ -765,44 +765,109 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ in, float* __restri
 }
 
 // ------------------------------------------------------------------ depthwise conv
-// NHWC, one thread = one output pixel x VEC channels, weights [r][s][c].
-// fp32/fp16 math in fp32: acc = sum x*w (r,s order), + bias, relu(neg_slope).
-template <typename T, int VEC>
-__global__ void dwconv_kernel(const T* __restrict__ in, const T* __restrict__ wgt,
-                              const float* __restrict__ bias, T* __restrict__ out, int n, int h, int w,
-                              int c, int oh, int ow, int r, int s, int ph, int pw, int sh, int sw,
-                              int dh, int dw, int relu, float slope) {
-    const int cv = c / VEC;
+// 128-bit vectorised depthwise convolution (saber_depthwiseconv_act.cu:84-295): one thread = one output pixel x 16
+// bytes of channels (4 fp32 | 8 fp16 | 16 int8). Consecutive threads take consecutive channel groups of a pixel, so
+// every tap is one coalesced 16-byte load per thread of the input and of the [r][s][c] weights (L1-resident).
+//   f32 / f16 : fp32 FMA in (r, s) order, + bias, relu(neg_slope)  -- the arithmetic of dwconv_kernel
+//   int8      : exact s32 accumulation (dp4a against the weight word masked to one byte = one channel's product),
+//               then the x86 Saber epilogue of the conv kernels: f = (acc + bias) * scale, relu, rne + saturate
+template <int MODE>   // 0 f32, 1 f16, 2 int8
+__global__ void __launch_bounds__(256)
+dwconv_vec_kernel(const uint4* __restrict__ in, const uint4* __restrict__ wgt, const float* __restrict__ bias,
+                  const float* __restrict__ scale, uint4* __restrict__ out, int n, int h, int w, int cv, int oh, int ow,
+                  int r, int s, int ph, int pw, int sh, int sw, int dh, int dw, int relu, float slope, int in_unsigned,
+                  int out_dtype) {
+    pdl_enter();
+    constexpr int NCH = MODE == 0 ? 4 : (MODE == 1 ? 8 : 16);
     const long long total = 1ll * n * oh * ow * cv;
-    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total;
-         idx += 1ll * gridDim.x * blockDim.x) {
+    for (long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x; idx < total; idx += 1ll * gridDim.x * blockDim.x) {
         const int v = static_cast<int>(idx % cv);
         long long t = idx / cv;
         const int x0 = static_cast<int>(t % ow); t /= ow;
         const int y0 = static_cast<int>(t % oh);
         const int b = static_cast<int>(t / oh);
-        float acc[VEC];
+        float facc[MODE == 2 ? 1 : NCH];
+        int iacc[MODE == 2 ? NCH : 1];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int i = 0; i < (MODE == 2 ? 1 : NCH); ++i) facc[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < (MODE == 2 ? NCH : 1); ++i) iacc[i] = 0;
         for (int kr = 0; kr < r; ++kr) {
             const int iy = y0 * sh - ph + kr * dh;
             if (iy < 0 || iy >= h) continue;
             for (int ks = 0; ks < s; ++ks) {
                 const int ix = x0 * sw - pw + ks * dw;
                 if (ix < 0 || ix >= w) continue;
-                const T* ip = in + ((1ll * b * h + iy) * w + ix) * c + v * VEC;
-                const T* wp = wgt + (1ll * kr * s + ks) * c + v * VEC;
+                const uint4 xv = __ldg(in + ((1ll * b * h + iy) * w + ix) * cv + v);
+                const uint4 wv = __ldg(wgt + (1ll * kr * s + ks) * cv + v);
+                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+                if constexpr (MODE == 0) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i)
-                    acc[i] = __fmaf_rn(static_cast<float>(ip[i]), static_cast<float>(wp[i]), acc[i]);
+                    for (int i = 0; i < 4; ++i) facc[i] = __fmaf_rn(__uint_as_float(xw[i]), __uint_as_float(ww[i]), facc[i]);
+                } else if constexpr (MODE == 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&xw[i]));
+                        const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
+                        facc[2 * i] = __fmaf_rn(a.x, c2.x, facc[2 * i]);
+                        facc[2 * i + 1] = __fmaf_rn(a.y, c2.y, facc[2 * i + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t wm = ww[i] & (0xFFu << (8 * j));
+                            int& a = iacc[4 * i + j];
+                            if (in_unsigned) asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(a) : "r"(xw[i]), "r"(wm));
+                            else asm("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(a) : "r"(xw[i]), "r"(wm));
+                        }
+                    }
+                }
             }
         }
-        T* op = out + ((1ll * b * oh + y0) * ow + x0) * c + v * VEC;
+        const int c0 = v * NCH;
+        const long long o = ((1ll * b * oh + y0) * ow + x0) * cv + v;
+        if constexpr (MODE == 2) {
+            float f[16];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float y = acc[i] + (bias ? __ldg(bias + v * VEC + i) : 0.f);
-            if (relu) y = y > 0.f ? y : y * slope;
-            op[i] = static_cast<T>(y);
+            for (int i = 0; i < 16; ++i) {
+                f[i] = __fmul_rn(__fadd_rn(__int2float_rn(iacc[i]), bias ? __ldg(bias + c0 + i) : 0.f),
+                                 scale ? __ldg(scale + c0 + i) : 1.f);
+                if (relu) f[i] = fmaxf(f[i], 0.f);
+            }
+            uint32_t q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t wd = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t code;
+                    if (out_dtype == B200_UINT8) asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(code) : "f"(f[4 * i + j]));
+                    else asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(code) : "f"(f[4 * i + j]));
+                    wd |= (code & 0xffu) << (8 * j);
+                }
+                q[i] = wd;
+            }
+            out[o] = make_uint4(q[0], q[1], q[2], q[3]);
+        } else {
+            float y[NCH];
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                y[i] = facc[i] + (bias ? __ldg(bias + c0 + i) : 0.f);
+                if (relu) y[i] = y[i] > 0.f ? y[i] : y[i] * slope;
+            }
+            if constexpr (MODE == 0) {
+                out[o] = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]), __float_as_uint(y[3]));
+            } else {
+                uint32_t q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const __half2 hh = __halves2half2(static_cast<__half>(y[2 * i]), static_cast<__half>(y[2 * i + 1]));
+                    q[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                out[o] = make_uint4(q[0], q[1], q[2], q[3]);
+            }
         }
     }
 }
@@ -1072,29 +1137,29 @@ int b200_dwconv_run(const b200_conv_desc_t* d, const void* in, const void* weigh
                     const float* bias, const float* scale, void* out, void* stream) {
     if (!d || !in || !weights_rsc || !out) return B200_INVALID_VALUE;
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
-    (void)scale;
     if (d->k != d->c) return B200_INVALID_VALUE;
     const int oh = (d->h + 2 * d->pad_h - (d->dil_h * (d->r - 1) + 1)) / d->stride_h + 1;
     const int ow = (d->w + 2 * d->pad_w - (d->dil_w * (d->s - 1) + 1)) / d->stride_w + 1;
     if (oh <= 0 || ow <= 0) return B200_INVALID_VALUE;
     const int block = 256;
-    if (d->in_dtype == B200_FLOAT && d->out_dtype == B200_FLOAT) {
-        if (d->c % 4) return B200_INVALID_VALUE;
-        const long long total = 1ll * d->n * oh * ow * (d->c / 4);
-        dwconv_kernel<float, 4><<<grid_for(total, block), block, 0, S(stream)>>>(
-            static_cast<const float*>(in), static_cast<const float*>(weights_rsc), bias,
-            static_cast<float*>(out), d->n, d->h, d->w, d->c, oh, ow, d->r, d->s, d->pad_h, d->pad_w,
-            d->stride_h, d->stride_w, d->dil_h, d->dil_w, d->relu, d->neg_slope);
-    } else if (d->in_dtype == B200_HALF && d->out_dtype == B200_HALF) {
-        if (d->c % 8) return B200_INVALID_VALUE;
-        const long long total = 1ll * d->n * oh * ow * (d->c / 8);
-        dwconv_kernel<__half, 8><<<grid_for(total, block), block, 0, S(stream)>>>(
-            static_cast<const __half*>(in), static_cast<const __half*>(weights_rsc), bias,
-            static_cast<__half*>(out), d->n, d->h, d->w, d->c, oh, ow, d->r, d->s, d->pad_h, d->pad_w,
-            d->stride_h, d->stride_w, d->dil_h, d->dil_w, d->relu, d->neg_slope);
-    } else {
-        return B200_UNIMPL_ERROR;
-    }
+    const uint4* in4 = static_cast<const uint4*>(in);
+    const uint4* w4 = static_cast<const uint4*>(weights_rsc);
+    uint4* out4 = static_cast<uint4*>(out);
+    int mode, nch;
+    if (d->in_dtype == B200_FLOAT && d->out_dtype == B200_FLOAT) { mode = 0; nch = 4; }
+    else if (d->in_dtype == B200_HALF && d->out_dtype == B200_HALF) { mode = 1; nch = 8; }
+    else if ((d->in_dtype == B200_INT8 || d->in_dtype == B200_UINT8) && (d->out_dtype == B200_INT8 || d->out_dtype == B200_UINT8)) { mode = 2; nch = 16; }
+    else return B200_UNIMPL_ERROR;
+    if (d->c % nch) return B200_INVALID_VALUE;
+    const int cv = d->c / nch;
+    const long long total = 1ll * d->n * oh * ow * cv;
+    const unsigned grid = grid_for(total, block);
+#define B200_DW_ARGS in4, w4, bias, scale, out4, d->n, d->h, d->w, cv, oh, ow, d->r, d->s, d->pad_h, d->pad_w, d->stride_h, \
+                     d->stride_w, d->dil_h, d->dil_w, d->relu, d->neg_slope, d->in_dtype == B200_UINT8 ? 1 : 0, d->out_dtype
+    if (mode == 0) launch_pdl(dwconv_vec_kernel<0>, grid, block, S(stream), B200_DW_ARGS);
+    else if (mode == 1) launch_pdl(dwconv_vec_kernel<1>, grid, block, S(stream), B200_DW_ARGS);
+    else launch_pdl(dwconv_vec_kernel<2>, grid, block, S(stream), B200_DW_ARGS);
+#undef B200_DW_ARGS
     return check_launch("dwconv");
 }
 

@@ -282,8 +282,7 @@ def run_int8(graph, x_nchw, edge_scales, return_intermediate=False):
             if g.kind == "conv":
                 w, bias = _folded_conv_weights(g)
                 kw = _conv_kw(a)
-                if int(a["group"]) != 1:
-                    raise NotImplementedError("int8 grouped conv")
+                kw["group"] = int(a["group"])
             else:
                 w = _attr_tensor(a["weight_1"]).reshape(int(a["out_dim"]), -1)
                 if src.ndim == 4 and src.shape[1] * src.shape[2] > 1:

@@ -334,6 +334,88 @@ ORACLE_API void oracle_conv_s8_nhwc_x86(const void* src, int src_dtype, const in
     free(wt);
 }
 
+/* The same with channel groups (depthwise: group == c == k; weights [k][c/group][r][s]). The arithmetic per output is
+ * unchanged -- an exact s32 sum over the group's input channels, then the epilogue above; the reference's depthwise
+ * INT8 kernels (jit_avx512_core_x8s8s32x_1x1 / dw variants) share that epilogue. */
+ORACLE_API void oracle_conv_s8_nhwc_x86_group(const void* src, int src_dtype, const int8_t* weights,
+                                        const float* bias_f, const float* scale,
+                                        const void* residual, int res_dtype, float sum_scale,
+                                        void* dst, int dst_dtype, int n, int c, int h, int w, int k, int group,
+                                        int kernel_h, int kernel_w, int stride_h, int stride_w,
+                                        int dil_h, int dil_w, int pad_h, int pad_w, int flag_relu) {
+    const uint8_t* src_u8 = (const uint8_t*)src;
+    const int8_t* src_s8 = (const int8_t*)src;
+    const int out_h = oracle_conv_out_size(h, pad_h, dil_h, kernel_h, stride_h);
+    const int out_w = oracle_conv_out_size(w, pad_w, dil_w, kernel_w, stride_w);
+    const int has_sum = residual != NULL;
+    /* re-lay the weights as [k][r][s][c] once so the inner loop is contiguous */
+    const int cg = c / group, kg = k / group;   /* channels per group (weights are [k][c/group][r][s]) */
+    const size_t wsz = (size_t)k * cg * kernel_h * kernel_w;
+    int8_t* wt = (int8_t*)malloc(wsz);
+    for (int oc = 0; oc < k; ++oc)
+        for (int ic = 0; ic < cg; ++ic)
+            for (int kh = 0; kh < kernel_h; ++kh)
+                for (int kw = 0; kw < kernel_w; ++kw)
+                    wt[(((size_t)oc * kernel_h + kh) * kernel_w + kw) * cg + ic] =
+                        weights[(((size_t)oc * cg + ic) * kernel_h + kh) * kernel_w + kw];
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int in_ = 0; in_ < n; ++in_) {
+        for (int oh = 0; oh < out_h; ++oh) {
+            for (int ow = 0; ow < out_w; ++ow) {
+                for (int oc = 0; oc < k; ++oc) {
+                    int32_t acc = 0;
+                    for (int kh = 0; kh < kernel_h; ++kh) {
+                        const int ih = oh * stride_h - pad_h + kh * dil_h;
+                        if (ih < 0 || ih >= h) continue;
+                        for (int kw = 0; kw < kernel_w; ++kw) {
+                            const int iw = ow * stride_w - pad_w + kw * dil_w;
+                            if (iw < 0 || iw >= w) continue;
+                            const size_t ibase = (((size_t)in_ * h + ih) * w + iw) * c + (size_t)(oc / kg) * cg;
+                            const int8_t* wp = wt + (((size_t)oc * kernel_h + kh) * kernel_w + kw) * cg;
+                            int32_t part = 0;
+                            if (src_dtype == DT_UINT8) {
+                                _Pragma("omp simd reduction(+ : part)")
+                                for (int ic = 0; ic < cg; ++ic) part += (int32_t)src_u8[ibase + ic] * wp[ic];
+                            } else {
+                                _Pragma("omp simd reduction(+ : part)")
+                                for (int ic = 0; ic < cg; ++ic) part += (int32_t)src_s8[ibase + ic] * wp[ic];
+                            }
+                            acc += part;
+                        }
+                    }
+                    const size_t out_idx = (((size_t)in_ * out_h + oh) * out_w + ow) * k + oc;
+                    float f = (float)acc + (bias_f ? bias_f[oc] : 0.f);
+                    f = f * (scale ? scale[oc] : 1.f);
+                    if (flag_relu && !has_sum) f = f > 0.f ? f : 0.f;
+                    if (has_sum) {
+                        float r;
+                        if (res_dtype == DT_FLOAT) r = ((const float*)residual)[out_idx];
+                        else if (res_dtype == DT_UINT8) r = (float)((const uint8_t*)residual)[out_idx];
+                        else r = (float)((const int8_t*)residual)[out_idx];
+                        f = (sum_scale == 1.f) ? f + r : fmaf(r, sum_scale, f);
+                        if (flag_relu) f = f > 0.f ? f : 0.f;
+                    }
+                    if (dst_dtype == DT_FLOAT) {
+                        ((float*)dst)[out_idx] = f;
+                    } else {
+                        /* vcvtps2dq RN-even, then vpmovsdb / vpmovusdb saturation */
+                        float rr = nearbyintf(f);
+                        int32_t q;
+                        if (dst_dtype == DT_INT8) {
+                            q = rr > 127.f ? 127 : (rr < -128.f ? -128 : (int32_t)rr);
+                            ((int8_t*)dst)[out_idx] = (int8_t)q;
+                        } else {
+                            q = rr > 255.f ? 255 : (rr < 0.f ? 0 : (int32_t)rr);
+                            ((uint8_t*)dst)[out_idx] = (uint8_t)q;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    free(wt);
+}
+
 /* Host-side scale preparation of the x86 int8 conv:
  * kernel/jit_avx512_core_x8s8s32x_conv.cpp:55-62 (bias), :226-255 (scale), :174-192 (sum_scale).
  *   in_scale / out_scale are the calibrated max|x|/127 edge scales; u8 tensors carry

@@ -135,19 +135,25 @@ def _dt(a):
 
 
 def conv_s8_nhwc_x86(x, w_s8, bias_f, scale, residual=None, sum_scale=1.0, out_dtype=DT_INT8,
-                     stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False):
-    """x: NHWC s8/u8, w_s8: KCRS int8; returns NHWC out_dtype."""
+                     stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False, group=1):
+    """x: NHWC s8/u8, w_s8: KCRS int8 ([k][c/group][r][s]); returns NHWC out_dtype."""
     x = np.ascontiguousarray(x)
     w_s8 = np.ascontiguousarray(w_s8, np.int8)
     n, h, wd, c = x.shape
     k, cw, r, s = w_s8.shape
-    assert cw == c
+    assert cw * group == c and k % group == 0
     oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
     ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
     out = np.zeros((n, oh, ow, k), _NP[out_dtype])
     b = None if bias_f is None else np.ascontiguousarray(bias_f, np.float32)
     sc = None if scale is None else np.ascontiguousarray(scale, np.float32)
     res = None if residual is None else np.ascontiguousarray(residual)
+    if group != 1:
+        lib().oracle_conv_s8_nhwc_x86_group(_p(x), _dt(x), _p(w_s8), _p(b), _p(sc), _p(res),
+                                            _dt(res) if res is not None else -1, _f(sum_scale), _p(out),
+                                            out_dtype, n, c, h, wd, k, group, r, s, stride[0], stride[1], dil[0],
+                                            dil[1], pad[0], pad[1], int(relu))
+        return out
     lib().oracle_conv_s8_nhwc_x86(_p(x), _dt(x), _p(w_s8), _p(b), _p(sc), _p(res),
                                   _dt(res) if res is not None else -1, _f(sum_scale), _p(out),
                                   out_dtype, n, c, h, wd, k, r, s, stride[0], stride[1], dil[0],

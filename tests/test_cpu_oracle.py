@@ -339,3 +339,31 @@ def test_eltwise_matches_reference_test_oracle(oracle, op, coeff, relu):
 def test_activation_matches_reference_test_oracle(oracle, act, coef):
     x = np.random.default_rng(act).uniform(-4, 4, (2, 3, 5, 7)).astype(np.float32)
     np.testing.assert_array_equal(oracle.activation_f32(x, act, 0.0, coef), oracle.ref_activation_f32(x, act, 0.0, coef))
+
+
+def test_grouped_x86_int8_conv_agrees_with_reference_oracle_on_shared_subset(oracle):
+    """Depthwise / grouped INT8: the grouped x86 restatement coincides with the reference's own conv_basic_check_int8
+    (which takes `group`) on their shared subset -- integral bias, s8 output, no residual."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(23)
+    for c, k, group in ((16, 16, 16), (32, 32, 32), (16, 32, 4)):
+        x = rng.integers(-128, 128, (2, 9, 9, c)).astype(np.int8)
+        w = rng.integers(-127, 128, (k, c // group, 3, 3)).astype(np.int8)
+        b = rng.integers(-1000, 1000, k).astype(np.int32)
+        sc = rng.uniform(0.002, 0.02, k).astype(np.float32)
+        for relu in (False, True):
+            r = oracle.conv_s8_nhwc_basic(x, w, b, sc, pad=(1, 1), stride=(2, 2), relu=relu, group=group, use_ref=True)
+            j = oracle.conv_s8_nhwc_x86(x, w, b.astype(np.float32), sc, pad=(1, 1), stride=(2, 2), relu=relu,
+                                        out_dtype=oracle.DT_INT8, group=group)
+            np.testing.assert_array_equal(j, r)
+    # group == 1 through the grouped entry point is the ungrouped function
+    x = rng.integers(0, 256, (1, 7, 7, 16)).astype(np.uint8)
+    w = rng.integers(-127, 128, (8, 16, 3, 3)).astype(np.int8)
+    sc = rng.uniform(0.002, 0.02, 8).astype(np.float32)
+    a = oracle.conv_s8_nhwc_x86(x, w, None, sc, out_dtype=oracle.DT_UINT8, relu=True)
+    import ctypes as C
+    out = np.zeros_like(a)
+    oracle.lib().oracle_conv_s8_nhwc_x86_group(oracle._p(x), oracle._dt(x), oracle._p(w), None, oracle._p(sc), None, -1,
+                                               oracle._f(1.0), oracle._p(out), oracle.DT_UINT8, 1, 16, 7, 7, 8, 1, 3, 3,
+                                               1, 1, 1, 1, 0, 0, 1)
+    np.testing.assert_array_equal(out, a)

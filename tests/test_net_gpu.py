@@ -390,9 +390,10 @@ def test_activation_sharing_and_weight_arena():
     shared.prediction(); shared.prediction(); shared.sync()
     np.testing.assert_array_equal(shared.get_output(), want)
     assert (want.argmax(1) == gold["top1_int8"][:batch]).all()
-    # footprint: >= 4x smaller than one buffer per edge
+    # footprint: >= 3.5x smaller than one buffer per edge (the largest edge of all -- conv1's 112 x 112 output -- no
+    # longer exists at all: the stem kernel pools it in shared memory; with it the ratio was > 4)
     assert shared.activation_bytes_unshared() == keep.activation_bytes()
-    assert shared.activation_bytes() * 4 <= shared.activation_bytes_unshared(), (
+    assert shared.activation_bytes() * 3.5 <= shared.activation_bytes_unshared(), (
         shared.activation_bytes(), shared.activation_bytes_unshared())
     # weights: the second Net built nothing new and points at the first Net's device images
     n_w = len(keep.weight_ptrs())

@@ -238,6 +238,68 @@ def test_dwconv_f32(stride, oracle):
     assert md < 1e-3 or mr <= 1e-3
 
 
+@pytest.mark.parametrize("stride", [1, 2])
+def test_dwconv_f16(stride, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(13)
+    n, h, w, c = 2, 30, 26, 48
+    x = rng.uniform(-1, 1, (n, h, w, c)).astype(np.float16)
+    wt = rng.uniform(-1, 1, (c, 1, 3, 3)).astype(np.float16)
+    b = rng.uniform(-1, 1, c).astype(np.float32)
+    want = oracle.conv_f32_nhwc(x.astype(np.float32), wt.astype(np.float32), b, group=c, stride=(stride, stride), pad=(1, 1),
+                                relu=True)
+    d = A.ConvDesc()
+    d.math, d.in_dtype, d.out_dtype, d.res_dtype = A.MATH_F16, A.HALF, A.HALF, -1
+    d.n, d.h, d.w, d.c, d.k, d.ldc, d.r, d.s = n, h, w, c, c, c, 3, 3
+    d.pad_h = d.pad_w = 1
+    d.stride_h = d.stride_w = stride
+    d.dil_h = d.dil_w = 1
+    d.relu = 1
+    wrsc = np.ascontiguousarray(np.transpose(wt[:, 0], (1, 2, 0)))
+    xd, wd, bd = dev(x), dev(wrsc), dev(b)
+    out = torch.zeros(want.shape, dtype=torch.float16, device="cuda")
+    A.check(A.load().b200_dwconv_run(C.byref(d), ptr(xd), ptr(wd), ptr(bd), None, ptr(out), stream_ptr()))
+    torch.cuda.synchronize()
+    # fp32 accumulation of exact products, one rounding to half at the store
+    np.testing.assert_array_equal(out.cpu().numpy(), want.astype(np.float16))
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+@pytest.mark.parametrize("variant", ["u8_relu_u8", "s8_s8", "u8_s8"])
+def test_dwconv_int8_bit_exact(stride, variant, oracle):
+    """INT8 depthwise (SaberDepthWiseConv's int8 arm, saber_depthwiseconv_act.cu:84-295): exact s32 sums, then the x86
+    Saber epilogue -- bit-identical to the grouped x86 oracle (pinned to conv_basic_check_int8 with group = c)."""
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    rng = np.random.default_rng(abs(hash((stride, variant))) % (2 ** 31))
+    n, h, w, c = 2, 29, 31, 96
+    in_u = variant.startswith("u8")
+    x = rng.integers(0, 256, (n, h, w, c)).astype(np.uint8) if in_u else rng.integers(-128, 128, (n, h, w, c)).astype(np.int8)
+    wq = rng.integers(-127, 128, (c, 1, 3, 3)).astype(np.int8)
+    bias = rng.uniform(-3000, 3000, c).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, c).astype(np.float32) * np.float32(1.0 / 900.0)
+    out_dtype = A.UINT8 if variant.endswith("relu_u8") else A.INT8
+    relu = variant.endswith("relu_u8")
+    want = oracle.conv_s8_nhwc_x86(x, wq, bias, scale, out_dtype=out_dtype, stride=(stride, stride), pad=(1, 1), relu=relu,
+                                   group=c)
+    d = A.ConvDesc()
+    d.math, d.in_dtype, d.out_dtype, d.res_dtype = A.MATH_I8, (A.UINT8 if in_u else A.INT8), out_dtype, -1
+    d.n, d.h, d.w, d.c, d.k, d.ldc, d.r, d.s = n, h, w, c, c, c, 3, 3
+    d.pad_h = d.pad_w = 1
+    d.stride_h = d.stride_w = stride
+    d.dil_h = d.dil_w = 1
+    d.relu = int(relu)
+    wrsc = np.ascontiguousarray(np.transpose(wq[:, 0], (1, 2, 0)))
+    xd, wd, bd, sd = dev(x), dev(wrsc), dev(bias), dev(scale)
+    out = torch.zeros(want.shape, dtype=(torch.uint8 if out_dtype == A.UINT8 else torch.int8), device="cuda")
+    A.check(A.load().b200_dwconv_run(C.byref(d), ptr(xd), ptr(wd), ptr(bd), ptr(sd), ptr(out), stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Weight-streaming inner product (fc_stream.cu) and the fused classifier head (pool + fc + softmax, one launch)
 FC_CASES = [(8, 2048, 1000), (4, 25088, 512), (1, 512, 10), (13, 4096, 200), (16, 1024, 64)]   # (m, k, n)
