@@ -66,7 +66,10 @@ struct StemParams {
     int32_t off_planes, off_stage, off_tail;
     int32_t tiles_img, tiles_total;      // tiles per image, tiles in all (walked by gridDim.x persistent CTAs)
     int32_t cpp, store_tw, store_items;  // store phase: 16-byte chunks per pixel, tile width, items per tile
-    FastDiv div_bn, div_tiles_img, div_tiles_w, div_qcols, div_sh, div_sw, div_cpp, div_tw;
+    int32_t pairs_row;                   // stride_w == 2: pixel pairs per patch row
+    int32_t pool_on_acc;                 // pool the raw accumulators, epilogue on the pooled pixels only (monotone epilogue)
+    int32_t groups, pool_items, off_pool_stage;   // 16-channel groups per tile, (pooled pixel, group) items, their staging rows
+    FastDiv div_bn, div_tiles_img, div_tiles_w, div_qcols, div_sh, div_sw, div_cpp, div_tw, div_pairs, div_groups;
     float inv_scale;
     ConvKParams kp;       // epilogue parameters (relu, dtypes, tables)
 };
@@ -81,6 +84,45 @@ struct StemElem {
 };
 
 __device__ __forceinline__ uint32_t swz16(int row, int lg) { return (row >> (7 - lg)) & ((1 << (lg - 4)) - 1); }
+
+// One 4-channel pixel in operand precision: `hi` holds PXB bytes (1 | 2 | 4 words), `lo` the low plane of the 3xTF32 split.
+template <int MK, bool X3>
+__device__ __forceinline__ void stem_convert(float v0, float v1, float v2, float v3, float inv_scale, uint32_t (&hi)[4],
+                                             uint32_t (&lo)[4]) {
+    if constexpr (MK == KIND_I8) {
+        const float v[4] = {v0, v1, v2, v3};
+        uint32_t wd = 0;
+#pragma unroll
+        for (int cch = 0; cch < 4; ++cch) {
+            // secur_cast2char(x * inv): roundf + clamp (reference x86_utils.h:318-347)
+            float f = roundf(__fmul_rn(v[cch], inv_scale));
+            f = fminf(fmaxf(f, -128.f), 127.f);
+            wd |= (static_cast<uint32_t>(static_cast<int>(f)) & 0xffu) << (8 * cch);
+        }
+        hi[0] = wd;
+    } else if constexpr (MK == KIND_F16) {
+        __half2 a = __floats2half2_rn(v0, v1), b = __floats2half2_rn(v2, v3);
+        hi[0] = *reinterpret_cast<uint32_t*>(&a); hi[1] = *reinterpret_cast<uint32_t*>(&b);
+    } else {
+        const uint32_t w[4] = {__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (X3) {   // x = hi + lo, hi = top 19 bits (exact split)
+                hi[i] = w[i] & 0xFFFFE000u;
+                lo[i] = __float_as_uint(__fsub_rn(__uint_as_float(w[i]), __uint_as_float(hi[i])));
+            } else {
+                hi[i] = w[i];
+            }
+        }
+    }
+}
+
+// max over raw accumulators: s32 for the int8 kind, fp32 bit patterns otherwise (r >= x ? r : x)
+template <int MK>
+__device__ __forceinline__ uint32_t acc_max(uint32_t a, uint32_t b) {
+    if constexpr (MK == KIND_I8) return static_cast<uint32_t>(max(static_cast<int32_t>(a), static_cast<int32_t>(b)));
+    else return __uint_as_float(a) >= __uint_as_float(b) ? a : b;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(STEM_THREADS)
@@ -159,74 +201,105 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
 
         // ---- 1. input patch -> operand planes. Pixel (qr, qc) of the patch is input (h0 + qr, w0 + qc); quantised /
         // converted once, it is stored at every (output column j, tap t) with j * stride_w + t == qc of row
-        // k = qr / stride_h of plane qr % stride_h -- a 4 / 8 / 16-byte store into the swizzled K-major row (k, j).
+        // k = qr / stride_h of plane qr % stride_h of the swizzled K-major operand.
         {
             const int h0 = i0 * p.stride_h - p.pad_h, w0 = j0 * p.stride_w - p.pad_w;
             const float* img = p.in + static_cast<size_t>(n_img) * p.c * plane;
-            constexpr int STEM_PXB = 5;     // pixels in flight per thread: all their loads are issued before the first use
-            for (int base = tid; base < npx; base += STEM_PXB * STEM_THREADS) {
-                float vv[STEM_PXB][3];
-                float v3[STEM_PXB];
+            if (p.stride_w == 2) {
+                // stride 2: the pixel PAIR (qc, qc + 1), qc even, is taps (2u, 2u + 1) of output column qc/2 - u: one
+                // 8 / 16 / 32-byte store per column instead of two half-sized ones
+                constexpr int NB = 3;    // pairs in flight per thread: all their loads are issued before the first use
+                const int npair = p.qrows * p.pairs_row;
+                for (int base = tid; base < npair; base += NB * STEM_THREADS) {
+                    float va[NB][4], vb[NB][4];
 #pragma unroll
-                for (int u = 0; u < STEM_PXB; ++u) {
-                    const int i = base + u * STEM_THREADS;
-                    const uint32_t qr = p.div_qcols.quot(i), qc = i - qr * p.qcols;
-                    const int y = h0 + static_cast<int>(qr), x = w0 + static_cast<int>(qc);
-                    const bool ok = i < npx && y >= 0 && y < p.h && x >= 0 && x < p.w_in;
-                    const float* px = img + static_cast<size_t>(ok ? y : 0) * p.w_in + (ok ? x : 0);
-#pragma unroll
-                    for (int cch = 0; cch < 3; ++cch) vv[u][cch] = (ok && cch < p.c) ? __ldg(px + cch * plane) : 0.f;
-                    v3[u] = (ok && p.c > 3) ? __ldg(px + 3 * plane) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < STEM_PXB; ++u) {
-                    const int i = base + u * STEM_THREADS;
-                    if (i >= npx) break;
-                    const uint32_t qr = p.div_qcols.quot(i), qc = i - qr * p.qcols;
-                    const uint32_t k = p.div_sh.quot(qr), par = qr - k * p.stride_h;
-                    uint32_t t = 0, j = qc;                     // stride_w == 1: every tap of column j = qc - t
-                    if (p.stride_w > 1) { j = p.div_sw.quot(qc); t = qc - j * p.stride_w; }
-                    // the pixel in operand precision
-                    uint32_t w0q = 0, w1q = 0, w2q = 0, w3q = 0;      // hi (or the only) plane: 4 | 8 | 16 bytes
-                    uint32_t l0q = 0, l1q = 0, l2q = 0, l3q = 0;      // X3: the low plane
-                    if constexpr (MK == KIND_I8) {
+                    for (int u = 0; u < NB; ++u) {
+                        const int i = base + u * STEM_THREADS;
+                        const uint32_t qr = p.div_pairs.quot(i), pi = i - qr * p.pairs_row;
+                        const int y = h0 + static_cast<int>(qr), x = w0 + 2 * static_cast<int>(pi);
+                        const bool oky = i < npair && y >= 0 && y < p.h;
+                        const bool ok0 = oky && x >= 0 && x < p.w_in, ok1 = oky && x + 1 >= 0 && x + 1 < p.w_in;
+                        const float* px = img + static_cast<size_t>(oky ? y : 0) * p.w_in + x;
 #pragma unroll
                         for (int cch = 0; cch < 4; ++cch) {
-                            // secur_cast2char(x * inv): roundf + clamp (reference x86_utils.h:318-347)
-                            float f = roundf(__fmul_rn(cch < 3 ? vv[u][cch] : v3[u], p.inv_scale));
-                            f = fminf(fmaxf(f, -128.f), 127.f);
-                            w0q |= (static_cast<uint32_t>(static_cast<int>(f)) & 0xffu) << (8 * cch);
-                        }
-                    } else if constexpr (MK == KIND_F16) {
-                        __half2 a = __floats2half2_rn(vv[u][0], vv[u][1]), b = __floats2half2_rn(vv[u][2], v3[u]);
-                        w0q = *reinterpret_cast<uint32_t*>(&a); w1q = *reinterpret_cast<uint32_t*>(&b);
-                    } else {
-                        w0q = __float_as_uint(vv[u][0]); w1q = __float_as_uint(vv[u][1]);
-                        w2q = __float_as_uint(vv[u][2]); w3q = __float_as_uint(v3[u]);
-                        if constexpr (X3) {   // x = hi + lo, hi = top 19 bits (exact split)
-                            const uint32_t h0q = w0q & 0xFFFFE000u, h1q = w1q & 0xFFFFE000u, h2q = w2q & 0xFFFFE000u, h3q = w3q & 0xFFFFE000u;
-                            l0q = __float_as_uint(__fsub_rn(__uint_as_float(w0q), __uint_as_float(h0q)));
-                            l1q = __float_as_uint(__fsub_rn(__uint_as_float(w1q), __uint_as_float(h1q)));
-                            l2q = __float_as_uint(__fsub_rn(__uint_as_float(w2q), __uint_as_float(h2q)));
-                            l3q = __float_as_uint(__fsub_rn(__uint_as_float(w3q), __uint_as_float(h3q)));
-                            w0q = h0q; w1q = h1q; w2q = h2q; w3q = h3q;
+                            va[u][cch] = (ok0 && cch < p.c) ? __ldg(px + cch * plane) : 0.f;
+                            vb[u][cch] = (ok1 && cch < p.c) ? __ldg(px + cch * plane + 1) : 0.f;
                         }
                     }
-                    const uint32_t plane_sa = planes_sa + par * PL * p.plane_bytes;
-                    int jj = static_cast<int>(j);
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        const int i = base + u * STEM_THREADS;
+                        if (i >= npair) break;
+                        const uint32_t qr = p.div_pairs.quot(i), pi = i - qr * p.pairs_row;
+                        const uint32_t k = p.div_sh.quot(qr), par = qr - k * p.stride_h;
+                        uint32_t ha[4], la[4], hb[4], lb[4];
+                        stem_convert<MK, X3>(va[u][0], va[u][1], va[u][2], va[u][3], p.inv_scale, ha, la);
+                        stem_convert<MK, X3>(vb[u][0], vb[u][1], vb[u][2], vb[u][3], p.inv_scale, hb, lb);
+                        const uint32_t plane_sa = planes_sa + par * PL * p.plane_bytes;
+#pragma unroll
+                        for (int q = 0; q < STEM_TAPS / 2; ++q) {
+                            const int jj = static_cast<int>(pi) - q;
+                            if (jj < 0 || jj >= p.cw) continue;
+                            const uint32_t row = k * p.cw + jj;
+                            const uint32_t boff = 2 * q * E::PXB;      // taps (2q, 2q + 1)
+                            const uint32_t a = plane_sa + row * E::ROWB + ((((boff >> 4) ^ swz16(row, E::LG))) << 4) + (boff & 15u);
+                            if constexpr (MK == KIND_I8) {
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(ha[0]), "r"(hb[0]) : "memory");
+                            } else if constexpr (MK == KIND_F16) {
+                                sts128(a, make_uint4(ha[0], ha[1], hb[0], hb[1]));
+                            } else {
+                                // two 16-byte chunks: a pixel each (the pair straddles chunks boff/16 and boff/16 + 1)
+                                const uint32_t a2 = plane_sa + row * E::ROWB + (((((boff >> 4) + 1) ^ swz16(row, E::LG))) << 4);
+                                sts128(a, make_uint4(ha[0], ha[1], ha[2], ha[3]));
+                                sts128(a2, make_uint4(hb[0], hb[1], hb[2], hb[3]));
+                                if constexpr (X3) {
+                                    sts128(a + p.plane_bytes, make_uint4(la[0], la[1], la[2], la[3]));
+                                    sts128(a2 + p.plane_bytes, make_uint4(lb[0], lb[1], lb[2], lb[3]));
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                constexpr int NB = 4;
+                for (int base = tid; base < npx; base += NB * STEM_THREADS) {
+                    float vv[NB][4];
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        const int i = base + u * STEM_THREADS;
+                        const uint32_t qr = p.div_qcols.quot(i), qc = i - qr * p.qcols;
+                        const int y = h0 + static_cast<int>(qr), x = w0 + static_cast<int>(qc);
+                        const bool ok = i < npx && y >= 0 && y < p.h && x >= 0 && x < p.w_in;
+                        const float* px = img + static_cast<size_t>(ok ? y : 0) * p.w_in + (ok ? x : 0);
+#pragma unroll
+                        for (int cch = 0; cch < 4; ++cch) vv[u][cch] = (ok && cch < p.c) ? __ldg(px + cch * plane) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        const int i = base + u * STEM_THREADS;
+                        if (i >= npx) break;
+                        const uint32_t qr = p.div_qcols.quot(i), qc = i - qr * p.qcols;
+                        const uint32_t k = p.div_sh.quot(qr), par = qr - k * p.stride_h;
+                        const uint32_t j = p.div_sw.quot(qc);
+                        uint32_t t = qc - j * p.stride_w;
+                        uint32_t hw[4], lw[4];
+                        stem_convert<MK, X3>(vv[u][0], vv[u][1], vv[u][2], vv[u][3], p.inv_scale, hw, lw);
+                        const uint32_t plane_sa = planes_sa + par * PL * p.plane_bytes;
+                        int jj = static_cast<int>(j);
 #pragma unroll 1
-                    for (; t < STEM_TAPS && jj >= 0; t += p.stride_w, --jj) {
-                        if (jj >= p.cw) continue;
-                        const uint32_t row = k * p.cw + jj;
-                        const uint32_t boff = t * E::PXB;
-                        const uint32_t a = plane_sa + row * E::ROWB + ((((boff >> 4) ^ swz16(row, E::LG))) << 4) + (boff & 15u);
-                        if constexpr (MK == KIND_I8) {
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(w0q) : "memory");
-                        } else if constexpr (MK == KIND_F16) {
-                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(w0q), "r"(w1q) : "memory");
-                        } else {
-                            sts128(a, make_uint4(w0q, w1q, w2q, w3q));
-                            if constexpr (X3) sts128(a + p.plane_bytes, make_uint4(l0q, l1q, l2q, l3q));
+                        for (; t < STEM_TAPS && jj >= 0; t += p.stride_w, --jj) {
+                            if (jj >= p.cw) continue;
+                            const uint32_t row = k * p.cw + jj;
+                            const uint32_t boff = t * E::PXB;
+                            const uint32_t a = plane_sa + row * E::ROWB + ((((boff >> 4) ^ swz16(row, E::LG))) << 4) + (boff & 15u);
+                            if constexpr (MK == KIND_I8) {
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(hw[0]) : "memory");
+                            } else if constexpr (MK == KIND_F16) {
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(hw[0]), "r"(hw[1]) : "memory");
+                            } else {
+                                sts128(a, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+                                if constexpr (X3) sts128(a + p.plane_bytes, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+                            }
                         }
                     }
                 }
@@ -270,13 +343,81 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
             __syncwarp();
         }
 
+        const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
+        const int oi0 = p.pool ? static_cast<int>(ti) * p.ph : i0, oj0 = p.pool ? static_cast<int>(tj) * p.pw : j0;
+        const int es = p.kp.out_es;
+        uint8_t* out = static_cast<uint8_t*>(p.out);
+        if (p.pool_on_acc) {
+            // ---- 3a. MAX pooling on the RAW accumulators: the epilogue (acc + bias) * scale [relu] -> rne + saturate is
+            // monotone non-decreasing in acc for a positive scale (float kinds: + bias, relu with a non-negative slope),
+            // so max commutes with it EXACTLY and only the pooled pixels -- a fifth of the tile for 3x3/s2 -- pay for it.
+            // Accumulators go TMEM -> registers -> a 16-byte-chunk-swizzled [128][bn] s32 tile in shared memory.
+            const uint32_t raw_sa = stage_sa;
+            const uint32_t nchunk = static_cast<uint32_t>(p.bn) >> 2;          // 16-byte chunks per row (4 | 8 | 16)
+            if (warp_idx < 4) {
+                mbar_wait(mma_bar, mma_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
+                const uint32_t row_sa = raw_sa + static_cast<uint32_t>(tid) * p.bn * 4;
+                const uint32_t sw = static_cast<uint32_t>(tid) & (nchunk - 1);
+#pragma unroll 1
+                for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                    if (n0 + c0 >= p.k) break;
+                    uint32_t v0[16];
+                    tmem_ld_32x32b_x16(t_row + c0, v0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        sts128(row_sa + ((((c0 >> 2) + q) ^ sw) << 4), make_uint4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
+                }
+                tc_fence_before();
+            }
+            mma_phase ^= 1;
+            __syncthreads();
+            // ---- 4a. item = (pooled pixel, 16 channels): window max, epilogue, 16 * out_es bytes to HBM
+            const uint32_t pst_sa = smem_u32(smem + p.off_pool_stage);
+            for (int it = tid; it < p.pool_items; it += STEM_THREADS) {
+                const uint32_t e = p.div_groups.quot(it), g = it - e * p.groups;
+                const uint32_t oi = p.div_tw.quot(e), oj = e - oi * p.store_tw;
+                const int gi = oi0 + static_cast<int>(oi), gj = oj0 + static_cast<int>(oj);
+                if (gi >= p.OH || gj >= p.OW || n0 + static_cast<int>(g) * 16 >= p.k) continue;
+                const int hs = max(gi * p.ps_h - p.pp_h, 0), he = min(gi * p.ps_h - p.pp_h + p.pk_h, p.Ho);
+                const int ws = max(gj * p.ps_w - p.pp_w, 0), we = min(gj * p.ps_w - p.pp_w + p.pk_w, p.Wo);
+                uint32_t v[16];
+                bool first = true;
+                for (int y = hs; y < he; ++y) {
+                    uint32_t m = (y - i0) * p.cw + (ws - j0);
+                    for (int x = ws; x < we; ++x, ++m) {
+                        const uint32_t rsa = raw_sa + m * p.bn * 4, sw = m & (nchunk - 1);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 t4 = lds128(rsa + (((g * 4 + q) ^ sw) << 4));
+                            if (first) { v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w; }
+                            else {
+                                v[4 * q] = acc_max<MK>(v[4 * q], t4.x); v[4 * q + 1] = acc_max<MK>(v[4 * q + 1], t4.y);
+                                v[4 * q + 2] = acc_max<MK>(v[4 * q + 2], t4.z); v[4 * q + 3] = acc_max<MK>(v[4 * q + 3], t4.w);
+                            }
+                        }
+                        first = false;
+                    }
+                }
+                if (first) continue;                                   // (an empty window cannot happen: defensive)
+                // the conv kernels' epilogue on the pooled accumulators, staged in this item's own row, then stored
+                const PanelRow prow = make_panel_row(pst_sa, lg_out, e);
+                epilogue16<MK>(p.kp, v, g * 16, bias_sa, scale_sa, prow, prow);
+                const size_t o = ((static_cast<size_t>(n_img) * p.OH + gi) * p.OW + gj) * p.ldc * es + static_cast<size_t>(n0 + g * 16) * es;
+                for (int q = 0; q < es; ++q) {
+                    if ((n0 + static_cast<int>(g) * 16) * es + q * 16 + 16 > p.k * es) break;      // (ragged last group)
+                    *reinterpret_cast<uint4*>(out + o + q * 16) = lds128(panel_addr(prow, g * 16 * es + q * 16));
+                }
+            }
+        } else {
         // ---- 3. fused epilogue into the staging tile (GEMM row m = i*cw + j <-> one thread)
         if (warp_idx < 4) {
             mbar_wait(mma_bar, mma_phase);
             tc_fence_after();
             const PanelRow out_row = make_panel_row(stage_sa, lg_out, tid);
             const PanelRow res_row = out_row;   // no residual
-            const uint32_t bias_sa = smem_u32(bias_s), scale_sa = smem_u32(scale_s);
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
 #pragma unroll 1
             for (int c0 = 0; c0 < p.bn; c0 += 16) {
@@ -293,10 +434,7 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
 
         // ---- 4. (max pool +) store: 16 bytes per thread and item, NHWC
         {
-            const int es = p.kp.out_es;
             const int out_dt = p.kp.out_dtype;
-            uint8_t* out = static_cast<uint8_t*>(p.out);
-            const int oi0 = p.pool ? static_cast<int>(ti) * p.ph : i0, oj0 = p.pool ? static_cast<int>(tj) * p.pw : j0;
             for (int it = tid; it < p.store_items; it += STEM_THREADS) {
                 const uint32_t e = p.div_cpp.quot(it), c16 = it - e * p.cpp;
                 const uint32_t oi = p.div_tw.quot(e), oj = e - oi * p.store_tw;
@@ -343,6 +481,7 @@ conv_stem_kernel(const StemParams p, const uint32_t idesc) {
                 const size_t o = ((static_cast<size_t>(n_img) * p.OH + gi) * p.OW + gj) * p.ldc * es + static_cast<size_t>(n0) * es + byte;
                 *reinterpret_cast<uint4*>(out + o) = acc;
             }
+        }
         }
         // the next tile rewrites the planes and the staging tile, and its MMAs the accumulator
         tc_fence_before();
@@ -459,7 +598,20 @@ int stem_plan(const b200_stem_desc_t* d, StemPlan* P) {
         p.wt_stride = (bn * rowb + 1023) & ~1023;
         p.off_planes = planes_n * p.R * p.wt_stride;
         p.off_stage = p.off_planes + p.stride_h * planes_n * p.plane_bytes;      // (1024-aligned: every part is)
-        p.off_tail = p.off_stage + BLOCK_M * bn * out_es;
+        // pooling on the raw accumulators needs the [128][bn] s32 tile and one staged row per pooled pixel
+        p.pool_on_acc = (p.pool && d->monotone_epilogue) ? 1 : 0;
+        if (p.pool_on_acc) {
+            // the raw tile reuses the planes (dead once the MMAs have retired; the next tile rewrites them after the
+            // barrier that ends this one); a single-panel pooled staging tile only needs the pooled pixels' rows
+            const int planes_bytes = p.stride_h * planes_n * p.plane_bytes, raw_bytes = BLOCK_M * bn * 4;
+            p.off_stage = p.off_planes;
+            p.off_pool_stage = p.off_planes + (planes_bytes > raw_bytes ? planes_bytes : raw_bytes);
+            const int pooled_rows = bn * out_es <= 128 ? ((p.ph * p.pw + 7) & ~7) : BLOCK_M;
+            p.off_tail = (p.off_pool_stage + pooled_rows * bn * out_es + 1023) & ~1023;
+        } else {
+            p.off_pool_stage = p.off_stage + BLOCK_M * bn * out_es;
+            p.off_tail = p.off_pool_stage;
+        }
         P->smem_bytes = p.off_tail + 2 * 64 * 4 + 16 + 1024;
         if (P->smem_bytes <= MAX_SMEM) break;
         if (bn == 16) return B200_OUT_OF_MEM;
@@ -471,6 +623,11 @@ int stem_plan(const b200_stem_desc_t* d, StemPlan* P) {
     p.store_items = (p.pool ? p.ph * p.pw : p.ch * p.cw) * p.cpp;
     p.div_bn.set(p.bn); p.div_tiles_img.set(p.tiles_img); p.div_tiles_w.set(p.tiles_w); p.div_qcols.set(p.qcols);
     p.div_sh.set(p.stride_h); p.div_sw.set(p.stride_w); p.div_cpp.set(p.cpp); p.div_tw.set(p.store_tw);
+    p.pairs_row = p.qcols / 2;        // (qcols is even whenever stride_w is)
+    p.div_pairs.set(p.pairs_row);
+    p.groups = p.bn / 16;
+    p.pool_items = p.pool ? p.ph * p.pw * p.groups : 0;
+    p.div_groups.set(p.groups);
     ConvKParams& kp = p.kp;
     kp.K = d->k;
     kp.relu = d->relu; kp.neg_slope = d->neg_slope; kp.sum_scale = 1.f;

@@ -24,6 +24,7 @@
 #include "../../include/b200_saber.h"
 #include "common.cuh"
 #include "softmax.cuh"
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -245,13 +246,13 @@ __global__ void __launch_bounds__(FC_THREADS) fc_stream_kernel(const FcParams p)
 }
 
 // ------------------------------------------------------------------------------------------------ fused head
-// INT8 classifier head in one launch WITHOUT grid barriers: the reduction dimension is split over the CTAs. CTA j owns
-// a slice of the channels: it pools exactly those channels of every image (no redundancy), multiplies them with its
-// slice of every weight row, and adds the integer partial sums into an s32 accumulator [m][n] with fire-and-forget
-// reductions -- integer addition is exact and order-free, so the result is deterministic and bit-identical to the
-// separate ops. Each CTA then takes a ticket; the last one to finish applies the x86 Saber epilogue
-// ((acc + bias) * scale), writes the fp32 logits, runs the softmax and leaves accumulator and ticket counter zeroed
-// for the next launch. No CTA ever waits for another one, so nothing depends on co-residency.
+// INT8 classifier head: global pooling + inner product in ONE launch, softmax in a second one (instead of three
+// dependent launches of 4-8 us each). One CLUSTER of m CTAs per slice of the output neurons: CTA r of a cluster pools
+// image r (hw x c bytes, exact packed 16-bit integer sums or byte maxima) into its own shared memory; after one cluster
+// barrier every CTA gathers the m pooled rows through distributed shared memory and computes its own neurons for all m
+// images -- a warp per neuron, 16 weight bytes per lane and step, dp4a, xor-shuffle fold, then the x86 Saber epilogue
+// (acc + bias) * scale. Pooling is repeated by every cluster (m x hw x c bytes from L2 each, ~0.8 MB for ResNet-50):
+// cheaper than a grid-wide dependency. Same arithmetic as b200_pool_run -> b200_fc_stream_run, bit for bit.
 struct HeadParams {
     const uint8_t* in;    // NHWC [m][hw][c]  u8 | s8
     uint8_t* pooled;      // [m][c]           same dtype (the pooling op's output tensor)
@@ -259,121 +260,138 @@ struct HeadParams {
     const float* bias;
     const float* scale;
     float* logits;        // [m][ldo]
-    float* prob;          // [m][ldp] or null
-    int32_t* acc;         // [m][n] s32, zero between launches
-    unsigned* ticket;     // zero between launches
-    int m, hw, c, n, ldo, ldp;
+    int m, hw, c, n, ldo;
     int in_unsigned, pool_max;
-    int vec_per_cta;      // 16-byte channel vectors per CTA
+    int n_cluster, n_cta; // neurons per cluster / per CTA
 };
 
 constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_MAX_M = 8;
-constexpr int HEAD_MAX_VEC = 4;       // 16-byte vectors per CTA slice (<= 64 channels)
-constexpr int HEAD_PARTS = 8;         // pixel groups per (image, vector) task
+constexpr int HEAD_MAX_C = 4096;
 
-__global__ void __launch_bounds__(HEAD_THREADS) head_i8_kernel(const HeadParams h) {
-    __shared__ int32_t part[HEAD_MAX_M * HEAD_MAX_VEC * HEAD_PARTS][16];
-    __shared__ __align__(16) uint8_t xs[HEAD_MAX_M][HEAD_MAX_VEC * 16];
-    __shared__ unsigned is_last;
+__global__ void __launch_bounds__(HEAD_THREADS) head_pool_fc_kernel(const HeadParams h) {
+    extern __shared__ __align__(16) uint8_t head_smem[];
+    uint8_t* xs = head_smem;                                      // [c] this CTA's pooled row
+    uint8_t* xall = head_smem + h.c;                              // [m][c]
+    uint32_t* part = reinterpret_cast<uint32_t*>(xall + static_cast<size_t>(h.m) * h.c);   // [pg][cv][8]
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int cv = h.c >> 4;                                   // vectors per pixel
-    const int v0 = blockIdx.x * h.vec_per_cta;
-    const int nvec = min(h.vec_per_cta, cv - v0);
-    const int tid = threadIdx.x;
-    // ---- 1. pool this CTA's channels: task = (image, vector, pixel group), exact integer sums / maxima
-    const int tasks = h.m * nvec * HEAD_PARTS;
-    if (tid < tasks) {
-        const int pg = tid % HEAD_PARTS, t2 = tid / HEAD_PARTS;
-        const int v = t2 % nvec, mi = t2 / nvec;
-        const uint4* src = reinterpret_cast<const uint4*>(h.in) + static_cast<size_t>(mi) * h.hw * cv + v0 + v;
-        int32_t r[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int cid = blockIdx.x / h.m;
+    const int cv = h.c >> 4;                                      // 16-byte vectors per pixel
+    const uint32_t flip = h.in_unsigned ? 0u : 0x80808080u;       // s8 -> biased u8
+    // ---- 1. pool image `rank`: thread (pg, v) folds pixels pg, pg + PG, ... of channel vector v
+    const int PG = HEAD_THREADS / cv > 0 ? HEAD_THREADS / cv : 1;
+    for (int v = tid % cv, pg = tid / cv; pg < PG && v < cv; v += HEAD_THREADS) {   // (cv <= 256: one trip)
+        const uint4* src = reinterpret_cast<const uint4*>(h.in) + static_cast<size_t>(rank) * h.hw * cv + v;
+        uint32_t a[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = h.pool_max ? INT32_MIN : 0;
-        for (int t = pg; t < h.hw; t += HEAD_PARTS) {
+        for (int j = 0; j < 8; ++j) a[j] = 0u;
+        for (int t = pg; t < h.hw; t += PG) {
             const uint4 y = __ldg(src + static_cast<size_t>(t) * cv);
-            const uint32_t w4[4] = {y.x, y.y, y.z, y.w};
+            const uint32_t w4[4] = {y.x ^ flip, y.y ^ flip, y.z ^ flip, y.w ^ flip};
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t b = (w4[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                const int32_t val = h.in_unsigned ? static_cast<int32_t>(b) : static_cast<int32_t>(static_cast<int8_t>(b));
-                r[j] = h.pool_max ? max(r[j], val) : r[j] + val;
+            for (int j = 0; j < 4; ++j) {
+                if (h.pool_max) {
+                    a[j] = __vmaxu4(a[j], w4[j]);
+                } else {      // bytes 0, 2 and bytes 1, 3 as two pairs of 16-bit lanes (255 * hw < 65536)
+                    a[2 * j] += w4[j] & 0x00FF00FFu;
+                    a[2 * j + 1] += (w4[j] >> 8) & 0x00FF00FFu;
+                }
             }
         }
+        uint32_t* dst = part + (static_cast<size_t>(pg) * cv + v) * 8;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) part[tid][j] = r[j];
+        for (int j = 0; j < 8; ++j) dst[j] = a[j];
     }
     __syncthreads();
-    for (int e = tid; e < h.m * nvec * 16; e += HEAD_THREADS) {
-        const int j = e & 15, t2 = e >> 4;                     // t2 = mi * nvec + v
-        int32_t sum = h.pool_max ? INT32_MIN : 0;
-        for (int pg = 0; pg < HEAD_PARTS; ++pg) {
-            const int32_t x = part[t2 * HEAD_PARTS + pg][j];
-            sum = h.pool_max ? max(sum, x) : sum + x;
+    for (int v = tid; v < cv; v += HEAD_THREADS) {
+        uint32_t a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0u;
+        for (int pg = 0; pg < PG; ++pg) {
+            const uint32_t* src = part + (static_cast<size_t>(pg) * cv + v) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (h.pool_max) { if (j < 4) a[j] = __vmaxu4(a[j], src[j]); }
+                else a[j] += src[j];
+            }
         }
-        // saber_pooling int8: fp32 sum (exact here) / window, rounded to nearest even, saturated
-        const float q = h.pool_max ? static_cast<float>(sum) : __fdiv_rn(static_cast<float>(sum), static_cast<float>(h.hw));
-        uint32_t code;
-        if (h.in_unsigned) asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(code) : "f"(q));
-        else { int32_t sc; asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(sc) : "f"(q)); code = static_cast<uint32_t>(sc) & 0xffu; }
-        const int v = t2 % nvec, mi = t2 / nvec;
-        xs[mi][v * 16 + j] = static_cast<uint8_t>(code);
-        h.pooled[static_cast<size_t>(mi) * h.c + (v0 + v) * 16 + j] = static_cast<uint8_t>(code);
-    }
-    __syncthreads();
-    // ---- 2. partial inner products over this slice, added into the s32 accumulator
-    for (int row = tid; row < h.n; row += HEAD_THREADS) {
-        const uint4* wr = reinterpret_cast<const uint4*>(h.w + static_cast<size_t>(row) * h.c) + v0;
-        uint4 wv[HEAD_MAX_VEC];
+        uint32_t codes[4];
 #pragma unroll
-        for (int v = 0; v < HEAD_MAX_VEC; ++v) wv[v] = v < nvec ? ldg_stream(wr + v) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 4; ++j) {
+            uint32_t wd = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                uint32_t code;
+                if (h.pool_max) {
+                    code = ((a[j] >> (8 * b)) & 0xffu) ^ (h.in_unsigned ? 0u : 0x80u);
+                } else {
+                    // byte b of word j: even bytes live in a[2j], odd ones in a[2j + 1]; low / high 16-bit lane
+                    const uint32_t lanes = a[2 * j + (b & 1)];
+                    const int32_t sum = static_cast<int32_t>((b & 2) ? (lanes >> 16) : (lanes & 0xffffu)) - (h.in_unsigned ? 0 : 128 * h.hw);
+                    // saber_pooling int8: fp32 sum (exact here) / window, rounded to nearest even, saturated
+                    const float q = __fdiv_rn(static_cast<float>(sum), static_cast<float>(h.hw));
+                    if (h.in_unsigned) asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(code) : "f"(q));
+                    else { int32_t sc; asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(sc) : "f"(q)); code = static_cast<uint32_t>(sc) & 0xffu; }
+                }
+                wd |= code << (8 * b);
+            }
+            codes[j] = wd;
+        }
+        const uint4 cq = make_uint4(codes[0], codes[1], codes[2], codes[3]);
+        reinterpret_cast<uint4*>(xs)[v] = cq;
+        if (cid == 0) reinterpret_cast<uint4*>(h.pooled + static_cast<size_t>(rank) * h.c)[v] = cq;   // the pooling op's tensor
+    }
+    // ---- 2. every CTA of the cluster gathers the m pooled rows
+    cluster_sync_all();
+    {
+        const uint32_t xs_sa = smem_u32(xs);
+        for (int i = tid; i < h.m * cv; i += HEAD_THREADS) {
+            const int mi = i / cv, v = i - mi * cv;
+            uint4 t;
+            const uint32_t ra = map_to_cta(xs_sa + v * 16, mi);
+            asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(ra));
+            reinterpret_cast<uint4*>(xall)[i] = t;
+        }
+    }
+    cluster_sync_all();       // nobody's pooled row is read after this: CTAs may finish at their own pace
+    // ---- 3. this CTA's neurons: a warp each, all m images at once
+    const int row_begin = cid * h.n_cluster + rank * h.n_cta;
+    const int row_end = min(min(row_begin + h.n_cta, (cid + 1) * h.n_cluster), h.n);
+    for (int row = row_begin + warp; row < row_end; row += HEAD_THREADS / 32) {
+        const uint4* wr = reinterpret_cast<const uint4*>(h.w + static_cast<size_t>(row) * h.c);
+        int acc[HEAD_MAX_M];
+#pragma unroll
+        for (int mi = 0; mi < HEAD_MAX_M; ++mi) acc[mi] = 0;
+        for (int v = lane; v < cv; v += 32) {
+            const uint4 wv = ldg_stream(wr + v);
+#pragma unroll
+            for (int mi = 0; mi < HEAD_MAX_M; ++mi) {
+                if (mi < h.m) {
+                    const uint4 xv = reinterpret_cast<const uint4*>(xall)[mi * cv + v];
+                    int a = acc[mi];
+                    if (h.in_unsigned) {
+                        a = dp4a_us(xv.x, wv.x, a); a = dp4a_us(xv.y, wv.y, a); a = dp4a_us(xv.z, wv.z, a); a = dp4a_us(xv.w, wv.w, a);
+                    } else {
+                        a = dp4a_ss(xv.x, wv.x, a); a = dp4a_ss(xv.y, wv.y, a); a = dp4a_ss(xv.z, wv.z, a); a = dp4a_ss(xv.w, wv.w, a);
+                    }
+                    acc[mi] = a;
+                }
+            }
+        }
 #pragma unroll
         for (int mi = 0; mi < HEAD_MAX_M; ++mi) {
-            if (mi < h.m) {
-                int a = 0;
 #pragma unroll
-                for (int v = 0; v < HEAD_MAX_VEC; ++v) {
-                    if (v < nvec) {
-                        const uint4 xv = *reinterpret_cast<const uint4*>(&xs[mi][v * 16]);
-                        if (h.in_unsigned) {
-                            a = dp4a_us(xv.x, wv[v].x, a); a = dp4a_us(xv.y, wv[v].y, a);
-                            a = dp4a_us(xv.z, wv[v].z, a); a = dp4a_us(xv.w, wv[v].w, a);
-                        } else {
-                            a = dp4a_ss(xv.x, wv[v].x, a); a = dp4a_ss(xv.y, wv[v].y, a);
-                            a = dp4a_ss(xv.z, wv[v].z, a); a = dp4a_ss(xv.w, wv[v].w, a);
-                        }
-                    }
-                }
-                asm volatile("red.global.add.s32 [%0], %1;" ::"l"(h.acc + static_cast<size_t>(mi) * h.n + row), "r"(a) : "memory");
-            }
+            for (int o = 16; o > 0; o >>= 1) acc[mi] += __shfl_xor_sync(0xffffffffu, acc[mi], o);
         }
-    }
-    // ---- 3. ticket: the last CTA finishes the head
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        is_last = atomicAdd(h.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int idx = tid; idx < h.m * h.n; idx += HEAD_THREADS) {
-        const int mi = idx / h.n, row = idx - mi * h.n;
-        int32_t a;
-        asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(a) : "l"(h.acc + idx) : "memory");
-        h.acc[idx] = 0;                                           // clean for the next launch
         // x86 Saber int8 epilogue, as epilogue16_i8 of the conv kernels: add, then multiply, each rounded
-        const float f = __fmul_rn(__fadd_rn(__int2float_rn(a), h.bias ? __ldg(h.bias + row) : 0.f), h.scale ? __ldg(h.scale + row) : 1.f);
-        h.logits[static_cast<size_t>(mi) * h.ldo + row] = f;
+        const float bs = h.bias ? __ldg(h.bias + row) : 0.f, sc = h.scale ? __ldg(h.scale + row) : 1.f;
+#pragma unroll
+        for (int mi = 0; mi < HEAD_MAX_M; ++mi)
+            if (mi < h.m && lane == mi) h.logits[static_cast<size_t>(mi) * h.ldo + row] = __fmul_rn(__fadd_rn(__int2float_rn(acc[mi]), bs), sc);
     }
-    if (tid == 0) *h.ticket = 0;
-    __syncthreads();
-    if (h.prob == nullptr) return;
-    // softmax: the CTA takes the rows one after the other with the block routine of softmax_rows_kernel
-    __shared__ float red[SOFTMAX_THREADS / 32];
-    for (int row = 0; row < h.m; ++row)
-        softmax_row_block(h.logits + static_cast<size_t>(row) * h.ldo, h.prob + static_cast<size_t>(row) * h.ldp, h.n, red);
 }
 
 static int fc_mode(int math) { return math == B200_MATH_I8 ? 0 : (math == B200_MATH_F16 ? 1 : 2); }
@@ -454,18 +472,20 @@ int b200_fc_stream_run(const b200_fc_stream_desc_t* d, const void* x, const void
 }
 
 size_t b200_head_workspace_bytes(const b200_head_desc_t* hd) {
-    if (!hd) return 0;
-    return (static_cast<size_t>(hd->fc.m) * hd->fc.n_out + 4) * sizeof(int32_t);   // s32 accumulator + ticket word
+    (void)hd;
+    return 16;      // (kept for the ABI: the two-launch head needs no scratch)
 }
 
 int b200_head_run(const b200_head_desc_t* hd, const void* in, void* pooled, const void* w_plain, const float* bias,
                   const float* scale, void* logits, float* prob, void* workspace, void* stream) {
-    if (!hd || !in || !pooled || !w_plain || !logits || !workspace) return B200_INVALID_VALUE;
+    (void)workspace;
+    if (!hd || !in || !pooled || !w_plain || !logits) return B200_INVALID_VALUE;
     const b200_fc_stream_desc_t* d = &hd->fc;
     if (!fc_args_ok(d) || hd->hw <= 0 || d->ldx != d->k) return B200_INVALID_VALUE;
-    // integer partial sums make the k-split reduction exact and order-free: int8 nets only (float heads keep the
-    // three separate ops), fp32 logits out, at most 8 rows
-    if (d->math != B200_MATH_I8 || d->out_dtype != B200_FLOAT || d->m > HEAD_MAX_M || d->relu) return B200_UNIMPL_ERROR;
+    // int8 nets only (float heads keep the three separate ops), fp32 logits out, at most 8 rows = one cluster
+    if (d->math != B200_MATH_I8 || d->out_dtype != B200_FLOAT || d->m > HEAD_MAX_M || d->relu || d->k > HEAD_MAX_C ||
+        (!hd->pool_max && hd->hw > 256))
+        return B200_UNIMPL_ERROR;
     if (!device_is_sm100()) return B200_WRONG_DEVICE;
     HeadParams h{};
     h.in = static_cast<const uint8_t*>(in);
@@ -473,36 +493,47 @@ int b200_head_run(const b200_head_desc_t* hd, const void* in, void* pooled, cons
     h.w = static_cast<const int8_t*>(w_plain);
     h.bias = bias; h.scale = scale;
     h.logits = static_cast<float*>(logits);
-    h.prob = prob;
-    h.acc = static_cast<int32_t*>(workspace);
-    h.ticket = reinterpret_cast<unsigned*>(h.acc + static_cast<size_t>(d->m) * d->n_out);
-    h.m = d->m; h.hw = hd->hw; h.c = d->k; h.n = d->n_out; h.ldo = d->ldo; h.ldp = hd->ldp;
+    h.m = d->m; h.hw = hd->hw; h.c = d->k; h.n = d->n_out; h.ldo = d->ldo;
     h.in_unsigned = d->in_dtype == B200_UINT8 ? 1 : 0;
     h.pool_max = hd->pool_max;
+    int clusters = sm_count() / d->m;
+    if (clusters < 1) clusters = 1;
+    if (clusters > d->n_out) clusters = d->n_out;
+    h.n_cluster = (d->n_out + clusters - 1) / clusters;
+    clusters = (d->n_out + h.n_cluster - 1) / h.n_cluster;
+    h.n_cta = (h.n_cluster + d->m - 1) / d->m;
     const int cv = d->k / 16;
-    // slice width: as many CTAs as the 256-thread pooling stage allows (m * vectors * 8 pixel groups <= 256)
-    int vpc = HEAD_THREADS / (HEAD_PARTS * d->m);
-    if (vpc > HEAD_MAX_VEC) vpc = HEAD_MAX_VEC;
-    if (vpc < 1) return B200_UNIMPL_ERROR;
-    while (vpc > 1 && (cv + vpc - 1) / vpc < 64) --vpc;      // keep at least ~64 CTAs busy
-    h.vec_per_cta = vpc;
-    const unsigned grid = static_cast<unsigned>((cv + vpc - 1) / vpc);
+    const int pg = HEAD_THREADS / cv > 0 ? HEAD_THREADS / cv : 1;
+    const size_t smem = static_cast<size_t>(d->k) * (1 + d->m) + static_cast<size_t>(pg) * cv * 32;
+    static std::atomic<bool> opted_in[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !opted_in[dev].load(std::memory_order_acquire)) {
+        cudaFuncSetAttribute(head_pool_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        opted_in[dev].store(true, std::memory_order_release);
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(static_cast<unsigned>(clusters * d->m));
     cfg.blockDim = dim3(HEAD_THREADS);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = static_cast<unsigned>(d->m);
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, head_i8_kernel, h);
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, head_pool_fc_kernel, h);
     count_launch();
     if (e == cudaSuccess) e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
         fprintf(stderr, "[b200_saber] head launch failed: %s\n", cudaGetErrorString(e));
         return B200_UNKNOWN_ERROR;
     }
+    if (prob != nullptr) return b200_softmax_rows(h.logits, prob, d->m, d->n_out, d->ldo, hd->ldp, stream);
     return B200_SUCCESS;
 }
 

@@ -195,10 +195,11 @@ Status NetCore::init(GraphCore& graph, Precision precision, int device) {
 // (b200_head_run). Every edge tensor of the three ops is still written, so the fusion is invisible to readers.
 void NetCore::plan_fused_head() {
     _head.on = false;
-    // Opt-in (B200_ANAKIN_FUSED_HEAD=1): measured on ResNet-50 INT8 b8 the single launch takes 37 us -- 512 K integer
-    // reductions into 8000 accumulators run at ~27 per ns -- against ~20 us for the three ops it replaces.
+    // On by default (B200_ANAKIN_FUSED_HEAD=0 keeps the three ops): pooling + inner product are one cluster launch, the
+    // softmax a second one. (A first version that split the reduction dimension over the CTAs and combined them with
+    // integer atomics took 37 us on ResNet-50 INT8 b8 -- slower than the ~17 us of the three ops -- and was replaced.)
     const char* env = getenv("B200_ANAKIN_FUSED_HEAD");
-    if (!(env && env[0] == '1')) return;
+    if (env && env[0] == '0') return;
     for (size_t i = 0; i + 2 < _exec.size(); ++i) {
         ExecOp &ep = _exec[i], &ef = _exec[i + 1], &es = _exec[i + 2];
         int is_max = 0, axis = 0;

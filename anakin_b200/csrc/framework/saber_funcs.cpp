@@ -327,6 +327,15 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
             out_scale = cout->get_scale()[0];
         }
     }
+    if (P.stem_fused) {
+        // the fused pooling may run on the raw accumulators when the epilogue is non-decreasing in them
+        bool pos = spec.neg_slope >= 0.f;
+        if (op == AK_INT8) {
+            pos = pos && in_scale > 0.f && out_scale > 0.f;
+            for (float sc : wq_scale) pos = pos && sc > 0.f;
+        }
+        P.stem_desc.monotone_epilogue = pos ? 1 : 0;
+    }
     if (P.depthwise) { d.c = cs; d.k = cs; d.ldc = cout->channel_stored(); }
     {
         const char* e = getenv("B200_SABER_FC_STREAM");

@@ -54,7 +54,7 @@ class StemDesc(C.Structure):
         ("pool_type", C.c_int32), ("pool_window_h", C.c_int32), ("pool_window_w", C.c_int32),
         ("pool_pad_h", C.c_int32), ("pool_pad_w", C.c_int32), ("pool_stride_h", C.c_int32),
         ("pool_stride_w", C.c_int32), ("pool_global", C.c_int32), ("pool_floor_as_conv", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("monotone_epilogue", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 

@@ -332,7 +332,10 @@ typedef struct {
     int32_t pool_type;  /* a b200_pool_t value: B200_POOL_MAX is what fuses */
     int32_t pool_window_h, pool_window_w, pool_pad_h, pool_pad_w, pool_stride_h, pool_stride_w;
     int32_t pool_global, pool_floor_as_conv;
-    int32_t reserved[2];
+    int32_t monotone_epilogue; /* caller's promise: every scale[] entry is > 0 (INT8) and neg_slope >= 0, i.e. the
+                                  epilogue is non-decreasing in the accumulator. The fused pooling then runs on the raw
+                                  accumulators and only pooled pixels pay for the epilogue -- same bits, less work */
+    int32_t reserved[1];
 } b200_stem_desc_t;
 B200_API int b200_stem_conv_out_hw(const b200_stem_desc_t* d, int32_t* oh, int32_t* ow);
 B200_API size_t b200_stem_packed_weight_bytes(const b200_stem_desc_t* d);

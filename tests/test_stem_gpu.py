@@ -28,13 +28,14 @@ STEM_CASES = [
 ]
 
 
-def _stem_desc(A, math, out_dtype, case, ldc, relu, inv_scale, neg_slope=0.0):
+def _stem_desc(A, math, out_dtype, case, ldc, relu, inv_scale, neg_slope=0.0, monotone=0):
     n, c, h, w, k, r, s, stride, pad, pool = case
     d = A.StemDesc()
     d.math, d.out_dtype = math, out_dtype
     d.n, d.c, d.h, d.w, d.k, d.ldc = n, c, h, w, k, ldc
     d.r, d.s, d.stride_h, d.stride_w, d.pad_h, d.pad_w = r, s, stride, stride, pad, pad
     d.relu, d.neg_slope, d.in_inv_scale = int(relu), neg_slope, inv_scale
+    d.monotone_epilogue = monotone
     if pool is not None:
         d.fuse_pool, d.pool_type = 1, A.POOL_MAX
         d.pool_window_h = d.pool_window_w = pool[0]
@@ -63,7 +64,8 @@ def _run_stem(A, d, x_nchw, w_operand, bias, scale, np_out):
 
 @pytest.mark.parametrize("case", STEM_CASES)
 @pytest.mark.parametrize("variant", ["relu_u8", "s8", "f32"])
-def test_stem_int8_bit_exact(case, variant, oracle):
+@pytest.mark.parametrize("monotone", [0, 1])     # 1: the fused pooling runs on the raw accumulators (positive scales)
+def test_stem_int8_bit_exact(case, variant, monotone, oracle):
     import torch
     from anakin_b200 import saber_abi as A
     rng = np.random.default_rng(abs(hash((case, variant))) % (2 ** 31))
@@ -85,7 +87,9 @@ def test_stem_int8_bit_exact(case, variant, oracle):
     ldc = (k + 15) // 16 * 16 + (16 if variant == "s8" else 0)     # one case family with a row pitch above k
     if out_dtype == A.FLOAT:
         ldc = (k + 3) // 4 * 4
-    d = _stem_desc(A, A.MATH_I8, out_dtype, case, ldc, relu, float(np.float32(1.0) / in_scale))
+    if monotone and pool is None:
+        pytest.skip("the flag only matters with a fused pooling")
+    d = _stem_desc(A, A.MATH_I8, out_dtype, case, ldc, relu, float(np.float32(1.0) / in_scale), monotone=monotone)
     tdt = {A.UINT8: torch.uint8, A.INT8: torch.int8, A.FLOAT: torch.float32}[out_dtype]
     got = _run_stem(A, d, x, wq, bias, scale, tdt)
     assert (got[..., k:] == 0).all(), "padding channels must stay untouched"
@@ -96,7 +100,8 @@ def test_stem_int8_bit_exact(case, variant, oracle):
 
 @pytest.mark.parametrize("case", [STEM_CASES[0], STEM_CASES[2], STEM_CASES[3], STEM_CASES[4], STEM_CASES[7]])
 @pytest.mark.parametrize("math", ["f16", "tf32x3", "tf32"])
-def test_stem_float(case, math, oracle):
+@pytest.mark.parametrize("monotone", [0, 1])
+def test_stem_float(case, math, monotone, oracle):
     import torch
     from anakin_b200 import saber_abi as A
     rng = np.random.default_rng(abs(hash((case, math))) % (2 ** 31))
@@ -121,7 +126,9 @@ def test_stem_float(case, math, oracle):
         want = want.astype(np.float16).astype(np.float32)     # the conv output edge is stored in half
     if pool is not None:
         want = oracle.pool_f32(want, (pool[0],) * 2, (pool[2],) * 2, (pool[1],) * 2, A.POOL_MAX, nhwc=True)
-    d = _stem_desc(A, mk, out_dtype, case, k, True, 1.0, neg_slope=0.1)
+    if monotone and pool is None:
+        pytest.skip("the flag only matters with a fused pooling")
+    d = _stem_desc(A, mk, out_dtype, case, k, True, 1.0, neg_slope=0.1, monotone=monotone)
     got = _run_stem(A, d, x, w_op, bias, None, tdt).astype(np.float32)
     assert got.shape == want.shape, (got.shape, want.shape)
     max_ratio, max_diff = oracle.tensor_cmp(want, got)
