@@ -593,6 +593,23 @@ bool slab_plan_setup(b200_conv_plan* pl) {
     }
     SlabLayout best{};
     bool have = false;
+    // measured preference among the tile widths (tools/layer_sweep.py, profiles/r02_layer_sweep_*.txt): the widest tile
+    // (<= 128) that still leaves >= 64 CTAs -- wider tiles re-read the input rectangle less often and issue fewer, fuller
+    // MMAs -- and the narrowest one when no width reaches 64 CTAs (batch 1). The estimate keeps deciding slab vs im2col.
+    SlabLayout pick{};
+    bool have_pick = false;
+    auto consider = [&](const SlabLayout& L) {
+        if (!have || L.est_clk < best.est_clk) { best = L; have = true; }
+        if (L.bn > 128) return;
+        const int ctas = d.n * L.sp.tiles_h * L.sp.tiles_w * ((d.k + L.bn - 1) / L.bn);
+        const int pick_ctas = have_pick ? d.n * pick.sp.tiles_h * pick.sp.tiles_w * ((d.k + pick.bn - 1) / pick.bn) : 0;
+        bool better;
+        if (!have_pick) better = true;
+        else if ((ctas >= 64) != (pick_ctas >= 64)) better = ctas >= 64;
+        else if (ctas >= 64) better = L.bn > pick.bn || (L.bn == pick.bn && L.est_clk < pick.est_clk);
+        else better = L.bn < pick.bn || (L.bn == pick.bn && L.est_clk < pick.est_clk);
+        if (better) { pick = L; have_pick = true; }
+    };
     const int parts[8] = {1, 2, 3, 4, 6, 8, 12, 16};
     if (d.fuse_pool) {
         // pooled tilings: a ph x pw tile of pooled pixels, its conv rectangle th x tw = ((ph-1)*ps + pk) x ((pw-1)*ps + pk)
@@ -621,7 +638,7 @@ bool slab_plan_setup(b200_conv_plan* pl) {
                 if (force_bn ? bn != force_bn : (bn > max_bn || (bn > kr32 && bn != 32))) continue;
                 SlabLayout L{};
                 if (!slab_layout(d, g, th, tw, bn, &L, &pt)) continue;
-                if (!have || L.est_clk < best.est_clk) { best = L; have = true; }
+                consider(L);
             }
         }
         if (!have) return false;
@@ -641,7 +658,7 @@ bool slab_plan_setup(b200_conv_plan* pl) {
             if (force_bn ? bn != force_bn : (bn > max_bn || (bn > kr32 && bn != 32))) continue;
             SlabLayout L{};
             if (!slab_layout(d, g, th, tw, bn, &L)) continue;
-            if (!have || L.est_clk < best.est_clk) { best = L; have = true; }
+            consider(L);
         }
     }
     if (!have) return false;
@@ -663,6 +680,8 @@ bool slab_plan_setup(b200_conv_plan* pl) {
         if (!force && !force_bn && est0 <= best.est_clk) return false;
     }
 
+    static const bool bn_rule = [] { const char* e = getenv("B200_SABER_SLAB_BN_RULE"); return !(e && e[0] == '0'); }();
+    if (have_pick && bn_rule && !force_bn) best = pick;
     ConvKParams& kp = pl->kp;
     kp.epi_bn = best.bn;
     kp.split = 1;

