@@ -51,6 +51,10 @@ SYMBOLS = {
     "anakin_net_activation_bytes_unshared": (_sz, [_vp]),
     "anakin_net_weight_ptrs": (_i, [_vp, C.POINTER(_vp), _i]),
     "anakin_weight_arena_stats": (_sz, [C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "anakin_weight_arena_set_receive": (None, [C.c_int]),
+    "anakin_weight_arena_flat_bytes": (_sz, [C.c_int]),
+    "anakin_weight_arena_export": (C.c_int, [C.c_int, _vp, _sz]),
+    "anakin_weight_arena_import": (C.c_int, [C.c_int, _vp, _sz]),
     "anakin_net_create_ex": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
     "anakin_net_profile_ops": (_i, [_vp, _i, _i, C.POINTER(C.c_float), _i]),
     "anakin_net_destroy": (None, [_vp]),
@@ -261,6 +265,24 @@ def weight_arena_stats():
     e, h, m = _sz(), _sz(), _sz()
     b = lib.anakin_weight_arena_stats(C.byref(e), C.byref(h), C.byref(m))
     return int(b), e.value, h.value, m.value
+
+
+def weight_arena_set_receive(on):
+    """Receive mode: Nets initialised while it is on allocate their packed-weight images without building them; the
+    images then arrive with weight_arena_import (multi-GPU replicas, see anakin_b200/dist.py)."""
+    load().anakin_weight_arena_set_receive(1 if on else 0)
+
+
+def weight_arena_flat_bytes(device):
+    return int(load().anakin_weight_arena_flat_bytes(device))
+
+
+def weight_arena_export(device, dev_ptr, nbytes):
+    _check(load().anakin_weight_arena_export(device, _vp(dev_ptr), nbytes), "weight_arena_export")
+
+
+def weight_arena_import(device, dev_ptr, nbytes):
+    _check(load().anakin_weight_arena_import(device, _vp(dev_ptr), nbytes), "weight_arena_import")
 
 
 class Worker:

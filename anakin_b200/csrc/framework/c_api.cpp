@@ -199,6 +199,14 @@ int anakin_net_weight_ptrs(anakin_net_t* n, const void** out, int cap) {
 size_t anakin_weight_arena_stats(size_t* entries, size_t* hits, size_t* misses) {
     return saber::weight_arena_stats(entries, hits, misses);
 }
+void anakin_weight_arena_set_receive(int on) { saber::weight_arena_set_receive(on != 0); }
+size_t anakin_weight_arena_flat_bytes(int device) { return saber::weight_arena_flat_bytes(device); }
+int anakin_weight_arena_export(int device, void* flat_dev, size_t cap) {
+    return saber::weight_arena_export(device, flat_dev, cap) == saber::SaberSuccess ? 0 : fail("weight arena export failed");
+}
+int anakin_weight_arena_import(int device, const void* flat_dev, size_t bytes) {
+    return saber::weight_arena_import(device, flat_dev, bytes) == saber::SaberSuccess ? 0 : fail("weight arena import failed");
+}
 void anakin_net_destroy(anakin_net_t* n) { delete n; }
 
 int anakin_worker_create(const char* model_path, int precision, int threads, const int* devices, int n_devices,

@@ -9,6 +9,7 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -22,11 +23,16 @@ namespace saber {
 // framework/core/net/worker.cpp:10-53). Entries are reference counted and freed with their last user.
 struct DevWeights {
     DeviceBuffer w, bias, scale;   // w: tcgen05-packed image, or the plain [n][k] image of a weight-streaming fc
+    int device = 0;
 };
 namespace {
 std::mutex g_arena_mu;
 std::map<std::string, std::weak_ptr<DevWeights>> g_arena;
+std::vector<std::weak_ptr<DevWeights>> g_arena_order;   // creation order: identical on every replica of one graph
+bool g_arena_receive = false;                            // allocate images without building them (see below)
 size_t g_arena_hits = 0, g_arena_misses = 0;
+constexpr size_t kFlatAlign = 256;
+size_t flat_pad(size_t n) { return (n + kFlatAlign - 1) / kFlatAlign * kFlatAlign; }
 
 template <typename T>
 void key_add(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
@@ -39,10 +45,56 @@ size_t weight_arena_stats(size_t* entries, size_t* hits, size_t* misses) {
         if (auto p = it->second.lock()) { bytes += p->w.bytes + p->bias.bytes + p->scale.bytes; ++n; ++it; }
         else it = g_arena.erase(it);
     }
+    g_arena_order.erase(std::remove_if(g_arena_order.begin(), g_arena_order.end(),
+                                       [](const std::weak_ptr<DevWeights>& w) { return w.expired(); }), g_arena_order.end());
     if (entries) *entries = n;
     if (hits) *hits = g_arena_hits;
     if (misses) *misses = g_arena_misses;
     return bytes;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Replicas on other GPUs (one process per GPU) need not fold, quantise and pack the weights again: the rank that built
+// them exports every image of its arena, in creation order, into ONE contiguous device buffer; that buffer travels by a
+// single NCCL broadcast over NVLink (bench.py / anakin_b200/dist.py), and the other ranks -- which built their Nets in
+// "receive" mode: same plans, same buffer sizes, no host-side packing -- import it. The reference has nothing of the
+// kind (its Worker replicates on one device, worker.cpp:10-53); SURVEY.md section 8e asks for NCCL-broadcast weights.
+void weight_arena_set_receive(bool on) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    g_arena_receive = on;
+}
+static std::vector<std::shared_ptr<DevWeights>> arena_entries_of(int device) {
+    std::vector<std::shared_ptr<DevWeights>> v;
+    for (auto& w : g_arena_order)
+        if (auto p = w.lock()) if (p->device == device) v.push_back(p);
+    return v;
+}
+size_t weight_arena_flat_bytes(int device) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    size_t n = 0;
+    for (auto& p : arena_entries_of(device)) n += flat_pad(p->w.bytes) + flat_pad(p->bias.bytes) + flat_pad(p->scale.bytes);
+    return n;
+}
+static SaberStatus arena_copy(int device, void* flat, size_t cap, bool to_flat) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    size_t off = 0;
+    for (auto& p : arena_entries_of(device)) {
+        DeviceBuffer* bufs[3] = {&p->w, &p->bias, &p->scale};
+        for (DeviceBuffer* b : bufs) {
+            if (b->bytes == 0) continue;
+            if (off + b->bytes > cap) return SaberInvalidValue;
+            uint8_t* f = static_cast<uint8_t*>(flat) + off;
+            if (cudaMemcpy(to_flat ? static_cast<void*>(f) : b->ptr, to_flat ? b->ptr : static_cast<void*>(f), b->bytes,
+                           cudaMemcpyDeviceToDevice) != cudaSuccess)
+                return SaberUnKownError;
+            off += flat_pad(b->bytes);
+        }
+    }
+    return SaberSuccess;
+}
+SaberStatus weight_arena_export(int device, void* flat_dev, size_t cap) { return arena_copy(device, flat_dev, cap, true); }
+SaberStatus weight_arena_import(int device, const void* flat_dev, size_t bytes) {
+    return arena_copy(device, const_cast<void*>(flat_dev), bytes, false);
 }
 
 struct ConvEngine::Impl {
@@ -364,8 +416,36 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
         else P.dw.reset();
         if (P.dw) ++g_arena_hits;
     }
+    bool receive;
+    { std::lock_guard<std::mutex> lk(g_arena_mu); receive = g_arena_receive; }
+    if (!P.dw && receive) {
+        // receive mode: the image arrives by broadcast (weight_arena_import); only its buffers are made here
+        std::shared_ptr<DevWeights> dw = std::make_shared<DevWeights>();
+        cudaGetDevice(&dw->device);
+        const int es = op == AK_INT8 ? 1 : (op == AK_HALF ? 2 : 4);
+        size_t w_bytes, n_tab;
+        if (P.depthwise) {
+            w_bytes = static_cast<size_t>(spec.r) * spec.s * cs * es;
+            n_tab = cs;
+        } else if (P.fc_stream) {
+            w_bytes = static_cast<size_t>(spec.k) * d.c * es;
+            n_tab = spec.k;
+        } else {
+            w_bytes = b200_conv_packed_weight_bytes(&d);
+            n_tab = spec.k;
+        }
+        if (w_bytes == 0 || dw->w.re_alloc(w_bytes, false) != SaberSuccess || dw->bias.re_alloc(n_tab * sizeof(float), false) != SaberSuccess ||
+            (op == AK_INT8 && dw->scale.re_alloc(n_tab * sizeof(float), false) != SaberSuccess))
+            return SaberOutOfMem;
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        g_arena[key] = dw;
+        g_arena_order.push_back(dw);
+        P.dw = dw;
+        ++g_arena_misses;
+    }
     if (!P.dw) {
         std::shared_ptr<DevWeights> dw = std::make_shared<DevWeights>();
+        cudaGetDevice(&dw->device);
         std::vector<float> bias_f(spec.k, 0.f), scale_f;
         // INT8 epilogue tables from the per-output-channel weight scales (jit_avx512_core_x8s8s32x_conv.cpp:55-62,226-255)
         auto int8_tables = [&](const std::vector<float>& w_scale, int count) {
@@ -504,6 +584,7 @@ SaberStatus ConvEngine::prepare(const Spec& spec, const Tensor<NV>& in, const Te
             P.dw = other;          // another thread built the same image meanwhile: keep one
         } else {
             g_arena[key] = dw;
+            g_arena_order.push_back(dw);
             P.dw = dw;
             ++g_arena_misses;
         }

@@ -54,6 +54,12 @@ private:
 // Live packed-weight images of this process: total device bytes; optionally entry count and how many
 // ConvEngine::prepare calls found their image already built (hits) or had to build it (misses).
 ANAKIN_EXPORT size_t weight_arena_stats(size_t* entries, size_t* hits, size_t* misses);
+// Multi-GPU replicas: export / import the whole arena of a device as one contiguous device buffer (one NCCL broadcast);
+// in receive mode ConvEngine::prepare allocates the images without building them. See saber_funcs.cpp.
+ANAKIN_EXPORT void weight_arena_set_receive(bool on);
+ANAKIN_EXPORT size_t weight_arena_flat_bytes(int device);
+ANAKIN_EXPORT SaberStatus weight_arena_export(int device, void* flat_dev, size_t cap);
+ANAKIN_EXPORT SaberStatus weight_arena_import(int device, const void* flat_dev, size_t bytes);
 
 // ------------------------------------------------------------------------------------- conv
 template <typename T, DataType OpDtype>

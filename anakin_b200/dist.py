@@ -23,6 +23,34 @@ def broadcast_bytes(blob, src=0, device="cpu"):
     return bytes(buf.cpu().numpy())
 
 
+def broadcast_weight_arena(device, src=0):
+    """One NCCL broadcast of the packed-weight arena of `device` (every conv / fc weight image, bias and scale table the
+    Nets of this process hold, contiguous in creation order) from rank `src`. The other ranks must have initialised
+    their Nets under api.weight_arena_set_receive(True): identical plans and buffers, nothing folded, quantised or
+    packed on their hosts. Returns (bytes, milliseconds)."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from . import api
+    nbytes = api.weight_arena_flat_bytes(device)
+    if not dist.is_initialized() or dist.get_world_size() == 1 or nbytes == 0:
+        return nbytes, 0.0
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(dist.get_world_size())]
+    dist.all_gather(sizes, torch.tensor([nbytes], dtype=torch.int64, device="cuda"))
+    if any(int(s.item()) != nbytes for s in sizes):
+        raise RuntimeError("weight arenas differ between ranks: %s" % [int(s.item()) for s in sizes])
+    flat = torch.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", device))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if dist.get_rank() == src:
+        api.weight_arena_export(device, flat.data_ptr(), nbytes)
+    dist.broadcast(flat, src)
+    if dist.get_rank() != src:
+        api.weight_arena_import(device, flat.data_ptr(), nbytes)
+    torch.cuda.synchronize()
+    return nbytes, (time.perf_counter() - t0) * 1e3
+
+
 def shard_range(total, rank, world):
     """Contiguous slice [lo, hi) of `total` requests owned by `rank` (remainder to the low ranks)."""
     base, rem = divmod(total, world)

@@ -87,6 +87,14 @@ ANAKIN_API size_t anakin_net_activation_bytes_unshared(anakin_net_t* n); /* one 
 ANAKIN_API int anakin_net_weight_ptrs(anakin_net_t* n, const void** out, int cap);
 /* live packed-weight images of this process: total device bytes (+ entries, lookups that hit / missed) */
 ANAKIN_API size_t anakin_weight_arena_stats(size_t* entries, size_t* hits, size_t* misses);
+/* Replicas on other GPUs (one process per GPU): the rank that built the weights exports the whole arena of `device` as one
+ * contiguous DEVICE buffer (creation order, 256-byte aligned images), that buffer is broadcast once with NCCL, and ranks
+ * whose Nets were initialised in receive mode (same plans and buffers, no fold / quantise / pack on the host) import it.
+ * "NCCL-broadcast weights over NVLink". Returns 0 on success. */
+ANAKIN_API void anakin_weight_arena_set_receive(int on);
+ANAKIN_API size_t anakin_weight_arena_flat_bytes(int device);
+ANAKIN_API int anakin_weight_arena_export(int device, void* flat_dev, size_t cap);
+ANAKIN_API int anakin_weight_arena_import(int device, const void* flat_dev, size_t bytes);
 /* Per-op device time in ms (same order as anakin_net_exec_order), mean of `iters` eager runs with a
  * CUDA-event pair around every op -- the reference's ENABLE_OP_TIMER (net.cpp:445-449,494-506).
  * reps > 1 launches each op `reps` times back to back inside its pair (steady-state device time). */

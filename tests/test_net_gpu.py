@@ -451,3 +451,43 @@ def test_calibrator_entropy_table_is_tighter_and_usable():
     assert all(ent[k] <= mx[k] * (1 + 1e-6) for k in mx)
     assert any(ent[k] < 0.98 * mx[k] for k in mx)                       # some tensor is actually clipped
     assert all(129 <= t <= calibrate.BIN_NUM for t in cal.thresh_map.values())
+
+
+def test_weight_arena_export_import_round_trip():
+    """Multi-GPU replicas receive the packed weights by one broadcast (anakin_b200/dist.py::broadcast_weight_arena). The
+    mechanism on one GPU, in a fresh process (its arena holds nothing else): export the arena of a Net, drop the Net,
+    build the same Net in receive mode (buffers only -- its output is wrong), import the exported image: bit-identical."""
+    import subprocess
+    import sys
+    code = r'''
+import gc, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from anakin_b200 import anakin_bin, api, modelzoo
+def build(batch):
+    G = api.Graph.from_bytes(anakin_bin.dumps(modelzoo.build("tiny_resnet", batch=batch, precision="int8")))
+    G.ResetBatchSize("input_0", batch); G.Optimize()
+    return G
+def run(net, x):
+    net.set_input("input_0", x); net.prediction(); net.sync(); return net.get_output().copy()
+x = modelzoo.synthetic_input(3, 32)
+G = build(3); a = api.Net(G, "int8", device=0)
+want = run(a, x)
+nbytes = api.weight_arena_flat_bytes(0)
+assert nbytes > 0 and nbytes %% 256 == 0
+flat = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+api.weight_arena_export(0, flat.data_ptr(), nbytes)
+del a, G; gc.collect()
+assert api.weight_arena_stats()[1] == 0, "arena must be empty once its Nets are gone"
+api.weight_arena_set_receive(True)
+G = build(3); b = api.Net(G, "int8", device=0)
+api.weight_arena_set_receive(False)
+assert api.weight_arena_flat_bytes(0) == nbytes
+assert not np.array_equal(run(b, x), want), "receive mode must not have built any weights"
+api.weight_arena_import(0, flat.data_ptr(), nbytes)
+got = run(b, x)
+np.testing.assert_array_equal(got, want)
+print("ROUND_TRIP_OK", nbytes)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ROUND_TRIP_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
