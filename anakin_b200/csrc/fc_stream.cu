@@ -265,9 +265,10 @@ struct HeadParams {
     int n_cluster, n_cta; // neurons per cluster / per CTA
 };
 
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 512;
 constexpr int HEAD_MAX_M = 8;
 constexpr int HEAD_MAX_C = 4096;
+constexpr int HEAD_LOADS = 8;       // pooling loads in flight per thread (the stage is pure load latency otherwise)
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_pool_fc_kernel(const HeadParams h) {
     extern __shared__ __align__(16) uint8_t head_smem[];
@@ -288,16 +289,25 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_pool_fc_kernel(const HeadPa
         uint32_t a[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = 0u;
-        for (int t = pg; t < h.hw; t += PG) {
-            const uint4 y = __ldg(src + static_cast<size_t>(t) * cv);
-            const uint32_t w4[4] = {y.x ^ flip, y.y ^ flip, y.z ^ flip, y.w ^ flip};
+        for (int t0 = pg; t0 < h.hw; t0 += PG * HEAD_LOADS) {
+            uint4 y[HEAD_LOADS];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (h.pool_max) {
-                    a[j] = __vmaxu4(a[j], w4[j]);
-                } else {      // bytes 0, 2 and bytes 1, 3 as two pairs of 16-bit lanes (255 * hw < 65536)
-                    a[2 * j] += w4[j] & 0x00FF00FFu;
-                    a[2 * j + 1] += (w4[j] >> 8) & 0x00FF00FFu;
+            for (int u = 0; u < HEAD_LOADS; ++u) {
+                const int t = t0 + u * PG;
+                // (a missing pixel contributes the neutral element of both folds: biased 0)
+                y[u] = t < h.hw ? __ldg(src + static_cast<size_t>(t) * cv) : make_uint4(flip, flip, flip, flip);
+            }
+#pragma unroll
+            for (int u = 0; u < HEAD_LOADS; ++u) {
+                const uint32_t w4[4] = {y[u].x ^ flip, y[u].y ^ flip, y[u].z ^ flip, y[u].w ^ flip};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (h.pool_max) {
+                        a[j] = __vmaxu4(a[j], w4[j]);
+                    } else {      // bytes 0, 2 and bytes 1, 3 as two pairs of 16-bit lanes (255 * hw < 65536)
+                        a[2 * j] += w4[j] & 0x00FF00FFu;
+                        a[2 * j + 1] += (w4[j] >> 8) & 0x00FF00FFu;
+                    }
                 }
             }
         }

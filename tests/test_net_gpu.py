@@ -491,3 +491,23 @@ print("ROUND_TRIP_OK", nbytes)
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ROUND_TRIP_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_worker_threads_on_two_devices():
+    """Worker with devices=[0, 1]: thread i drives GPU i from ONE process (per-device shared-memory opt-in, per-device
+    weight arena, tensor maps encoded per device). Needs two GPUs (`gpurun --gpus 2`); skipped on a single-GPU box."""
+    import torch
+    from anakin_b200 import api, modelzoo
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    gold = np.load(os.path.join(GOLD, "tiny_resnet_golden.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        model = os.path.join(d, "tiny.anakin.bin")
+        modelzoo.save(modelzoo.build("tiny_resnet", 4, "int8"), model)
+        w = api.Worker(model, "int8", threads=2, devices=(0, 1), batch=4)
+        w.wait_ready()
+        x = modelzoo.synthetic_input(4, 32)
+        for _ in range(8):          # requests alternate between the two threads / devices
+            out = w.sync_prediction(x, 4 * 12).reshape(4, 12)[:, :10]
+            np.testing.assert_allclose(out, gold["prob_int8"][:4], rtol=1e-4, atol=1e-6)
+        del w
