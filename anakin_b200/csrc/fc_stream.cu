@@ -506,7 +506,12 @@ int b200_head_run(const b200_head_desc_t* hd, const void* in, void* pooled, cons
     h.m = d->m; h.hw = hd->hw; h.c = d->k; h.n = d->n_out; h.ldo = d->ldo;
     h.in_unsigned = d->in_dtype == B200_UINT8 ? 1 : 0;
     h.pool_max = hd->pool_max;
-    int clusters = sm_count() / d->m;
+    // Every cluster pools all m images again, and clusters that read the same lines at the same time queue up at the L2
+    // slices (18 clusters: 15 us; tools/bench_head.py): as few clusters as keep a CTA's weight slice around 64 KB
+    int clusters = static_cast<int>((static_cast<int64_t>(d->n_out) * d->k + static_cast<int64_t>(d->m) * 65536 - 1) /
+                                    (static_cast<int64_t>(d->m) * 65536));
+    if (const char* e = getenv("B200_HEAD_CLUSTERS")) { if (atoi(e) > 0) clusters = atoi(e); }   // tuning experiments only
+    if (clusters > sm_count() / d->m) clusters = sm_count() / d->m;
     if (clusters < 1) clusters = 1;
     if (clusters > d->n_out) clusters = d->n_out;
     h.n_cluster = (d->n_out + clusters - 1) / clusters;
