@@ -866,8 +866,10 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     // Measured (tools/tile_tune.py): a CTA's k loop advances at ~0.25 us per 128-byte k-iteration -- one
     // SM ingests only ~42 B/clk from L2 -- and the two cluster barriers + DSMEM hop cost ~1.5 us, so
     // splitting pays only for long loops on grids that stay within one wave.
-    // (k_iters >= 16: the 1x1 2048 -> 512 layers of the 7x7 stage, 6.4 us split in two vs 7.2 us, tools/layer_sweep.py)
-    if (split_enabled && k_iters >= 16 && ctas * 2 <= sms) {
+    // (k_iters >= 16 would also split the 1x1 2048 -> 512 layers of the 7x7 stage: 6.4 vs 7.2 us timed alone,
+    // tools/layer_sweep.py, but 2.4 us SLOWER per step inside the net -- cluster launches overlap their neighbours less)
+    static const int split_min_iters = [] { const char* e = getenv("B200_SABER_SPLIT_MIN_ITERS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 24; }();
+    if (split_enabled && k_iters >= split_min_iters && ctas * 2 <= sms) {
         split = 2;
         if (k_iters >= 32 && ctas * 4 <= sms) split = 4;
     }

@@ -593,9 +593,11 @@ bool slab_plan_setup(b200_conv_plan* pl) {
     }
     SlabLayout best{};
     bool have = false;
-    // measured preference among the tile widths (tools/layer_sweep.py, profiles/r02_layer_sweep_*.txt): the widest tile
-    // (<= 128) that still leaves >= 64 CTAs -- wider tiles re-read the input rectangle less often and issue fewer, fuller
-    // MMAs -- and the narrowest one when no width reaches 64 CTAs (batch 1). The estimate keeps deciding slab vs im2col.
+    // Alternative rule (B200_SABER_SLAB_BN_RULE=1): the widest tile (<= 128) that still leaves >= 64 CTAs, the narrowest one
+    // when no width reaches 64 CTAs. It wins by 9 us over ResNet-50 b8 when every layer is timed alone (a chain of identical
+    // launches, tools/layer_sweep.py) and LOSES 9 us inside the real net (same box, bench.py A/B: 315.3 vs 306.0 us): the
+    // wider tiles take the whole SM's shared memory, so the next layer's CTAs cannot become resident early and its
+    // prologue + weight prefetch no longer hide under this layer (PDL). The estimate-driven choice stays the default.
     SlabLayout pick{};
     bool have_pick = false;
     auto consider = [&](const SlabLayout& L) {
@@ -680,7 +682,7 @@ bool slab_plan_setup(b200_conv_plan* pl) {
         if (!force && !force_bn && est0 <= best.est_clk) return false;
     }
 
-    static const bool bn_rule = [] { const char* e = getenv("B200_SABER_SLAB_BN_RULE"); return !(e && e[0] == '0'); }();
+    static const bool bn_rule = [] { const char* e = getenv("B200_SABER_SLAB_BN_RULE"); return e && e[0] == '1'; }();
     if (have_pick && bn_rule && !force_bn) best = pick;
     ConvKParams& kp = pl->kp;
     kp.epi_bn = best.bn;

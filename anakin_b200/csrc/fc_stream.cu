@@ -375,8 +375,18 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_pool_fc_kernel(const HeadPa
         int acc[HEAD_MAX_M];
 #pragma unroll
         for (int mi = 0; mi < HEAD_MAX_M; ++mi) acc[mi] = 0;
-        for (int v = lane; v < cv; v += 32) {
-            const uint4 wv = ldg_stream(wr + v);
+        // all weight vectors of the neuron in flight at once (cv <= 256: at most 8 per lane)
+        uint4 wvs[HEAD_MAX_C / 16 / 32];
+#pragma unroll
+        for (int j = 0; j < HEAD_MAX_C / 16 / 32; ++j) {
+            const int v = lane + 32 * j;
+            wvs[j] = v < cv ? ldg_stream(wr + v) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < HEAD_MAX_C / 16 / 32; ++j) {
+            const int v = lane + 32 * j;
+            if (v >= cv) break;
+            const uint4 wv = wvs[j];
 #pragma unroll
             for (int mi = 0; mi < HEAD_MAX_M; ++mi) {
                 if (mi < h.m) {

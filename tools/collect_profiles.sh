@@ -18,6 +18,9 @@ python tools/bench_pointwise.py > $O/pointwise_gbs.txt 2>&1
 ncu --set full --clock-control none -c 40 -o $O/pointwise -f python tools/bench_pointwise.py --once > $O/ncu_pointwise.log 2>&1
 python tools/ncu_keymetrics.py $O/pointwise.ncu-rep > $O/ncu_pointwise_keymetrics.txt 2>&1
 rm -f $O/pointwise.ncu-rep
+# 3b. the classifier head kernel alone (small report, kept)
+ncu --set full --clock-control none --import-source on -k regex:head_pool -c 1 -o $O/head -f \
+    python tools/profile_net.py --batch 8 --iters 1 --reps 1 > /dev/null 2>&1
 # 4. steady-state per-op tables
 python tools/profile_net.py --batch 8 > $O/per_op_b8.txt 2>&1
 python tools/profile_net.py --batch 1 > $O/per_op_b1.txt 2>&1
