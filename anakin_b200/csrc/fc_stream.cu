@@ -268,19 +268,39 @@ struct HeadParams {
 constexpr int HEAD_THREADS = 512;
 constexpr int HEAD_MAX_M = 8;
 constexpr int HEAD_MAX_C = 4096;
-constexpr int HEAD_LOADS = 8;       // pooling loads in flight per thread (the stage is pure load latency otherwise)
+constexpr int HEAD_LOADS = 16;      // pooling loads in flight per thread (the stage is pure load latency otherwise)
+constexpr int HEAD_PRE_ROWS = 2;    // neurons per warp whose weights are fetched before anything else
+constexpr int HEAD_PRE_VECS = 4;    // ... when a row is at most 4 x 32 vectors (c <= 2048)
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_pool_fc_kernel(const HeadParams h) {
     extern __shared__ __align__(16) uint8_t head_smem[];
     uint8_t* xs = head_smem;                                      // [c] this CTA's pooled row
     uint8_t* xall = head_smem + h.c;                              // [m][c]
     uint32_t* part = reinterpret_cast<uint32_t*>(xall + static_cast<size_t>(h.m) * h.c);   // [pg][cv][8]
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = static_cast<int>(cluster_ctarank());
     const int cid = blockIdx.x / h.m;
     const int cv = h.c >> 4;                                      // 16-byte vectors per pixel
+    const int row_begin = cid * h.n_cluster + rank * h.n_cta;
+    const int row_end = min(min(row_begin + h.n_cta, (cid + 1) * h.n_cluster), h.n);
+    // The weights do not depend on the previous kernel: the first HEAD_PRE_ROWS neurons of every warp are on their way
+    // before the grid dependency resolves (PDL), so their DRAM / L2 latency is off the pool -> gather -> dot chain.
+    uint4 wpre[HEAD_PRE_ROWS][HEAD_PRE_VECS];
+    const bool prefetched = cv <= 32 * HEAD_PRE_VECS;
+    if (prefetched) {
+#pragma unroll
+        for (int pr = 0; pr < HEAD_PRE_ROWS; ++pr) {
+            const int row = row_begin + warp + pr * (HEAD_THREADS / 32);
+#pragma unroll
+            for (int j = 0; j < HEAD_PRE_VECS; ++j) {
+                const int v = lane + 32 * j;
+                wpre[pr][j] = (row < row_end && v < cv) ? ldg_stream(reinterpret_cast<const uint4*>(h.w + static_cast<size_t>(row) * h.c) + v)
+                                                        : make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t flip = h.in_unsigned ? 0u : 0x80808080u;       // s8 -> biased u8
     // ---- 1. pool image `rank`: thread (pg, v) folds pixels pg, pg + PG, ... of channel vector v
     const int PG = HEAD_THREADS / cv > 0 ? HEAD_THREADS / cv : 1;
@@ -368,19 +388,21 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_pool_fc_kernel(const HeadPa
     }
     cluster_sync_all();       // nobody's pooled row is read after this: CTAs may finish at their own pace
     // ---- 3. this CTA's neurons: a warp each, all m images at once
-    const int row_begin = cid * h.n_cluster + rank * h.n_cta;
-    const int row_end = min(min(row_begin + h.n_cta, (cid + 1) * h.n_cluster), h.n);
-    for (int row = row_begin + warp; row < row_end; row += HEAD_THREADS / 32) {
+    int pr_idx = 0;
+    for (int row = row_begin + warp; row < row_end; row += HEAD_THREADS / 32, ++pr_idx) {
         const uint4* wr = reinterpret_cast<const uint4*>(h.w + static_cast<size_t>(row) * h.c);
         int acc[HEAD_MAX_M];
 #pragma unroll
         for (int mi = 0; mi < HEAD_MAX_M; ++mi) acc[mi] = 0;
-        // all weight vectors of the neuron in flight at once (cv <= 256: at most 8 per lane)
+        // all weight vectors of the neuron in flight at once (cv <= 256: at most 8 per lane); the first rows of the warp
+        // were fetched at kernel entry
         uint4 wvs[HEAD_MAX_C / 16 / 32];
+        const bool pre = prefetched && pr_idx < HEAD_PRE_ROWS;
 #pragma unroll
         for (int j = 0; j < HEAD_MAX_C / 16 / 32; ++j) {
             const int v = lane + 32 * j;
-            wvs[j] = v < cv ? ldg_stream(wr + v) : make_uint4(0, 0, 0, 0);
+            if (pre) wvs[j] = j < HEAD_PRE_VECS ? (pr_idx == 0 ? wpre[0][j < HEAD_PRE_VECS ? j : 0] : wpre[1][j < HEAD_PRE_VECS ? j : 0]) : make_uint4(0, 0, 0, 0);
+            else wvs[j] = v < cv ? ldg_stream(wr + v) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int j = 0; j < HEAD_MAX_C / 16 / 32; ++j) {

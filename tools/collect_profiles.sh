@@ -15,7 +15,7 @@ python tools/ncu_traffic.py $O/pred_full.ncu-rep $O/ncu_conv_per_launch.txt $O/c
 rm -f $O/pred_full.ncu-rep     # ~80 MB: over the copy-back limit; the text summaries are what is kept
 # 3. pointwise / streaming kernels: achieved GB/s (CUDA events) and the DRAM-side counters of one launch each
 python tools/bench_pointwise.py > $O/pointwise_gbs.txt 2>&1
-ncu --set full --clock-control none -c 40 -o $O/pointwise -f python tools/bench_pointwise.py --once > $O/ncu_pointwise.log 2>&1
+ncu --set full --clock-control none -k regex:b200 -c 40 -o $O/pointwise -f python tools/bench_pointwise.py --once > $O/ncu_pointwise.log 2>&1
 python tools/ncu_keymetrics.py $O/pointwise.ncu-rep > $O/ncu_pointwise_keymetrics.txt 2>&1
 rm -f $O/pointwise.ncu-rep
 # 3b. the classifier head kernel alone (small report, kept)

@@ -25,7 +25,7 @@ def main(rep, txt_out, json_out):
     name_i = hdr.index("Kernel Name")
     recs = []
     for r in rows[2:]:
-        rec = {"kernel": re.sub(r"\(.*", "", r[name_i]).replace("void b200::", "")}
+        rec = {"kernel": re.sub(r"\(.*", "", r[name_i]).replace("void ", "").replace("b200::", "")}
         for name, short in COLS:
             i = idx[short]
             if i < 0 or not r[i]:
