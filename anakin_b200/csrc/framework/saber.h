@@ -151,7 +151,9 @@ struct DeviceBuffer {
             // device buffers start zeroed: NHWC channel padding is never written by any kernel and
             // must read as 0 (a NaN there would poison 0-weight products in the float convs)
             if (cudaMalloc(&ptr, n) != cudaSuccess) { ptr = nullptr; (void)cudaGetLastError(); return SaberOutOfMem; }
-            if (cudaMemset(ptr, 0, n) != cudaSuccess) { (void)cudaGetLastError(); }
+            // (the fill runs on the legacy default stream, which does not order against the Nets' non-blocking streams:
+            // wait for it here -- allocation time only -- so that no later kernel can race with a late memset)
+            if (cudaMemset(ptr, 0, n) != cudaSuccess || cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { (void)cudaGetLastError(); }
         }
         bytes = n;
         return SaberSuccess;
