@@ -387,39 +387,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
         };
-        if (SPLITK) {
 #pragma unroll 1
-            for (int c0 = cbeg; c0 < cend; c0 += 16) {
-                if (n0_epi + c0 >= p.K) break;  // warp-uniform; TMA clips the unwritten columns anyway
-                uint32_t v0[16];
-                tmem_ld_32x32b_x16(t_row + c0, v0);
-                tmem_ld_wait();
-                add_partials(v0, c0);
-                epilogue16<MK>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
-            }
-        } else {
-            // software pipeline over the 16-column groups: the tcgen05.ld of group g + 1 is in flight while group g goes
-            // through bias / scale / residual / requantise (the read-out of the wide 56 x 56 tiles is the longest phase
-            // of their launch)
-            uint32_t va[16], vb[16];
-            int c0 = cbeg;
-            bool more = c0 < cend && n0_epi + c0 < p.K;
-            if (more) tmem_ld_32x32b_x16(t_row + c0, va);
-#pragma unroll 1
-            while (more) {
-                tmem_ld_wait_regs(va);
-                const int c1 = c0 + 16;
-                const bool next = c1 < cend && n0_epi + c1 < p.K;
-                if (next) tmem_ld_32x32b_x16(t_row + c1, vb);
-                epilogue16<MK>(p, va, c0, bias_sa, scale_sa, res_row, out_row);
-                if (!next) break;
-                tmem_ld_wait_regs(vb);
-                const int c2 = c1 + 16;
-                more = c2 < cend && n0_epi + c2 < p.K;
-                if (more) tmem_ld_32x32b_x16(t_row + c2, va);
-                epilogue16<MK>(p, vb, c1, bias_sa, scale_sa, res_row, out_row);
-                c0 = c2;
-            }
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            if (n0_epi + c0 >= p.K) break;  // warp-uniform; TMA clips the unwritten columns anyway
+            uint32_t v0[16];
+            tmem_ld_32x32b_x16(t_row + c0, v0);
+            tmem_ld_wait();
+            if (SPLITK) add_partials(v0, c0);
+            epilogue16<MK>(p, v0, c0, bias_sa, scale_sa, res_row, out_row);
         }
         tc_fence_before();
         fence_proxy_async_smem();                                          // staged tile -> visible to the TMA engine

@@ -235,7 +235,7 @@ def calibrate(graph, images_nchw):
     return {k: (v / 127.0 if v > 0 else 1.0) for k, v in absmax.items()}
 
 
-def run_int8(graph, x_nchw, edge_scales, return_intermediate=False):
+def run_int8(graph, x_nchw, edge_scales, return_intermediate=False, fast=False):
     """INT8 forward with x86 Saber semantics. edge_scales: {node_name: output scale}."""
     groups = plan(graph)
     int8_ops = {"Convolution", "BatchNorm", "Scale", "ReLU", "Pooling", "Eltwise", "Dense", "Split", "Input"}
@@ -310,8 +310,9 @@ def run_int8(graph, x_nchw, edge_scales, return_intermediate=False):
                     raise NotImplementedError("fp32 residual into int8 ConvEltwise")
             scale, bias_f, sum_scale = O.int8_conv_scales(w_scale, bias, s_in, sdt, s_out, out_dt,
                                                           res_scale, res_dt)
+            # fast: the AVX-512 VNNI implementation of the same arithmetic (bit-identical; bench.py's CPU arm)
             y = O.conv_s8_nhwc_x86(src, wq, bias_f, scale, residual=res, sum_scale=sum_scale,
-                                   out_dtype=out_dt, relu=g.relu, **kw)
+                                   out_dtype=out_dt, relu=g.relu, fast=fast, **kw)
             put(g, y, out_dt, s_out)
         elif g.kind == "pool":
             src, sdt, s_in = vals[g.inputs[0]]

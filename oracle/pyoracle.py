@@ -20,8 +20,8 @@ DT_FLOAT, DT_INT8, DT_UINT8 = 1, 3, 7
 
 def build(ref=True):
     """Compile liboracle.so (always) and oracle/_ref (only where /root/reference exists)."""
-    src = os.path.join(_HERE, "oracle.c")
-    if (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_vnni.c", "Makefile")]
+    if (not os.path.exists(_LIB)) or any(os.path.getmtime(_LIB) < os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
     if ref and os.path.isdir("/root/reference/test/saber") and not all(os.path.exists(os.path.join(_HERE, "_ref", n)) for n in
                     ("libanakin_ref_oracle.so", "libanakin_ref_shapes.so", "libanakin_ref_fold.so",
@@ -37,6 +37,9 @@ def lib():
     global _lib
     if _lib is None:
         build(ref=False)
+        # idle OpenMP threads must sleep, not spin: on a CPU-quota'd container spinning waiters starve the workers
+        # (measured here: 64 ms instead of 1 ms for a small parallel loop). Only effective when libgomp is not loaded yet.
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         _lib = C.CDLL(_LIB)
         _lib.oracle_conv_out_size.restype = C.c_int
         _lib.oracle_num_threads.restype = C.c_int
@@ -134,14 +137,38 @@ def _dt(a):
     return {np.dtype(np.float32): DT_FLOAT, np.dtype(np.int8): DT_INT8, np.dtype(np.uint8): DT_UINT8}[a.dtype]
 
 
+def vnni_available():
+    return bool(lib().oracle_vnni_available())
+
+
 def conv_s8_nhwc_x86(x, w_s8, bias_f, scale, residual=None, sum_scale=1.0, out_dtype=DT_INT8,
-                     stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False, group=1):
-    """x: NHWC s8/u8, w_s8: KCRS int8 ([k][c/group][r][s]); returns NHWC out_dtype."""
+                     stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False, group=1, fast=False):
+    """x: NHWC s8/u8, w_s8: KCRS int8 ([k][c/group][r][s]); returns NHWC out_dtype.
+    fast=True: the AVX-512 VNNI implementation of the same arithmetic (oracle_vnni.c; bit-identical, used by the
+    CPU-baseline arm of bench.py) where the CPU has it and group == 1; channels are zero-padded to a multiple of 4."""
     x = np.ascontiguousarray(x)
     w_s8 = np.ascontiguousarray(w_s8, np.int8)
     n, h, wd, c = x.shape
     k, cw, r, s = w_s8.shape
     assert cw * group == c and k % group == 0
+    if fast and group == 1 and vnni_available():
+        if c % 4:
+            cp = (c + 3) // 4 * 4
+            xp = np.zeros((n, h, wd, cp), x.dtype); xp[..., :c] = x
+            wpad = np.zeros((k, cp, r, s), np.int8); wpad[:, :c] = w_s8
+            x, w_s8, c = xp, wpad, cp
+        oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
+        ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
+        out = np.zeros((n, oh, ow, k), _NP[out_dtype])
+        b = None if bias_f is None else np.ascontiguousarray(bias_f, np.float32)
+        sc = None if scale is None else np.ascontiguousarray(scale, np.float32)
+        res = None if residual is None else np.ascontiguousarray(residual)
+        rc = lib().oracle_conv_s8_nhwc_x86_vnni(_p(x), _dt(x), _p(w_s8), _p(b), _p(sc), _p(res),
+                                                _dt(res) if res is not None else -1, _f(sum_scale), _p(out),
+                                                out_dtype, n, c, h, wd, k, r, s, stride[0], stride[1], dil[0],
+                                                dil[1], pad[0], pad[1], int(relu))
+        if rc == 0:
+            return out
     oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
     ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
     out = np.zeros((n, oh, ow, k), _NP[out_dtype])

@@ -367,3 +367,26 @@ def test_grouped_x86_int8_conv_agrees_with_reference_oracle_on_shared_subset(ora
                                                oracle._f(1.0), oracle._p(out), oracle.DT_UINT8, 1, 16, 7, 7, 8, 1, 3, 3,
                                                1, 1, 1, 1, 0, 0, 1)
     np.testing.assert_array_equal(out, a)
+
+
+def test_vnni_int8_conv_is_bit_identical_to_the_scalar_restatement(oracle):
+    """oracle_vnni.c (the CPU-baseline arm's AVX-512 VNNI convolution) == oracle_conv_s8_nhwc_x86 on every dtype pair,
+    with / without residual, signed and unsigned inputs, channel counts that need padding, ragged tiles. Skipped where
+    the CPU has no AVX-512 VNNI (the fast path then falls back to the scalar code by itself)."""
+    if not oracle.vnni_available():
+        pytest.skip("no AVX-512 VNNI on this CPU")
+    rng = np.random.default_rng(31)
+    cases = [(2, 14, 256, 72, 3, 1, 1, True), (1, 9, 16, 40, 3, 2, 1, False), (2, 20, 64, 130, 1, 1, 0, True),
+             (1, 32, 3, 64, 7, 2, 3, False), (1, 7, 36, 17, 5, 1, 2, True)]
+    for n, h, c, k, r, st, pad, uns in cases:
+        x = (rng.integers(0, 256, (n, h, h, c)).astype(np.uint8) if uns else rng.integers(-128, 128, (n, h, h, c)).astype(np.int8))
+        w = rng.integers(-127, 128, (k, c, r, r)).astype(np.int8)
+        b = rng.uniform(-1000, 1000, k).astype(np.float32)
+        sc = rng.uniform(0.5, 1.5, k).astype(np.float32) * np.float32(1e-3)
+        oh = oracle.conv_out_size(h, pad, 1, r, st)
+        res = rng.integers(0, 256, (n, oh, oh, k)).astype(np.uint8)
+        for od in (oracle.DT_UINT8, oracle.DT_INT8, oracle.DT_FLOAT):
+            for rs in (None, res):
+                kw = dict(residual=rs, sum_scale=0.37, out_dtype=od, stride=(st, st), pad=(pad, pad), relu=od != oracle.DT_INT8)
+                np.testing.assert_array_equal(oracle.conv_s8_nhwc_x86(x, w, b, sc, fast=True, **kw),
+                                              oracle.conv_s8_nhwc_x86(x, w, b, sc, **kw), err_msg=str((n, h, c, k, r, od)))
