@@ -235,7 +235,7 @@ def calibrate(graph, images_nchw):
     return {k: (v / 127.0 if v > 0 else 1.0) for k, v in absmax.items()}
 
 
-def run_int8(graph, x_nchw, edge_scales, return_intermediate=False, fast=False):
+def run_int8(graph, x_nchw, edge_scales, return_intermediate=False, fast=False, weight_cache=None):
     """INT8 forward with x86 Saber semantics. edge_scales: {node_name: output scale}."""
     groups = plan(graph)
     int8_ops = {"Convolution", "BatchNorm", "Scale", "ReLU", "Pooling", "Eltwise", "Dense", "Split", "Input"}
@@ -279,24 +279,38 @@ def run_int8(graph, x_nchw, edge_scales, return_intermediate=False, fast=False):
             put(g, arr, dt, sc)
         elif g.kind in ("conv", "dense"):
             src, sdt, s_in = vals[g.inputs[0]]
+            # weight_cache (a dict the caller keeps between calls): BN/Scale fold and weight quantisation are init-time
+            # work in the reference (Net::init, trans_weights) -- the CPU-baseline arm times inference, not them
+            ckey = (g.head["name"], tuple(src.shape[1:]))
+            cached = weight_cache.get(ckey) if weight_cache is not None else None
             if g.kind == "conv":
-                w, bias = _folded_conv_weights(g)
+                w, bias = (None, cached[2]) if cached else _folded_conv_weights(g)
                 kw = _conv_kw(a)
                 kw["group"] = int(a["group"])
             else:
-                w = _attr_tensor(a["weight_1"]).reshape(int(a["out_dim"]), -1)
                 if src.ndim == 4 and src.shape[1] * src.shape[2] > 1:
-                    # NCHW-flatten order -> permute weight columns to NHWC order
                     n_, h_, w_, c_ = src.shape
-                    w = w.reshape(-1, c_, h_, w_).transpose(0, 2, 3, 1).reshape(w.shape[0], -1)
+                if not cached:
+                    w = _attr_tensor(a["weight_1"]).reshape(int(a["out_dim"]), -1)
+                    if src.ndim == 4 and src.shape[1] * src.shape[2] > 1:
+                        # NCHW-flatten order -> permute weight columns to NHWC order
+                        w = w.reshape(-1, c_, h_, w_).transpose(0, 2, 3, 1).reshape(w.shape[0], -1)
+                    w = w.reshape(w.shape[0], -1, 1, 1)
+                    bias = _attr_tensor(a["weight_2"]).reshape(-1) if a.get("bias_term") else np.zeros(w.shape[0], np.float32)
+                else:
+                    bias = cached[2]
+                if src.ndim == 4 and src.shape[1] * src.shape[2] > 1:
                     src = src.reshape(n_, 1, 1, -1)
-                w = w.reshape(w.shape[0], -1, 1, 1)
-                bias = _attr_tensor(a["weight_2"]).reshape(-1) if a.get("bias_term") else np.zeros(w.shape[0], np.float32)
                 kw = dict(stride=(1, 1), pad=(0, 0), dil=(1, 1))
             if sdt == DT_FLOAT:  # quantise the fp32 input with the input edge's scale
                 src = O.quant_fp32_s8(src, s_in)
                 sdt = DT_INT8
-            wq, w_scale = O.quant_weights_per_oc(w)
+            if cached:
+                wq, w_scale = cached[0], cached[1]
+            else:
+                wq, w_scale = O.quant_weights_per_oc(w)
+                if weight_cache is not None:
+                    weight_cache[ckey] = (wq, w_scale, bias)
             s_out = edge_scales[g.out_name]
             if consumers_int8(g):
                 out_dt = DT_UINT8 if g.relu else DT_INT8
