@@ -868,7 +868,9 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     // splitting pays only for long loops on grids that stay within one wave.
     // (k_iters >= 16 would also split the 1x1 2048 -> 512 layers of the 7x7 stage: 6.4 vs 7.2 us timed alone,
     // tools/layer_sweep.py, but 2.4 us SLOWER per step inside the net -- cluster launches overlap their neighbours less)
-    static const int split_min_iters = [] { const char* e = getenv("B200_SABER_SPLIT_MIN_ITERS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 24; }();
+    // Float kinds split from 16 iterations: their k loops move 2-4x the bytes per MAC (ResNet-50 FP32 b1 in-net: 0.547 vs 0.571 ms).
+    static const int split_min_env = [] { const char* e = getenv("B200_SABER_SPLIT_MIN_ITERS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }();
+    const int split_min_iters = split_min_env ? split_min_env : (d->math == B200_MATH_I8 ? 24 : 16);
     if (split_enabled && k_iters >= split_min_iters && ctas * 2 <= sms) {
         split = 2;
         if (k_iters >= 32 && ctas * 4 <= sms) split = 4;
