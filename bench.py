@@ -72,7 +72,8 @@ class ClockSampler:
         self.index = index
         self.period_ms = period_ms
         self.proc = None
-        self.lines = []
+        self.lines = []      # (host time, csv line)
+        self.window = None   # (t0, t1): only samples inside it are reported when set
 
     def start(self):
         try:
@@ -86,7 +87,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -98,7 +99,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if self.window is not None and not (self.window[0] <= ts <= self.window[1]):
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -314,16 +317,24 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-timed steps, inputs resident, L2 flushed between steps (outside the event pairs)
-    for _ in range(max(3, args.warmup)):
+    # (nvidia-smi needs a few hundred ms before its first line: start it before the warm-up so that it is already
+    # sampling, every 25 ms, when the timed region begins; only samples inside the load window are reported)
+    sampler = ClockSampler(local_rank, period_ms=25)
+    if rank == 0:
+        sampler.start()
+    t_w = time.perf_counter()
+    n_warm = 0
+    while n_warm < max(3, args.warmup) or (rank == 0 and sampler.proc and not sampler.lines and time.perf_counter() - t_w < 2.0):
         net.prediction()
+        n_warm += 1
+        if n_warm % 16 == 0:
+            net.sync()
     net.sync()
-    sampler = ClockSampler(local_rank)
     K = args.steps
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_region0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for i in range(K):
             if flush is not None:
@@ -332,8 +343,24 @@ def main():
             net.prediction()
             stops[i].record(stream)
     barrier()
+    t_region1 = time.perf_counter()
     per_step = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(per_step.sum())
+    clocks_window = "timed region"
+    if rank == 0 and sampler.proc and not any(t_region0 <= ts <= t_region1 for ts, _ in sampler.lines):
+        # the timed region was shorter than the sampling period: keep the very same load running (untimed) until a
+        # few samples have landed, and report those
+        clocks_window = "same load continued right after the timed region (region shorter than the 25 ms sampling period)"
+        t_c = time.perf_counter()
+        with torch.cuda.stream(stream):
+            while time.perf_counter() - t_c < 0.25:
+                for _ in range(8):
+                    if flush is not None:
+                        flush.zero_()
+                    net.prediction()
+                net.sync()
+        t_region1 = time.perf_counter()
+    sampler.window = (t_region0, t_region1)
 
     # ---- back-to-back (warm L2) replay, for context
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,6 +398,8 @@ def main():
     worker_ms = None
     T = args.worker_threads
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = clocks_window
     # the Worker leg is host-threaded: poll nvidia-smi slowly there (each query takes driver locks)
     sampler2 = ClockSampler(local_rank, period_ms=1000)
     if rank == 0 and T > 0 and not os.environ.get("BENCH_NO_SAMPLER_E2E"):
