@@ -43,8 +43,6 @@ struct ConvKParams {
     int32_t out_panels;  // epi_bn*out_es / out_pw
     int32_t res_es, res_pw, res_panels;  // same for the residual tile (0 panels = no residual)
     int32_t split;       // split-K factor = cluster size along z (1, 2 or 4)
-    int32_t a_rows;      // pixels one A load delivers: 128, or 64 when the whole layer has <= 64 output pixels (the zero-filled
-                         // rows of a 128-pixel im2col box still cost their shared-memory fill time, 38.7 B/clk per SM)
     const float* bias;
     const float* scale;
 };

@@ -147,7 +147,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (lane == 0) {
             // ===================== TMA producer =====================
             const uint32_t b_sub_bytes = BN * p.chunk;
-            const uint32_t tx_per_sub = p.a_rows * p.chunk + (X3 ? 2 : 1) * b_sub_bytes;
+            const uint32_t tx_per_sub = BLOCK_M * p.chunk + (X3 ? 2 : 1) * b_sub_bytes;
             // Weights do not depend on the previous kernel: the first trip round the ring gets its B tiles
             // (and the whole stage's expect_tx) before the grid-dependency wait, so their HBM / L2 latency
             // overlaps the previous kernel's tail. Only this thread reads the prior grid's output.
@@ -605,7 +605,7 @@ static int encode_map_a(b200_conv_plan* pl, const void* in) {
     int upper[2] = {d.pad_w - (d.s - 1) * d.dil_w, d.pad_h - (d.r - 1) * d.dil_h};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride_w), static_cast<cuuint32_t>(d.stride_h), 1};
     CUresult r = g_encode_im2col(&pl->map_a, tma_dtype(d.math), 4, const_cast<void*>(in), dims, strides, lower,
-                                 upper, static_cast<cuuint32_t>(g.chunk_el), static_cast<cuuint32_t>(pl->kp.a_rows), estr,
+                                 upper, static_cast<cuuint32_t>(g.chunk_el), BLOCK_M, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_width(g.chunk),
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -852,10 +852,6 @@ int b200_conv_plan_create(const b200_conv_desc_t* d, const void* packed_weights_
     kp.bias = bias_dev; kp.scale = scale_dev;
     kp.out_es = out_es;
     kp.res_es = res_es;
-    // a layer of <= 64 output pixels (the 7x7 stage at batch 1) loads 64-pixel A boxes: rows 64..127 of the operand tile
-    // keep whatever they held (they only feed accumulator rows that no store ever reads)
-    static const bool half_a = [] { const char* e = getenv("B200_SABER_HALF_A"); return !(e && e[0] == '0'); }();
-    kp.a_rows = (half_a && g.M_total <= 64) ? 64 : BLOCK_M;
 
     // ---- pipeline depth: as deep as the k loop needs, within the shared-memory budget. A grid that
     // exceeds one wave keeps two CTAs per SM resident (epilogue of one overlaps the main loop of the

@@ -291,7 +291,7 @@ bool persistent_plan_setup(b200_conv_plan* pl) {
     const b200_conv_desc_t& d = pl->desc;
     const char* env = getenv("B200_SABER_PERSISTENT");
     if (env && env[0] == '0') return false;
-    if (d.math == B200_MATH_TF32X3 || pl->kp.split != 1 || pl->kp.a_rows != BLOCK_M) return false;
+    if (d.math == B200_MATH_TF32X3 || pl->kp.split != 1) return false;
     const int sms = sm_count();
     const int tiles = static_cast<int>(pl->grid.x * pl->grid.y);
     const bool force = env && env[0] == '2';
