@@ -198,16 +198,26 @@ __device__ __forceinline__ void fc_body(const FcParams& p, uint8_t* smem_x, int 
                                 }
                             }
                     }
-                    for (; v < nv; v += 32) {
-                        uint4 wv[R];
+                    if (v < nv) {
+                        // the rest of the row (all of it for rows below U x 512 bytes -- MobileNet's fc7, the INT8 heads):
+                        // still every load in flight before the first use, each guarded; same per-lane order as above
+                        uint4 wv[R][U];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) wv[r] = ldg_stream(wrow[r] + v);
+                        for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int mi = 0; mi < FC_MT; ++mi) {
-                            if (mi < mt) {
-                                const uint4 xv = xs[mi * row_vecs + v];
+                            for (int u = 0; u < U; ++u)
+                                wv[r][u] = (v + 32 * u < nv) ? ldg_stream(wrow[r] + v + 32 * u) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                                for (int r = 0; r < R; ++r) fc_dot<MODE>(acc[mi][r], xv, wv[r], p.in_unsigned != 0);
+                        for (int u = 0; u < U; ++u) {
+                            if (v + 32 * u < nv) {
+#pragma unroll
+                                for (int mi = 0; mi < FC_MT; ++mi) {
+                                    if (mi < mt) {
+                                        const uint4 xv = xs[mi * row_vecs + v + 32 * u];
+#pragma unroll
+                                        for (int r = 0; r < R; ++r) fc_dot<MODE>(acc[mi][r], xv, wv[r][u], p.in_unsigned != 0);
+                                    }
+                                }
                             }
                         }
                     }
