@@ -233,12 +233,31 @@ def tiny_resnet(batch=1, seed=7, hw=32, num_classes=10):
     return g.finalize()
 
 
+def tiny_mobilenet(batch=1, seed=11, hw=32, num_classes=10):
+    """MobileNet-v1 in miniature: 3x3/s2 stem, four depthwise-separable pairs (stride 1 and 2, 32..256 channels), global
+    average pool, fc, softmax -- every op kind of MobileNet-v1 at a size the CPU oracle walks in milliseconds (the INT8
+    depthwise path of the net is checked on it)."""
+    g = GraphBuilder("TinyMobileNet", seed)
+    x = g.input("input_0", (batch, 3, hw, hw))
+    x = g.conv_bn_scale("conv1", x, 3, 32, 3, 2, 1, relu=True)
+    cfg = [(32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 2)]
+    for i, (cin, cout, s) in enumerate(cfg):
+        x = g.conv_bn_scale("conv%d_dw" % (i + 2), x, cin, cin, 3, s, 1, relu=True, group=cin)
+        x = g.conv_bn_scale("conv%d_sep" % (i + 2), x, cin, cout, 1, 1, 0, relu=True)
+    x = g.pool("pool6", x, hw // 8, 1, 0, "AVG", global_pooling=True)
+    x = g.dense("fc7", x, 256, num_classes, gain=3.0)
+    x = g.softmax("prob", x)
+    g.output("prob_out", x)
+    return g.finalize()
+
+
 BUILDERS = {
     "resnet50": lambda batch=1, seed=1234: resnet(50, batch, seed),
     "resnet101": lambda batch=1, seed=1234: resnet(101, batch, seed),
     "vgg16": vgg16,
     "mobilenet_v1": mobilenet_v1,
     "tiny_resnet": lambda batch=1, seed=7: tiny_resnet(batch, seed),
+    "tiny_mobilenet": lambda batch=1, seed=11: tiny_mobilenet(batch, seed),
 }
 
 
@@ -291,7 +310,8 @@ def load_calibration(model_name):
         return json.load(f)["edge_scales"]
 
 
-HEAD_DENSE = {"tiny_resnet": "fc", "resnet50": "fc1000", "resnet101": "fc1000", "vgg16": "fc8", "mobilenet_v1": "fc7"}
+HEAD_DENSE = {"tiny_resnet": "fc", "resnet50": "fc1000", "resnet101": "fc1000", "vgg16": "fc8", "mobilenet_v1": "fc7",
+              "tiny_mobilenet": "fc7"}
 
 
 def center_head(graph, model_name):

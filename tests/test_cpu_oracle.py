@@ -265,13 +265,13 @@ def test_quantisation_rules(oracle):
     np.testing.assert_array_equal(q, np.array([[127, -126, 63, 0]], np.int8))
 
 
-@pytest.mark.parametrize("model", ["tiny_resnet", "resnet50"])
+@pytest.mark.parametrize("model", ["tiny_resnet", "tiny_mobilenet", "resnet50", "mobilenet_v1"])
 def test_model_walker_reproduces_golden(model, oracle):
     """The committed golden outputs are what the oracle produces today (guards oracle drift)."""
     from anakin_b200 import modelzoo
     from oracle import model_walker as W
     gold = np.load(os.path.join(GOLD, "%s_golden.npz" % model))
-    hw = 32 if model == "tiny_resnet" else 224
+    hw = 32 if model.startswith("tiny") else 224
     n = 2
     g = modelzoo.build(model, batch=1)
     x = modelzoo.synthetic_input(n, hw)

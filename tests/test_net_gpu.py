@@ -93,11 +93,14 @@ def test_tiny_resnet_fp32(batch, oracle):
 
 
 @pytest.mark.parametrize("batch", [1, 4])
-def test_tiny_resnet_int8_bit_exact(batch, oracle):
+@pytest.mark.parametrize("model", ["tiny_resnet", "tiny_mobilenet"])
+def test_tiny_nets_int8_bit_exact(model, batch, oracle):
+    """Every int8 edge of the net against the x86-semantics oracle. tiny_mobilenet: the INT8 depthwise kernel
+    (SaberDepthWiseConv's INT8 arm) and the stem kernel without a pooling, in-net."""
     from anakin_b200 import modelzoo
     from oracle import model_walker as W
-    g, G = _build("tiny_resnet", batch, "int8")
-    scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration("tiny_resnet").items()}
+    g, G = _build(model, batch, "int8")
+    scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration(model).items()}
     x = modelzoo.synthetic_input(batch, 32)
     want, trace = W.run_int8(g, x, scales, return_intermediate=True)
     net = _run(G, "int8", x)
@@ -252,6 +255,44 @@ def test_resnet101_int8_golden():
     assert (got.argmax(1) == gold["top1_int8"][:4]).all()
     logits, info = net.read_tensor("fc1000")
     np.testing.assert_array_equal(_valid(logits, info).reshape(4, -1), gold["logits_int8"][:4])
+
+
+def test_mobilenet_v1_int8_golden(oracle):
+    """MobileNet-v1 in INT8 at the batch size C5 names: 13 INT8 depthwise layers + 13 1x1 layers + the 3x3/s2 stem; logits
+    and top-1 against the committed oracle outputs, two depthwise edges against a fresh oracle run."""
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    gold = np.load(os.path.join(GOLD, "mobilenet_v1_golden.npz"))
+    batch = 16
+    g, G = _build("mobilenet_v1", batch, "int8")
+    x = modelzoo.synthetic_input(batch)
+    net = _run(G, "int8", x)
+    got = net.get_output()
+    np.testing.assert_array_equal(_logits(net, "fc7", batch), gold["logits_int8"])
+    assert (got.argmax(1) == gold["top1_int8"]).all() and len(set(gold["top1_int8"].tolist())) >= 3
+    scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration("mobilenet_v1").items()}
+    g2 = modelzoo.build("mobilenet_v1", batch=2, precision="int8")
+    _, trace = W.run_int8(g2, x[:2], scales, return_intermediate=True)
+    for node in ("conv1", "conv2_dw", "conv3_dw", "conv7_sep", "conv14_dw", "conv14_sep"):
+        arr, info = net.read_tensor(node)
+        want_t = trace[node][0]
+        np.testing.assert_array_equal(_valid(arr, info)[:2].reshape(want_t.shape), want_t, err_msg=node)
+
+
+def test_tiny_mobilenet_fp32_and_fp16(oracle):
+    from anakin_b200 import modelzoo
+    gold = np.load(os.path.join(GOLD, "tiny_mobilenet_golden.npz"))
+    nb = gold["top1_fp32"].shape[0]
+    x = modelzoo.synthetic_input(nb, 32)
+    g, G = _build("tiny_mobilenet", nb, "fp32")
+    net = _run(G, "fp32", x)
+    _check_fp32_logits(oracle, gold["logits_fp32"], _logits(net, "fc7", nb), "tiny_mobilenet fp32", gold["logit_offset"])
+    assert (net.get_output().argmax(1) == gold["top1_fp32"]).all()
+    g, G = _build("tiny_mobilenet", nb, "fp16")
+    net16 = _run(G, "fp16", x)
+    l16, l32 = _logits(net16, "fc7", nb).astype(np.float32), gold["logits_fp32"]
+    bound = 4.0 * np.sqrt(10.0) * 2.0 ** -11 * float(np.abs(l32 + gold["logit_offset"]).max())   # 10 fp16 edges in series
+    assert np.abs(l16 - l32).max() <= bound, (float(np.abs(l16 - l32).max()), bound)
 
 
 def test_vgg16_fp32_golden():

@@ -8,7 +8,7 @@ build container; the GPU box only reads the results):
   <model>_golden.npz   oracle outputs for the bench / parity inputs (seed 42+i): fp32 logits
                        + probabilities, int8 logits + probabilities, top-1 indices
 
-  python tools/make_golden.py [tiny_resnet resnet50 resnet101 vgg16 mobilenet_v1]
+  python tools/make_golden.py [tiny_resnet tiny_mobilenet resnet50 resnet101 vgg16 mobilenet_v1]
 """
 import json
 import os
@@ -23,12 +23,12 @@ from anakin_b200 import modelzoo as Z  # noqa: E402
 from oracle import model_walker as W  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
-HW = {"tiny_resnet": 32}
+HW = {"tiny_resnet": 32, "tiny_mobilenet": 32}
 LOGITS = Z.HEAD_DENSE
-INT8_MODELS = {"tiny_resnet", "resnet50", "resnet101"}
+INT8_MODELS = {"tiny_resnet", "tiny_mobilenet", "resnet50", "resnet101", "mobilenet_v1"}
 # golden images per model: the batch sizes BASELINE.json's configs name are all covered (C2 b8, C3 b4, C4 b32 -> 4 per
 # GPU, C5 b16), ResNet-50 holds 32
-IMAGES = {"tiny_resnet": 8, "resnet50": 32, "resnet101": 8, "vgg16": 4, "mobilenet_v1": 16}
+IMAGES = {"tiny_resnet": 8, "tiny_mobilenet": 8, "resnet50": 32, "resnet101": 8, "vgg16": 4, "mobilenet_v1": 16}
 
 
 def _dense_input(vals, g, name):
@@ -82,4 +82,4 @@ def main(models):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or ["tiny_resnet", "resnet50", "resnet101", "vgg16", "mobilenet_v1"])
+    main(sys.argv[1:] or ["tiny_resnet", "tiny_mobilenet", "resnet50", "resnet101", "vgg16", "mobilenet_v1"])
