@@ -994,6 +994,176 @@ dwconv_row_kernel(const uint4* __restrict__ in, const uint4* __restrict__ wgt, c
     }
 }
 
+// Shared-memory tiled 3x3 / stride-1 / dilation-1 depthwise conv (the big MobileNet layers). dwconv_row_kernel re-reads
+// every input vector ~4.5 times from L1/L2 (3 filter rows x 1.5 for the column overlap of neighbouring threads), which is
+// what bounds it at a third of the HBM rate; here a block stages the (8 + 2) x (TW + 2) pixel halo tile of CVB channel
+// vectors once (cp.async, zero-filled outside the image) and every tap comes from shared memory: 1.4x halo re-read.
+// Thread = (channel vector, 4 adjacent outputs of one row), 256 threads = 8 rows x (32 / CVB) groups x CVB vectors, so a
+// tile is 8 x (128 / CVB) output pixels. The row pitch is congruent to CVB * 16 modulo 128 and 8 / CVB rows interleave
+// inside a quarter warp, which makes every 16-byte shared load conflict-free. Arithmetic and tap order (r, s) are those of
+// dwconv_vec_kernel (a padding tap adds an exact zero): results are bit-identical for INT8, equal for the float kinds.
+// One tile per block, three blocks per SM (two for INT8). Measured and dropped: a two-buffer walk over the
+// tiles (next tile streaming in under the arithmetic) and a 2 x 2-pixel patch per thread with packed fp32x2 FMAs.
+template <int MODE, int CVB>
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
+dwconv_tile_kernel(const uint4* __restrict__ in, const uint4* __restrict__ wgt, const float* __restrict__ bias,
+                   const float* __restrict__ scale, uint4* __restrict__ out, int h, int w, int cv, int oh, int ow,
+                   int ph, int pw, int relu, float slope, int in_unsigned, int out_dtype, int tiles_x, int tiles_y, int cblocks) {
+    constexpr int NCH = MODE == 0 ? 4 : (MODE == 1 ? 8 : 16);
+    constexpr int TH = 8, XP = 4, XG = 32 / CVB, TW = XG * XP, IH = TH + 2, IW = TW + 2, YSUB = 8 / CVB;
+    constexpr int RAW = IW * CVB * 16;
+    constexpr int PITCH = RAW + ((CVB * 16 - RAW % 128) + 128) % 128;
+    static_assert(PITCH % 128 == (CVB * 16) % 128 && PITCH % 16 == 0, "row pitch");
+    __shared__ __align__(128) uint8_t tile[IH * PITCH];
+    pdl_enter();
+    const int tid = threadIdx.x;
+    // tile index -> (image, tile row, tile column, channel block); channel blocks vary fastest
+    auto decode = [&](int ti, int& b, int& ty, int& tx, int& cb) {
+        unsigned t = static_cast<unsigned>(ti);
+        cb = static_cast<int>(t % static_cast<unsigned>(cblocks)); t /= static_cast<unsigned>(cblocks);
+        tx = static_cast<int>(t % static_cast<unsigned>(tiles_x)); t /= static_cast<unsigned>(tiles_x);
+        ty = static_cast<int>(t % static_cast<unsigned>(tiles_y));
+        b = static_cast<int>(t / static_cast<unsigned>(tiles_y));
+    };
+    // stage the halo tile of tile `ti` (one cp.async group)
+    auto stage = [&](int ti) {
+        int b, ty, tx, cb;
+        decode(ti, b, ty, tx, cb);
+        const int iy0 = ty * TH - ph, ix0 = tx * TW - pw;
+        const uint4* img = in + 1ll * b * h * w * cv + cb * CVB;
+        const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+        for (int i = tid; i < IH * IW * CVB; i += 256) {
+            const int v = i % CVB, col = (i / CVB) % IW, row = i / (CVB * IW);
+            const int iy = iy0 + row, ix = ix0 + col;
+            const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+            const uint4* src = ok ? img + (1ll * iy * w + ix) * cv + v : img;
+            const uint32_t dst = tile_s + row * PITCH + (col * CVB + v) * 16;
+            const int bytes = ok ? 16 : 0;      // src-size 0: the 16 bytes are zero-filled, nothing is read
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int v = tid & (CVB - 1);
+    const int ysub = (tid / CVB) & (YSUB - 1);
+    const int xg = (tid >> 3) & (XG - 1);
+    const int y = (tid >> 3) / XG * YSUB + ysub;
+    const int ti = blockIdx.x;
+    stage(ti);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    {
+        int b, ty, tx, cb;
+        decode(ti, b, ty, tx, cb);
+        const uint8_t* cur = tile;
+        const int oy = ty * TH + y, ox0 = tx * TW + xg * XP;
+        if (oy < oh && ox0 < ow) {
+            const int vg = cb * CVB + v;
+            float facc[XP][MODE == 2 ? 1 : NCH];
+            int iacc[XP][MODE == 2 ? NCH : 1];
+#pragma unroll
+            for (int p = 0; p < XP; ++p) {
+#pragma unroll
+                for (int i = 0; i < (MODE == 2 ? 1 : NCH); ++i) facc[p][i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < (MODE == 2 ? NCH : 1); ++i) iacc[p][i] = 0;
+            }
+#pragma unroll
+            for (int kr = 0; kr < 3; ++kr) {
+                uint4 wv[3];
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) wv[ks] = __ldg(wgt + (kr * 3 + ks) * cv + vg);
+                const uint8_t* rowp = cur + (y + kr) * PITCH + (xg * XP * CVB + v) * 16;
+                uint4 xv[XP + 2];
+#pragma unroll
+                for (int col = 0; col < XP + 2; ++col) xv[col] = *reinterpret_cast<const uint4*>(rowp + col * CVB * 16);
+#pragma unroll
+                for (int p = 0; p < XP; ++p) {
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint4 xq = xv[p + ks], wq = wv[ks];
+                        const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w}, ww[4] = {wq.x, wq.y, wq.z, wq.w};
+                        if constexpr (MODE == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) facc[p][i] = __fmaf_rn(__uint_as_float(xw[i]), __uint_as_float(ww[i]), facc[p][i]);
+                        } else if constexpr (MODE == 1) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&xw[i]));
+                                const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
+                                facc[p][2 * i] = __fmaf_rn(a.x, c2.x, facc[p][2 * i]);
+                                facc[p][2 * i + 1] = __fmaf_rn(a.y, c2.y, facc[p][2 * i + 1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint32_t wm = ww[i] & (0xFFu << (8 * j));
+                                    int& a = iacc[p][4 * i + j];
+                                    if (in_unsigned) asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(a) : "r"(xw[i]), "r"(wm));
+                                    else asm("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(a) : "r"(xw[i]), "r"(wm));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- epilogue (that of dwconv_vec_kernel), bias / scale as 16-byte loads
+            const int c0 = vg * NCH;
+            float bv[NCH], sv[MODE == 2 ? NCH : 1];
+#pragma unroll
+            for (int i = 0; i < NCH / 4; ++i) {
+                const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+                if constexpr (MODE == 2) {
+                    const float4 s4 = scale ? __ldg(reinterpret_cast<const float4*>(scale + c0) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    sv[4 * i] = s4.x; sv[4 * i + 1] = s4.y; sv[4 * i + 2] = s4.z; sv[4 * i + 3] = s4.w;
+                }
+            }
+            uint4* orow = out + ((1ll * b * oh + oy) * ow + ox0) * cv + vg;
+#pragma unroll
+            for (int p = 0; p < XP; ++p) {
+                if (ox0 + p >= ow) break;
+                uint32_t q[4];
+                if constexpr (MODE == 2) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t wd = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f = __fmul_rn(__fadd_rn(__int2float_rn(iacc[p][4 * i + j]), bv[4 * i + j]), sv[4 * i + j]);
+                            if (relu) f = fmaxf(f, 0.f);
+                            uint32_t code;
+                            if (out_dtype == B200_UINT8) asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(code) : "f"(f));
+                            else asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(code) : "f"(f));
+                            wd |= (code & 0xffu) << (8 * j);
+                        }
+                        q[i] = wd;
+                    }
+                } else {
+                    float yv[NCH];
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) {
+                        yv[i] = facc[p][i] + bv[i];
+                        if (relu) yv[i] = yv[i] > 0.f ? yv[i] : yv[i] * slope;
+                    }
+                    if constexpr (MODE == 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) q[i] = __float_as_uint(yv[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const __half2 hh = __halves2half2(static_cast<__half>(yv[2 * i]), static_cast<__half>(yv[2 * i + 1]));
+                            q[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                        }
+                    }
+                }
+                orow[1ll * p * cv] = make_uint4(q[0], q[1], q[2], q[3]);
+            }
+        }
+    }
+}
+
 static unsigned grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148ll * 16;
@@ -1274,6 +1444,37 @@ int b200_dwconv_run(const b200_conv_desc_t* d, const void* in, const void* weigh
     else return B200_UNIMPL_ERROR;
     if (d->c % nch) return B200_INVALID_VALUE;
     const int cv = d->c / nch;
+    // big 3x3 / stride-1 layers: the shared-memory tiled kernel. B200_SABER_DW_TILE: 0 never, 2 whenever the shape fits
+    // (default: feature maps of at least 28 x 28, below that the tile would be mostly halo and idle lanes)
+    static const int tile_mode = [] { const char* e = getenv("B200_SABER_DW_TILE"); return e ? atoi(e) : 1; }();
+    const int cvb = cv % 8 == 0 ? 8 : (cv == 4 ? 4 : (cv == 2 ? 2 : 0));
+    if (tile_mode > 0 && cvb && d->r == 3 && d->s == 3 && d->stride_h == 1 && d->stride_w == 1 && d->dil_h == 1 && d->dil_w == 1 &&
+        d->pad_h <= 1 && d->pad_w <= 1) {
+        const int tw = 128 / cvb;
+        const int tiles_x = (ow + tw - 1) / tw, tiles_y = (oh + 7) / 8, cblocks = cv / cvb;
+        const double util = static_cast<double>(oh) * ow / (static_cast<double>(tiles_y) * 8 * tiles_x * tw);
+        const long long blocks = 1ll * d->n * tiles_y * tiles_x * cblocks;
+        // INT8 (its row kernel keeps only 2 outputs per thread): from 7 x 7 up (MobileNet-v1 INT8 b16 in-net 12.97 -> 7.32 us
+        // per 14 x 14 layer); float kinds: from 28 x 28 (at 14 x 14 the row kernel is 0.4 us faster per layer)
+        const bool take = tile_mode >= 2 ? util >= 0.5 : (mode == 2 ? util >= 0.35 : (util >= 0.6 && oh * ow >= 28 * 28));
+        if (blocks < (1ll << 31) && take) {
+            const unsigned g = static_cast<unsigned>(blocks);
+#define B200_DWT_ARGS in4, w4, bias, scale, out4, d->h, d->w, cv, oh, ow, d->pad_h, d->pad_w, d->relu, d->neg_slope, \
+                      d->in_dtype == B200_UINT8 ? 1 : 0, d->out_dtype, tiles_x, tiles_y, cblocks
+#define B200_DWT_LAUNCH(M)                                                                              \
+            do {                                                                                        \
+                if (cvb == 8) launch_pdl(dwconv_tile_kernel<M, 8>, g, block, S(stream), B200_DWT_ARGS); \
+                else if (cvb == 4) launch_pdl(dwconv_tile_kernel<M, 4>, g, block, S(stream), B200_DWT_ARGS); \
+                else launch_pdl(dwconv_tile_kernel<M, 2>, g, block, S(stream), B200_DWT_ARGS);          \
+            } while (0)
+            if (mode == 0) B200_DWT_LAUNCH(0);
+            else if (mode == 1) B200_DWT_LAUNCH(1);
+            else B200_DWT_LAUNCH(2);
+#undef B200_DWT_LAUNCH
+#undef B200_DWT_ARGS
+            return check_launch("dwconv");
+        }
+    }
     if (d->s == 3 && d->dil_w == 1 && (d->stride_w == 1 || d->stride_w == 2)) {
         // 3-wide filters: several adjacent outputs per thread (dwconv_row_kernel)
         const int xp = mode == 2 ? 2 : 4;

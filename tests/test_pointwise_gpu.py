@@ -300,6 +300,70 @@ def test_dwconv_int8_bit_exact(stride, variant, oracle):
     np.testing.assert_array_equal(out.cpu().numpy(), want)
 
 
+# shapes that take the shared-memory tiled kernel (3x3 / stride 1, >= 28 x 28 outputs for the float kinds): 8, 4 and 2 channel vectors per
+# block, several channel blocks, ragged tiles in both directions, with and without padding
+DW_TILE_CASES = [  # (n, h, w, vectors of 16 B per pixel, pad)
+    (2, 30, 37, 8, 1), (1, 29, 70, 4, 1), (1, 40, 120, 2, 1), (1, 56, 56, 16, 1), (2, 34, 45, 8, 0), (1, 31, 66, 4, 0),
+    # more tiles than co-resident blocks (3 x 148): several waves of blocks
+    (112, 28, 28, 8, 1), (112, 28, 60, 4, 1),
+]
+
+
+@pytest.mark.parametrize("case", DW_TILE_CASES)
+@pytest.mark.parametrize("kind", ["f32", "f16", "u8_relu_u8", "s8_s8"])
+def test_dwconv_tiled(case, kind, oracle):
+    import torch
+    from anakin_b200 import saber_abi as A
+    from gpu_util import dev, ptr, stream_ptr
+    n, h, w, cv, pad = case
+    rng = np.random.default_rng(abs(hash((case, kind))) % (2 ** 31))
+    d = A.ConvDesc()
+    d.res_dtype = -1
+    d.r = d.s = 3
+    d.pad_h = d.pad_w = pad
+    d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
+    sd = None
+    if kind in ("f32", "f16"):
+        np_t, es = (np.float32, 4) if kind == "f32" else (np.float16, 2)
+        c = cv * 16 // es
+        x = rng.uniform(-1, 1, (n, h, w, c)).astype(np_t)
+        wt = rng.uniform(-1, 1, (c, 1, 3, 3)).astype(np_t)
+        b = rng.uniform(-1, 1, c).astype(np.float32)
+        want = oracle.conv_f32_nhwc(x.astype(np.float32), wt.astype(np.float32), b, group=c, pad=(pad, pad), relu=True, neg_slope=0.1)
+        d.math, d.in_dtype, d.out_dtype = (A.MATH_TF32, A.FLOAT, A.FLOAT) if kind == "f32" else (A.MATH_F16, A.HALF, A.HALF)
+        d.relu, d.neg_slope = 1, 0.1
+        tdt = torch.float32 if kind == "f32" else torch.float16
+    else:
+        c = cv * 16
+        in_u = kind.startswith("u8")
+        x = rng.integers(0, 256, (n, h, w, c)).astype(np.uint8) if in_u else rng.integers(-128, 128, (n, h, w, c)).astype(np.int8)
+        wt = rng.integers(-127, 128, (c, 1, 3, 3)).astype(np.int8)
+        b = rng.uniform(-3000, 3000, c).astype(np.float32)
+        scale = rng.uniform(0.5, 1.5, c).astype(np.float32) * np.float32(1.0 / 900.0)
+        relu = kind.endswith("relu_u8")
+        out_dtype = A.UINT8 if relu else A.INT8
+        want = oracle.conv_s8_nhwc_x86(x, wt, b, scale, out_dtype=out_dtype, pad=(pad, pad), relu=relu, group=c)
+        d.math, d.in_dtype, d.out_dtype = A.MATH_I8, (A.UINT8 if in_u else A.INT8), out_dtype
+        d.relu = int(relu)
+        sd = dev(scale)
+        tdt = torch.uint8 if relu else torch.int8
+    d.n, d.h, d.w, d.c, d.k, d.ldc = n, h, w, c, c, c
+    wrsc = np.ascontiguousarray(np.transpose(wt[:, 0], (1, 2, 0)))
+    xd, wd, bd = dev(x), dev(wrsc), dev(b)
+    out = torch.zeros(want.shape, dtype=tdt, device="cuda")
+    A.check(A.load().b200_dwconv_run(C.byref(d), ptr(xd), ptr(wd), ptr(bd), ptr(sd), ptr(out), stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    if kind == "f32":
+        mr, md = oracle.tensor_cmp(want, got)
+        assert md < 1e-3 or mr <= 1e-3
+        assert np.abs(got - want).max() <= 1e-5        # 9 fp32 FMAs against the oracle's fp32 sum
+    elif kind == "f16":
+        np.testing.assert_array_equal(got, want.astype(np.float16))   # fp32 accumulation, one rounding at the store
+    else:
+        np.testing.assert_array_equal(got, want)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Weight-streaming inner product (fc_stream.cu) and the fused classifier head (pool + fc + softmax, one launch)
 FC_CASES = [(8, 2048, 1000), (4, 25088, 512), (1, 512, 10), (13, 4096, 200), (16, 1024, 64)]   # (m, k, n)
