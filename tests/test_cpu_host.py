@@ -78,6 +78,28 @@ def test_product_never_imports_the_oracle():
     assert not bad, bad
 
 
+def test_mobilenet_graph_fuses_depthwise_pairs_and_keeps_int8_marks():
+    """Graph::Optimize on the depthwise-separable nets: every Convolution (grouped ones included) absorbs its BatchNorm /
+    Scale / ReLU; the global AVG pooling stays a node of its own in INT8 (only MAX pooling folds into an INT8 conv)."""
+    from anakin_b200 import anakin_bin, api, modelzoo
+    for model, convs in (("tiny_mobilenet", 9), ("mobilenet_v1", 27)):
+        g = modelzoo.build(model, batch=2, precision="int8")
+        G = api.Graph.from_bytes(anakin_bin.dumps(g))
+        G.Optimize()
+        ops = [op for _, op, _, _ in G.describe()]
+        assert ops.count("ConvBatchnormScaleRelu") == convs, ops
+        assert ops.count("Pooling") == 1 and ops.count("Dense") == 1 and ops.count("Softmax") == 1
+        assert not any(o in ("BatchNorm", "Scale", "ReLU") for o in ops)
+        # the depthwise nodes keep group == channels through the fusion (the ConvEngine keys its depthwise path on it)
+        dw = [n for n in g["nodes"] if n["op"] == "Convolution" and n["attrs"]["group"] > 1]
+        assert len(dw) == (convs - 1) // 2 and all(n["attrs"]["group"] == n["attrs"]["filter_num"] for n in dw)
+    # the calibration tables cover every node of the graphs they are applied to
+    for model in ("tiny_mobilenet", "mobilenet_v1"):
+        cal = modelzoo.load_calibration(model)
+        g = modelzoo.build(model, batch=1)
+        assert all(n["name"] in cal for n in g["nodes"] if n["op"] not in ("Output",)), model
+
+
 def test_anakin_bin_python_roundtrip():
     from anakin_b200 import anakin_bin, modelzoo
     g = modelzoo.tiny_resnet(2)

@@ -69,7 +69,7 @@ def test_descriptor_fixture_matches_the_reference_protos():
         assert build_descriptor_set().SerializeToString(deterministic=True) == f.read()
 
 
-@pytest.mark.parametrize("model,precision", [("tiny_resnet", "int8"), ("tiny_resnet", "fp32")])
+@pytest.mark.parametrize("model,precision", [("tiny_resnet", "int8"), ("tiny_resnet", "fp32"), ("tiny_mobilenet", "int8")])
 def test_writers_are_byte_identical_to_protobuf(pb, model, precision):
     from anakin_b200 import anakin_bin, modelzoo
     g = modelzoo.build(model, batch=2, precision=precision)
