@@ -131,7 +131,8 @@ def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, 
     if precision == "int8":
         scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration(model).items()}
     per_img = max(0.05, GOP_PER_IMAGE.get(model, 1.0) / (150.0 if (precision == "int8" and O.vnni_available()) else 25.0))  # expected GOP/s on 8 cores
-    if steps is None:
+    auto_steps = steps is None
+    if auto_steps:
         n_img = max(1, min(batch, int(budget_s / per_img / 3)))
         steps, warmup = 3, 0
     else:
@@ -146,6 +147,11 @@ def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, 
         run()      # fills the cache: BN fold + weight quantisation are init-time work (Net::init), not timed
     for _ in range(warmup):
         run()
+    if auto_steps and precision == "int8":
+        # one warm step sizes the sample: about a quarter of the budget, between 3 and 200 steps
+        t0 = time.perf_counter()
+        run()
+        steps = int(min(200, max(3, budget_s / 4.0 / max(time.perf_counter() - t0, 1e-4))))
     t0 = time.perf_counter()
     for _ in range(steps):
         run()
@@ -153,7 +159,7 @@ def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, 
     return {"value": n_img * steps / dt, "unit": "images/s", "cores": O.num_threads(), "kind": "port",
             "sample": "%d step(s) x %d image(s) of %s %s via oracle/model_walker.py (x86-semantics restatement, %s"
                       "OpenMP, not Anakin's MKL/xbyak build)" % (steps, n_img, model, precision,
-                                                                  "AVX-512 VNNI convolutions, " if vnni else ""),
+                                                                  "AVX-512 VNNI convolutions on weights packed once, AVX-512 pooling, " if vnni else ""),
             "ms_per_step": dt / steps * 1e3, "images_per_step": n_img}
 
 

@@ -337,7 +337,7 @@ def run_int8(graph, x_nchw, edge_scales, return_intermediate=False, fast=False, 
             if sdt == DT_FLOAT:
                 put(g, O.pool_f32(src, *args, nhwc=True, **kwp), DT_FLOAT, s_in)
             else:
-                put(g, O.pool_s8_nhwc(src, *args, **kwp), sdt, s_in)  # scale passes through
+                put(g, O.pool_s8_nhwc(src, *args, fast=fast, **kwp), sdt, s_in)  # scale passes through
         elif g.kind == "eltwise":
             (x0, d0, s0), (x1, d1, s1) = vals[g.inputs[0]], vals[g.inputs[1]]
             s_out = edge_scales[g.out_name]

@@ -141,32 +141,62 @@ def vnni_available():
     return bool(lib().oracle_vnni_available())
 
 
+_VNNI_PACKS = {}   # id(weight array) -> (the array itself: keeps the id alive, pack handle, padded channel count)
+
+
+def _vnni_pack(w_s8):
+    """The VNNI weight pack of a KCRS int8 array, made once per array (init-time work like the reference's trans_weights;
+    the baseline arm keeps its quantised weights in a cache, so every layer is packed once)."""
+    ent = _VNNI_PACKS.get(id(w_s8))
+    if ent is not None and ent[0] is w_s8:
+        return ent[1], ent[2]
+    if len(_VNNI_PACKS) >= 512:      # callers that pass a fresh array every time (tests) must not grow this without bound
+        vnni_release()
+    k, c, r, s = w_s8.shape
+    cp = (c + 3) // 4 * 4
+    src = w_s8
+    if cp != c:
+        src = np.zeros((k, cp, r, s), np.int8); src[:, :c] = w_s8
+    lib().oracle_vnni_pack.restype = C.c_void_p
+    handle = C.c_void_p(lib().oracle_vnni_pack(_p(src), k, cp, r, s))
+    assert handle.value, "oracle_vnni_pack failed"
+    _VNNI_PACKS[id(w_s8)] = (w_s8, handle, cp)
+    return handle, cp
+
+
+def vnni_release():
+    """Free every cached weight pack."""
+    for _, handle, _ in _VNNI_PACKS.values():
+        lib().oracle_vnni_free(handle)
+    _VNNI_PACKS.clear()
+
+
 def conv_s8_nhwc_x86(x, w_s8, bias_f, scale, residual=None, sum_scale=1.0, out_dtype=DT_INT8,
                      stride=(1, 1), dil=(1, 1), pad=(0, 0), relu=False, group=1, fast=False):
     """x: NHWC s8/u8, w_s8: KCRS int8 ([k][c/group][r][s]); returns NHWC out_dtype.
     fast=True: the AVX-512 VNNI implementation of the same arithmetic (oracle_vnni.c; bit-identical, used by the
-    CPU-baseline arm of bench.py) where the CPU has it and group == 1; channels are zero-padded to a multiple of 4."""
+    CPU-baseline arm of bench.py) where the CPU has it and group == 1; channels are zero-padded to a multiple of 4. The
+    weight pack is cached per weight ARRAY (pass the same object again to reuse it)."""
     x = np.ascontiguousarray(x)
     w_s8 = np.ascontiguousarray(w_s8, np.int8)
     n, h, wd, c = x.shape
     k, cw, r, s = w_s8.shape
     assert cw * group == c and k % group == 0
     if fast and group == 1 and vnni_available():
-        if c % 4:
-            cp = (c + 3) // 4 * 4
+        handle, cp = _vnni_pack(w_s8)
+        if cp != c:
             xp = np.zeros((n, h, wd, cp), x.dtype); xp[..., :c] = x
-            wpad = np.zeros((k, cp, r, s), np.int8); wpad[:, :c] = w_s8
-            x, w_s8, c = xp, wpad, cp
+            x, c = xp, cp
         oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
         ow = conv_out_size(wd, pad[1], dil[1], s, stride[1])
-        out = np.zeros((n, oh, ow, k), _NP[out_dtype])
+        out = np.empty((n, oh, ow, k), _NP[out_dtype])
         b = None if bias_f is None else np.ascontiguousarray(bias_f, np.float32)
         sc = None if scale is None else np.ascontiguousarray(scale, np.float32)
         res = None if residual is None else np.ascontiguousarray(residual)
-        rc = lib().oracle_conv_s8_nhwc_x86_vnni(_p(x), _dt(x), _p(w_s8), _p(b), _p(sc), _p(res),
-                                                _dt(res) if res is not None else -1, _f(sum_scale), _p(out),
-                                                out_dtype, n, c, h, wd, k, r, s, stride[0], stride[1], dil[0],
-                                                dil[1], pad[0], pad[1], int(relu))
+        rc = lib().oracle_conv_s8_nhwc_x86_vnni_packed(handle, _p(x), _dt(x), _p(b), _p(sc), _p(res),
+                                                       _dt(res) if res is not None else -1, _f(sum_scale), _p(out),
+                                                       out_dtype, n, c, h, wd, k, r, s, stride[0], stride[1], dil[0],
+                                                       dil[1], pad[0], pad[1], int(relu))
         if rc == 0:
             return out
     oh = conv_out_size(h, pad[0], dil[0], r, stride[0])
@@ -382,7 +412,8 @@ def pool_f32(x, window, pad, stride, ptype, nhwc=False, global_pooling=False, fl
 
 
 def pool_s8_nhwc(x, window, pad, stride, ptype, global_pooling=False, floor_as_conv=False,
-                 use_ref=False):
+                 use_ref=False, fast=False):
+    """fast=True: the AVX-512 implementation of the same arithmetic (oracle_vnni.c, bit-identical; bench.py's CPU arm)."""
     x = np.ascontiguousarray(x)
     n, h, w, c = x.shape
     if global_pooling:
@@ -394,6 +425,9 @@ def pool_s8_nhwc(x, window, pad, stride, ptype, global_pooling=False, floor_as_c
     if use_ref:
         ref_lib().ref_pool_basic_check_int8(_p(x), _p(out), uns, n, c, h, w, oh, ow, window[1],
                                             window[0], stride[1], stride[0], pad[1], pad[0], int(ptype))
+    elif fast and vnni_available():
+        lib().oracle_pool_s8_nhwc_fast(_p(x), _p(out), uns, n, c, h, w, oh, ow, window[0], window[1],
+                                       pad[0], pad[1], stride[0], stride[1], int(ptype))
     else:
         lib().oracle_pool_s8_nhwc(_p(x), _p(out), uns, n, c, h, w, oh, ow, window[0], window[1],
                                   pad[0], pad[1], stride[0], stride[1], int(ptype))

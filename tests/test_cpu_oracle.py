@@ -282,6 +282,24 @@ def test_model_walker_reproduces_golden(model, oracle):
     assert (got.argmax(1) == gold["top1_int8"][:n]).all()
 
 
+@pytest.mark.parametrize("model", ["tiny_resnet", "tiny_mobilenet", "resnet50"])
+def test_baseline_arm_walker_equals_the_scalar_walker(model, oracle):
+    """bench.py's CPU arm (run_int8(fast=True, weight_cache=...): VNNI convolutions with cached weight packs, AVX-512
+    pooling) gives the golden outputs, on the first call (cache being filled) and on a second one (cache reused)."""
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    gold = np.load(os.path.join(GOLD, "%s_golden.npz" % model))
+    n = 2
+    g = modelzoo.build(model, batch=1)
+    x = modelzoo.synthetic_input(n, 32 if model.startswith("tiny") else 224)
+    scales = {k: float(np.float32(v)) for k, v in modelzoo.load_calibration(model).items()}
+    cache = {}
+    for _ in range(2):
+        got = W.run_int8(g, x, scales, fast=True, weight_cache=cache)["prob_out"]
+        np.testing.assert_array_equal(got, gold["prob_int8"][:n])
+    assert cache
+
+
 def test_softmax_eltwise_activation_oracles(oracle):
     rng = np.random.default_rng(2)
     x = rng.uniform(-5, 5, (4, 10)).astype(np.float32)
@@ -369,6 +387,24 @@ def test_grouped_x86_int8_conv_agrees_with_reference_oracle_on_shared_subset(ora
     np.testing.assert_array_equal(out, a)
 
 
+def test_fast_int8_pooling_is_bit_identical_to_the_scalar_restatement(oracle):
+    """oracle_pool_s8_nhwc_fast (the CPU-baseline arm's AVX-512 pooling) == oracle_pool_s8_nhwc: max / avg incl. / avg excl.
+    padding, s8 and u8 codes, padded and ceil-mode windows, global pooling, channel counts off the vector widths."""
+    if not oracle.vnni_available():
+        pytest.skip("no AVX-512 on this CPU")
+    rng = np.random.default_rng(77)
+    for (n, h, w, c) in [(2, 13, 17, 64), (1, 12, 12, 100), (3, 7, 7, 2048), (1, 9, 5, 8)]:
+        for uns in (True, False):
+            x = rng.integers(0, 256, (n, h, w, c)).astype(np.uint8) if uns else rng.integers(-128, 128, (n, h, w, c)).astype(np.int8)
+            for ptype in (1, 2, 3):
+                for window, pad, stride, glob in (((3, 3), (0, 0), (2, 2), False), ((3, 3), (1, 1), (2, 2), False),
+                                                  ((2, 2), (0, 0), (2, 2), False), ((3, 2), (1, 0), (1, 2), False),
+                                                  ((7, 7), (0, 0), (1, 1), True)):
+                    a = oracle.pool_s8_nhwc(x, window, pad, stride, ptype, global_pooling=glob, fast=True)
+                    b = oracle.pool_s8_nhwc(x, window, pad, stride, ptype, global_pooling=glob)
+                    np.testing.assert_array_equal(a, b, err_msg=str((n, h, w, c, uns, ptype, window, pad, stride, glob)))
+
+
 def test_vnni_int8_conv_is_bit_identical_to_the_scalar_restatement(oracle):
     """oracle_vnni.c (the CPU-baseline arm's AVX-512 VNNI convolution) == oracle_conv_s8_nhwc_x86 on every dtype pair,
     with / without residual, signed and unsigned inputs, channel counts that need padding, ragged tiles. Skipped where
@@ -390,3 +426,23 @@ def test_vnni_int8_conv_is_bit_identical_to_the_scalar_restatement(oracle):
                 kw = dict(residual=rs, sum_scale=0.37, out_dtype=od, stride=(st, st), pad=(pad, pad), relu=od != oracle.DT_INT8)
                 np.testing.assert_array_equal(oracle.conv_s8_nhwc_x86(x, w, b, sc, fast=True, **kw),
                                               oracle.conv_s8_nhwc_x86(x, w, b, sc, **kw), err_msg=str((n, h, c, k, r, od)))
+    # residual dtypes (s8, fp32), sum_scale == 1 (plain add instead of the fma), dilation, fewer pixels than one register tile,
+    # fewer output channels than one vector, the inner product as a 1x1 conv, no bias / no scale tables, relu into s8
+    for (n, h, wd, c, k, r, st, pad, dil, res_dt, ss) in [(1, 3, 4, 8, 10, 1, 1, 0, 1, np.int8, 1.0), (2, 11, 13, 12, 33, 3, 1, 2, 2, np.float32, 1.0),
+                                                          (8, 1, 1, 2048, 1000, 1, 1, 0, 1, None, 1.0), (3, 8, 5, 32, 48, 3, 2, 1, 1, np.int8, 0.61)]:
+        x = rng.integers(0, 256, (n, h, wd, c)).astype(np.uint8)
+        w = rng.integers(-127, 128, (k, c, r, r)).astype(np.int8)
+        oh, ow = oracle.conv_out_size(h, pad, dil, r, st), oracle.conv_out_size(wd, pad, dil, r, st)
+        res = None
+        if res_dt is np.int8:
+            res = rng.integers(-128, 128, (n, oh, ow, k)).astype(np.int8)
+        elif res_dt is np.float32:
+            res = rng.uniform(-50, 50, (n, oh, ow, k)).astype(np.float32)
+        sc = rng.uniform(0.5, 1.5, k).astype(np.float32) * np.float32(1e-3)
+        for od, bias, scale, relu in ((oracle.DT_INT8, None, sc, True), (oracle.DT_UINT8, rng.uniform(-900, 900, k).astype(np.float32), sc, False),
+                                      (oracle.DT_FLOAT, None, None, False)):
+            kw = dict(residual=res, sum_scale=ss, out_dtype=od, stride=(st, st), pad=(pad, pad), dil=(dil, dil), relu=relu)
+            np.testing.assert_array_equal(oracle.conv_s8_nhwc_x86(x, w, bias, scale, fast=True, **kw),
+                                          oracle.conv_s8_nhwc_x86(x, w, bias, scale, **kw), err_msg=str((n, h, wd, c, k, r, od)))
+    # the pack of a weight array is made once and reused
+    assert oracle._vnni_pack(w)[0].value == oracle._vnni_pack(w)[0].value
