@@ -142,12 +142,13 @@ def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, 
     # (oracle/oracle_vnni.c: bit-identical to the scalar restatement, ~10x faster)
     vnni = precision == "int8" and O.vnni_available()
     wcache = {}
-    run = (lambda: W.run_int8(g, x, scales, fast=True, weight_cache=wcache)) if precision == "int8" else (lambda: W.run_fp32(g, x))
-    if precision == "int8":
-        run()      # fills the cache: BN fold + weight quantisation are init-time work (Net::init), not timed
+    avx512 = O.vnni_available()
+    run = (lambda: W.run_int8(g, x, scales, fast=True, weight_cache=wcache)) if precision == "int8" else \
+        (lambda: W.run_fp32(g, x, fast=avx512, weight_cache=wcache))
+    run()      # fills the cache: BN fold, weight quantisation and packing are init-time work (Net::init), not timed
     for _ in range(warmup):
         run()
-    if auto_steps and precision == "int8":
+    if auto_steps:
         # one warm step sizes the sample: about a quarter of the budget, between 3 and 200 steps
         t0 = time.perf_counter()
         run()
@@ -159,7 +160,8 @@ def cpu_oracle_images_per_s(model, precision, batch, budget_s=20.0, steps=None, 
     return {"value": n_img * steps / dt, "unit": "images/s", "cores": O.num_threads(), "kind": "port",
             "sample": "%d step(s) x %d image(s) of %s %s via oracle/model_walker.py (x86-semantics restatement, %s"
                       "OpenMP, not Anakin's MKL/xbyak build)" % (steps, n_img, model, precision,
-                                                                  "AVX-512 VNNI convolutions on weights packed once, AVX-512 pooling, " if vnni else ""),
+                                                                  "AVX-512 VNNI convolutions on weights packed once, AVX-512 pooling, " if vnni else
+                                                                  ("AVX-512 FMA convolutions on weights packed once, " if avx512 else "")),
             "ms_per_step": dt / steps * 1e3, "images_per_step": n_img}
 
 

@@ -156,10 +156,12 @@ def _conv_kw(a):
     return dict(stride=tuple(a["strides"]), pad=tuple(a["padding"]), dil=tuple(a["dilation_rate"]))
 
 
-def run_fp32(graph, x_nchw, collect_absmax=False, return_values=False):
+def run_fp32(graph, x_nchw, collect_absmax=False, return_values=False, fast=False, weight_cache=None):
     """FP32 forward (NHWC internally). Returns {output_name: ndarray}, and with collect_absmax
     also {node_name: max|x|} of every node's output (for max-abs calibration,
-    CalibrationAlgoType::MAXABS, saber/saber_types.h:357-360)."""
+    CalibrationAlgoType::MAXABS, saber/saber_types.h:357-360).
+    fast / weight_cache (bench.py's CPU arm): AVX-512 convolutions and inner products (equal up to float re-association), the
+    BN/Scale fold and the weight packs kept between calls (init-time work in the reference: Net::init)."""
     groups = plan(graph)
     vals = {}
     absmax = {}
@@ -181,11 +183,16 @@ def run_fp32(graph, x_nchw, collect_absmax=False, return_values=False):
         elif g.kind == "split":
             put(g, vals[g.inputs[0]])
         elif g.kind == "conv":
-            w, bias = _folded_conv_weights(g)
+            cached = weight_cache.get(g.head["name"]) if weight_cache is not None else None
+            if cached is None:
+                cached = _folded_conv_weights(g)
+                if weight_cache is not None:
+                    weight_cache[g.head["name"]] = cached
+            w, bias = cached
             res = vals[g.residual] if g.elt is not None else None
             src = vals[[b for b in g.inputs][0]]
             y = O.conv_f32_nhwc(src, w, bias, residual=res, group=int(a["group"]), relu=g.relu,
-                                neg_slope=g.relu_alpha, beta=1.0, **_conv_kw(a))
+                                neg_slope=g.relu_alpha, beta=1.0, fast=fast, **_conv_kw(a))
             put(g, y)
         elif g.kind == "eltwise":
             op = {"Add": 2, "Mul": 1, "Prod": 1, "Max": 3}[a["type"]]
@@ -205,11 +212,22 @@ def run_fp32(graph, x_nchw, collect_absmax=False, return_values=False):
             if x.ndim == 4:  # Dense flattens in NCHW order (saber_fc.cu:27-35)
                 x = np.transpose(x, (0, 3, 1, 2))
             x = np.ascontiguousarray(x).reshape(x.shape[0], -1)
-            w = _attr_tensor(a["weight_1"]).reshape(int(a["out_dim"]), -1)
-            b = _attr_tensor(a["weight_2"]).reshape(-1) if a.get("bias_term") else None
-            y = O.fc_f32(x, w, b)
-            if g.relu:
-                y = O.activation_f32(y, 2, g.relu_alpha)
+            if fast and weight_cache is not None:
+                # the inner product as a 1x1 convolution over [m, 1, 1, K] through the packed AVX-512 path
+                cached = weight_cache.get(g.head["name"])
+                if cached is None:
+                    w = np.ascontiguousarray(_attr_tensor(a["weight_1"]).reshape(int(a["out_dim"]), -1, 1, 1), np.float32)
+                    b = _attr_tensor(a["weight_2"]).reshape(-1) if a.get("bias_term") else None
+                    cached = weight_cache[g.head["name"]] = (w, b)
+                w, b = cached
+                y = O.conv_f32_nhwc(x.reshape(x.shape[0], 1, 1, -1), w, b, relu=bool(g.relu), neg_slope=g.relu_alpha,
+                                    fast=True).reshape(x.shape[0], -1)
+            else:
+                w = _attr_tensor(a["weight_1"]).reshape(int(a["out_dim"]), -1)
+                b = _attr_tensor(a["weight_2"]).reshape(-1) if a.get("bias_term") else None
+                y = O.fc_f32(x, w, b)
+                if g.relu:
+                    y = O.activation_f32(y, 2, g.relu_alpha)
             put(g, y.reshape(y.shape[0], 1, 1, -1))
         elif g.kind == "softmax":
             x = vals[g.inputs[0]]

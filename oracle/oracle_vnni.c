@@ -284,3 +284,122 @@ ORACLE_API void oracle_pool_s8_nhwc_fast(const void* src, void* dst, int is_unsi
         }
     }
 }
+
+/* ------------------------------------------------------------------ fp32 convolution for the baseline arm
+ * oracle_conv_f32_nhwc (oracle.c; group == 1) with AVX-512: the same sums -- residual * beta, the taps in (kh, kw, ic)
+ * order, bias, relu(neg_slope) -- with one fused multiply-add per product instead of the scalar code's separately rounded
+ * multiply and its width-dependent `omp simd` reduction tree. The two differ by float re-association / contraction only
+ * (tests/test_cpu_oracle.py bounds the difference with the reference's tensor_cmp criterion at 1e-5); goldens and parity
+ * tests keep using oracle.c, this one is timed. Weights packed once per layer into [k / 32][tap][c][32]. */
+typedef struct {
+    int k, c, kh, kw, kblocks, taps;
+    float* wp;          /* [kblocks][taps][c][KB] */
+} f32_pack_t;
+
+ORACLE_API void* oracle_f32_pack(const float* weights, int k, int c, int kernel_h, int kernel_w) {
+    if (!oracle_vnni_available()) return NULL;
+    f32_pack_t* pk = (f32_pack_t*)calloc(1, sizeof(f32_pack_t));
+    pk->k = k; pk->c = c; pk->kh = kernel_h; pk->kw = kernel_w;
+    pk->taps = kernel_h * kernel_w; pk->kblocks = (k + KB - 1) / KB;
+    const size_t elems = (size_t)pk->kblocks * pk->taps * c * KB;
+    pk->wp = (float*)aligned_alloc(64, elems * sizeof(float));
+    memset(pk->wp, 0, elems * sizeof(float));
+    const int taps = pk->taps;
+#pragma omp parallel for schedule(static)
+    for (int oc = 0; oc < k; ++oc) {
+        const int kb = oc / KB, j = oc % KB;
+        for (int ic = 0; ic < c; ++ic)
+            for (int t = 0; t < taps; ++t)
+                pk->wp[(((size_t)kb * taps + t) * c + ic) * KB + j] = weights[((size_t)oc * c + ic) * taps + t];
+    }
+    return pk;
+}
+
+ORACLE_API void oracle_f32_free(void* p) {
+    f32_pack_t* pk = (f32_pack_t*)p;
+    if (!pk) return;
+    free(pk->wp);
+    free(pk);
+}
+
+ORACLE_API int oracle_conv_f32_nhwc_packed(const void* packed, const float* src, const float* bias, const float* residual,
+                                           float* dst, int n, int c, int h, int w, int k, int kernel_h, int kernel_w,
+                                           int stride_h, int stride_w, int dil_h, int dil_w, int pad_h, int pad_w,
+                                           int flag_bias, int flag_relu, float neg_slope, float beta) {
+    const f32_pack_t* pk = (const f32_pack_t*)packed;
+    if (!pk || pk->k != k || pk->c != c || pk->kh != kernel_h || pk->kw != kernel_w) return 1;
+    const int out_h = (h + 2 * pad_h - (dil_h * (kernel_h - 1) + 1)) / stride_h + 1;
+    const int out_w = (w + 2 * pad_w - (dil_w * (kernel_w - 1) + 1)) / stride_w + 1;
+    const int taps = pk->taps, kblocks = pk->kblocks, kpad = kblocks * KB;
+    float* tb = (float*)aligned_alloc(64, (size_t)kpad * sizeof(float));
+    for (int i = 0; i < kpad; ++i) tb[i] = (flag_bias && bias && i < k) ? bias[i] : 0.f;
+    float* zpix = (float*)aligned_alloc(64, ((size_t)c * sizeof(float) + 63) / 64 * 64);
+    memset(zpix, 0, ((size_t)c * sizeof(float) + 63) / 64 * 64);
+    const long long M = (long long)n * out_h * out_w;
+    const long long mtiles = (M + PT - 1) / PT;
+    const __m512 vbeta = _mm512_set1_ps(beta), vslope = _mm512_set1_ps(neg_slope), zero = _mm512_setzero_ps();
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
+    for (int kb = 0; kb < kblocks; ++kb) {
+        for (long long mt = 0; mt < mtiles; ++mt) {
+            const long long m0 = mt * PT;
+            const int np = (int)(M - m0 < PT ? M - m0 : PT);
+            const int oc0 = kb * KB;
+            const int left = k - oc0;
+            const __mmask16 l0 = left >= 16 ? (__mmask16)0xFFFF : (__mmask16)((1u << left) - 1u);
+            const __mmask16 l1 = left >= 32 ? (__mmask16)0xFFFF : (left > 16 ? (__mmask16)((1u << (left - 16)) - 1u) : (__mmask16)0);
+            int pn[PT], poh[PT], pow_[PT];
+            __m512 acc[PT][2];
+            for (int p = 0; p < PT; ++p) {
+                const long long m = m0 + (p < np ? p : 0);
+                pn[p] = (int)(m / ((long long)out_h * out_w));
+                const int rem = (int)(m - (long long)pn[p] * out_h * out_w);
+                poh[p] = rem / out_w;
+                pow_[p] = rem - poh[p] * out_w;
+                if (residual && p < np) {
+                    const float* rp = residual + (size_t)m * k + oc0;
+                    acc[p][0] = _mm512_mul_ps(_mm512_maskz_loadu_ps(l0, rp), vbeta);
+                    acc[p][1] = _mm512_mul_ps(_mm512_maskz_loadu_ps(l1, rp + 16), vbeta);
+                } else {
+                    acc[p][0] = acc[p][1] = zero;
+                }
+            }
+            const float* wkb = pk->wp + (size_t)kb * taps * c * KB;
+            for (int kh = 0; kh < kernel_h; ++kh) {
+                for (int kw = 0; kw < kernel_w; ++kw) {
+                    const float* px[PT];
+                    for (int p = 0; p < PT; ++p) {
+                        const int ih = poh[p] * stride_h - pad_h + kh * dil_h;
+                        const int iw = pow_[p] * stride_w - pad_w + kw * dil_w;
+                        const int ok = p < np && ih >= 0 && ih < h && iw >= 0 && iw < w;
+                        px[p] = ok ? src + (((size_t)pn[p] * h + ih) * w + iw) * c : zpix;
+                    }
+                    const float* wt_p = wkb + (size_t)(kh * kernel_w + kw) * c * KB;
+                    for (int ic = 0; ic < c; ++ic) {
+                        const __m512 w0 = _mm512_load_ps(wt_p + (size_t)ic * KB);
+                        const __m512 w1 = _mm512_load_ps(wt_p + (size_t)ic * KB + 16);
+#pragma GCC unroll 14
+                        for (int p = 0; p < PT; ++p) {
+                            const __m512 a = _mm512_set1_ps(px[p][ic]);
+                            acc[p][0] = _mm512_fmadd_ps(a, w0, acc[p][0]);
+                            acc[p][1] = _mm512_fmadd_ps(a, w1, acc[p][1]);
+                        }
+                    }
+                }
+            }
+            const __m512 b0 = _mm512_load_ps(tb + oc0), b1 = _mm512_load_ps(tb + oc0 + 16);
+            for (int p = 0; p < np; ++p) {
+                float* op = dst + (size_t)(m0 + p) * k + oc0;
+                __m512 f0 = _mm512_add_ps(acc[p][0], b0), f1 = _mm512_add_ps(acc[p][1], b1);
+                if (flag_relu) {
+                    f0 = _mm512_mask_mul_ps(f0, _mm512_cmp_ps_mask(f0, zero, _CMP_LE_OQ), f0, vslope);   /* acc > 0 ? acc : acc * slope */
+                    f1 = _mm512_mask_mul_ps(f1, _mm512_cmp_ps_mask(f1, zero, _CMP_LE_OQ), f1, vslope);
+                }
+                _mm512_mask_storeu_ps(op, l0, f0);
+                if (l1) _mm512_mask_storeu_ps(op + 16, l1, f1);
+            }
+        }
+    }
+    free(tb);
+    free(zpix);
+    return 0;
+}

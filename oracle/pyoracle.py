@@ -113,8 +113,34 @@ def conv_f32_nchw(x, w, bias, group=1, stride=(1, 1), dil=(1, 1), pad=(0, 0), re
     return out
 
 
+_F32_PACKS = {}    # id(weight array) -> (the array, pack handle)
+
+
+def _f32_pack(w):
+    ent = _F32_PACKS.get(id(w))
+    if ent is not None and ent[0] is w:
+        return ent[1]
+    if len(_F32_PACKS) >= 512:
+        f32_release()
+    k, c, r, s = w.shape
+    lib().oracle_f32_pack.restype = C.c_void_p
+    handle = C.c_void_p(lib().oracle_f32_pack(_p(w), k, c, r, s))
+    assert handle.value, "oracle_f32_pack failed"
+    _F32_PACKS[id(w)] = (w, handle)
+    return handle
+
+
+def f32_release():
+    for _, handle in _F32_PACKS.values():
+        lib().oracle_f32_free(handle)
+    _F32_PACKS.clear()
+
+
 def conv_f32_nhwc(x, w, bias, residual=None, group=1, stride=(1, 1), dil=(1, 1), pad=(0, 0),
-                  relu=False, neg_slope=0.0, beta=1.0):
+                  relu=False, neg_slope=0.0, beta=1.0, fast=False):
+    """fast=True (bench.py's CPU arm only): the AVX-512 implementation in oracle_vnni.c -- same sums with fused multiply-adds,
+    equal to the scalar restatement up to float re-association (not bit-identical: goldens and parity tests use the default).
+    The weight pack is cached per weight ARRAY."""
     x = np.ascontiguousarray(x, np.float32)
     w = np.ascontiguousarray(w, np.float32)
     n, h, wd, c = x.shape
@@ -124,6 +150,12 @@ def conv_f32_nhwc(x, w, bias, residual=None, group=1, stride=(1, 1), dil=(1, 1),
     out = np.zeros((n, oh, ow, k), np.float32)
     b = None if bias is None else np.ascontiguousarray(bias, np.float32)
     res = None if residual is None else np.ascontiguousarray(residual, np.float32)
+    if fast and group == 1 and vnni_available():
+        rc = lib().oracle_conv_f32_nhwc_packed(_f32_pack(w), _p(x), _p(b), _p(res), _p(out), n, c, h, wd, k, r, s,
+                                               stride[0], stride[1], dil[0], dil[1], pad[0], pad[1],
+                                               int(b is not None), int(relu), _f(neg_slope), _f(beta))
+        if rc == 0:
+            return out
     lib().oracle_conv_f32_nhwc(_p(x), _p(w), _p(b), _p(res), _p(out), n, c, h, wd, k, group, r, s,
                                stride[0], stride[1], dil[0], dil[1], pad[0], pad[1],
                                int(b is not None), int(relu), _f(neg_slope), _f(beta))

@@ -387,6 +387,37 @@ def test_grouped_x86_int8_conv_agrees_with_reference_oracle_on_shared_subset(ora
     np.testing.assert_array_equal(out, a)
 
 
+def test_fast_fp32_conv_equals_the_scalar_restatement_up_to_reassociation(oracle):
+    """oracle_conv_f32_nhwc_packed (the CPU-baseline arm's AVX-512 fp32 convolution: same sums, fused multiply-adds) against
+    oracle_conv_f32_nhwc with the reference's own criterion (tensor_cmp_host) at 1e-5 -- 100x tighter than the 1e-3 the parity
+    tests apply to the GPU path; and the walker on top of it against the committed fp32 goldens."""
+    if not oracle.vnni_available():
+        pytest.skip("no AVX-512 on this CPU")
+    rng = np.random.default_rng(5)
+    for (n, h, w, c, k, r, st, pad, dil) in [(2, 14, 14, 64, 72, 3, 1, 1, 1), (1, 9, 11, 16, 40, 3, 2, 1, 2), (3, 7, 7, 128, 130, 1, 1, 0, 1),
+                                             (1, 20, 20, 3, 64, 7, 2, 3, 1), (4, 1, 1, 512, 100, 1, 1, 0, 1), (1, 5, 5, 8, 10, 3, 1, 1, 1)]:
+        x = rng.uniform(-1, 1, (n, h, w, c)).astype(np.float32)
+        wt = (rng.standard_normal((k, c, r, r)) * np.sqrt(2.0 / (c * r * r))).astype(np.float32)
+        b = rng.uniform(-0.5, 0.5, k).astype(np.float32)
+        oh, ow = oracle.conv_out_size(h, pad, dil, r, st), oracle.conv_out_size(w, pad, dil, r, st)
+        res = rng.uniform(-1, 1, (n, oh, ow, k)).astype(np.float32)
+        for rs, bias, relu in ((None, b, True), (res, b, True), (res, None, False)):
+            kw = dict(residual=rs, stride=(st, st), pad=(pad, pad), dil=(dil, dil), relu=relu, neg_slope=0.1, beta=1.0)
+            want = oracle.conv_f32_nhwc(x, wt, bias, **kw)
+            got = oracle.conv_f32_nhwc(x, wt, bias, fast=True, **kw)
+            mr, md = oracle.tensor_cmp(want, got)
+            assert md < 1e-5 or mr <= 1e-5, ((n, h, w, c, k, r), mr, md)
+    from anakin_b200 import modelzoo
+    from oracle import model_walker as W
+    gold = np.load(os.path.join(GOLD, "tiny_resnet_golden.npz"))
+    g = modelzoo.build("tiny_resnet", batch=1)
+    cache = {}
+    for _ in range(2):
+        _, vals = W.run_fp32(g, modelzoo.synthetic_input(4, 32), return_values=True, fast=True, weight_cache=cache)
+        mr, md = oracle.tensor_cmp(gold["logits_fp32"][:4], vals["fc"].reshape(4, -1))
+        assert md < 1e-4 or mr <= 1e-4, (mr, md)
+
+
 def test_fast_int8_pooling_is_bit_identical_to_the_scalar_restatement(oracle):
     """oracle_pool_s8_nhwc_fast (the CPU-baseline arm's AVX-512 pooling) == oracle_pool_s8_nhwc: max / avg incl. / avg excl.
     padding, s8 and u8 codes, padded and ceil-mode windows, global pooling, channel counts off the vector widths."""
